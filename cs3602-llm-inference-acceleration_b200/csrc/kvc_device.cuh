@@ -1,0 +1,299 @@
+// kvc_device.cuh — device-side building blocks of the sm_100a KV-compression path.
+//
+//   K1  row_sumsq / group_sum     128-bit coalesced loads of key rows, fp32 sum of squares,
+//                                 warp-shuffle reduction over the lanes that share a row
+//                                 (replaces torch.norm(K, p=2, dim=-1), e.g. l2_compress.py:70)
+//   K2  block_radix_select        per-(b,h) radix select in shared memory: 12-bit histogram
+//                                 fused into the scan, then refinement passes over the
+//                                 on-chip keys; ties go to the lowest token index; indices
+//                                 are emitted already ascending (replaces argsort + [:k] +
+//                                 torch.sort, e.g. h2o_l2.py:128-132, and topk + sort,
+//                                 snapkv_lite.py:134-137)
+//   K3  gather loop               row-granular 16-byte-chunk gather of K and V straight into
+//                                 the compacted output (replaces expand + gather x2 + cat x2,
+//                                 e.g. fix_size_l2.py:132-147)
+//
+// Everything here is HBM-bound byte/compare work: no tensor cores on purpose.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kvc.h"
+
+namespace kvc {
+
+constexpr int kHistBits = 12;
+constexpr int kHistBins = 1 << kHistBits;  // 4096 bins * 4 B = 16 KB
+constexpr int kMiscInts = 128;             // 512 B of per-CTA scalars / per-warp counters
+constexpr int kMaxPoolHalo = 32;           // pooling_kernel <= 64
+
+// misc[] slots
+constexpr int kMiscBin = 0;     // find_bin result: bin
+constexpr int kMiscBelow = 1;   // find_bin result: count strictly below bin
+constexpr int kMiscMaxRaw = 2;  // snapkv: max norm (raw dtype bits, positive => integer order)
+constexpr int kMiscWarpA = 32;  // 32 ints: per-warp counter A (scan totals / lt counts)
+constexpr int kMiscWarpB = 64;  // 32 ints: per-warp counter B (eq counts)
+constexpr int kMiscHalo = 96;   // 32 ints: snapkv pooling halo (raw norms of the previous tile's tail)
+
+// ---------------------------------------------------------------- dtype traits
+template <int DT>
+struct Traits;
+template <>
+struct Traits<KVC_DTYPE_F32> {
+    using Key = uint32_t;
+    static constexpr int kElemBytes = 4;
+    static constexpr int kKeyBits = 32;
+    __device__ static __forceinline__ uint32_t to_raw(float x) { return __float_as_uint(x); }
+    __device__ static __forceinline__ float from_raw(uint32_t r) { return __uint_as_float(r); }
+    __device__ static __forceinline__ float sumsq(int4 v, float acc) {
+        float a = __int_as_float(v.x), b = __int_as_float(v.y), c = __int_as_float(v.z), d = __int_as_float(v.w);
+        acc = fmaf(a, a, acc);
+        acc = fmaf(b, b, acc);
+        acc = fmaf(c, c, acc);
+        acc = fmaf(d, d, acc);
+        return acc;
+    }
+};
+template <>
+struct Traits<KVC_DTYPE_BF16> {
+    using Key = uint16_t;
+    static constexpr int kElemBytes = 2;
+    static constexpr int kKeyBits = 16;
+    __device__ static __forceinline__ uint32_t to_raw(float x) {
+        return (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(x));
+    }
+    __device__ static __forceinline__ float from_raw(uint32_t r) { return __uint_as_float(r << 16); }
+    __device__ static __forceinline__ float sumsq(int4 v, float acc) {
+        const uint32_t w[4] = {(uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float lo = __uint_as_float(w[i] << 16);
+            float hi = __uint_as_float(w[i] & 0xffff0000u);
+            acc = fmaf(lo, lo, acc);
+            acc = fmaf(hi, hi, acc);
+        }
+        return acc;
+    }
+};
+template <>
+struct Traits<KVC_DTYPE_F16> {
+    using Key = uint16_t;
+    static constexpr int kElemBytes = 2;
+    static constexpr int kKeyBits = 16;
+    __device__ static __forceinline__ uint32_t to_raw(float x) {
+        return (uint32_t)__half_as_ushort(__float2half_rn(x));
+    }
+    __device__ static __forceinline__ float from_raw(uint32_t r) {
+        return __half2float(__ushort_as_half((unsigned short)r));
+    }
+    __device__ static __forceinline__ float sumsq(int4 v, float acc) {
+        const uint32_t w[4] = {(uint32_t)v.x, (uint32_t)v.y, (uint32_t)v.z, (uint32_t)v.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float lo = __half2float(__ushort_as_half((unsigned short)(w[i] & 0xffffu)));
+            float hi = __half2float(__ushort_as_half((unsigned short)(w[i] >> 16)));
+            acc = fmaf(lo, lo, acc);
+            acc = fmaf(hi, hi, acc);
+        }
+        return acc;
+    }
+};
+
+// Round an fp32 value to the storage dtype and back (what a torch op on that dtype returns).
+template <int DT>
+__device__ __forceinline__ float round_dt(float x) {
+    return Traits<DT>::from_raw(Traits<DT>::to_raw(x));
+}
+
+// IEEE bits -> unsigned key whose integer order equals the float order (-x < +x, +NaN last).
+template <typename Key>
+__device__ __forceinline__ Key ordered_key(uint32_t raw, bool descending) {
+    constexpr int kBits = sizeof(Key) * 8;
+    const uint32_t sign = (raw >> (kBits - 1)) & 1u;
+    uint32_t k = sign ? ~raw : (raw | (1u << (kBits - 1)));
+    if (descending) k = ~k;
+    return (Key)k;
+}
+
+// ---------------------------------------------------------------- memory helpers
+__device__ __forceinline__ int4 ldg128_stream(const void* p) {
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stg128_stream(void* p, int4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w)
+                 : "memory");
+}
+
+// ---------------------------------------------------------------- K1: lane-group reduction
+// Sum `v` over groups of N consecutive lanes (group g = lanes [g*N, g*N+N)); the result is
+// valid in the first lane of each group.  The summation order is fixed, so a row's norm does
+// not depend on where in the warp the row was processed.
+template <int N>
+__device__ __forceinline__ float group_sum(float v) {
+    if constexpr (N == 1) {
+        return v;
+    } else if constexpr ((N & (N - 1)) == 0) {
+#pragma unroll
+        for (int o = N / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        return v;
+    } else if constexpr (N % 2 == 0) {
+        v += __shfl_down_sync(0xffffffffu, v, N / 2);
+        return group_sum<N / 2>(v);  // first N/2 lanes of the group now hold pair sums
+    } else {
+        float t = v;
+#pragma unroll
+        for (int j = 1; j < N; ++j) t += __shfl_down_sync(0xffffffffu, v, j);
+        return t;
+    }
+}
+// Runtime power-of-two group width (generic head_dim path).
+__device__ __forceinline__ float group_sum_pow2(float v, int n) {
+    for (int o = n >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------- K2: block radix select
+// Exclusive block scan over the histogram to find the bin holding the k-th smallest key
+// (1-based k).  Writes misc[kMiscBin], misc[kMiscBelow]; ends with __syncthreads().
+template <int NT>
+__device__ __forceinline__ void find_bin(const uint32_t* hist, int nbins, uint32_t k, int32_t* misc) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (nbins + NT - 1) / NT;
+    const int b0 = tid * per;
+    uint32_t loc = 0;
+    if ((per & 3) == 0) {
+        for (int i = 0; i < per; i += 4) {
+            if (b0 + i < nbins) {
+                uint4 h = *reinterpret_cast<const uint4*>(hist + b0 + i);
+                loc += h.x + h.y + h.z + h.w;
+            }
+        }
+    } else {
+        for (int i = 0; i < per; ++i)
+            if (b0 + i < nbins) loc += hist[b0 + i];
+    }
+    uint32_t inc = loc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) misc[kMiscWarpA + warp] = (int32_t)inc;
+    __syncthreads();
+    uint32_t wbase = 0;
+    for (int w = 0; w < warp; ++w) wbase += (uint32_t)misc[kMiscWarpA + w];
+    const uint32_t excl = wbase + inc - loc;
+    if (excl < k && k <= excl + loc) {  // exactly one thread
+        uint32_t c = excl;
+        for (int i = 0; i < per; ++i) {
+            const uint32_t h = hist[b0 + i];
+            if (c + h >= k) {
+                misc[kMiscBin] = b0 + i;
+                misc[kMiscBelow] = (int32_t)c;
+                break;
+            }
+            c += h;
+        }
+    }
+    __syncthreads();
+}
+
+// Select the k (1 <= k <= R) smallest keys of keys[0..R) (ties -> lowest index) and write
+// their positions, ascending, as base + position into out_idx[0..k).
+// Precondition: hist[] already holds the histogram of (key >> (KeyBits-12)) over all R keys
+// (it is accumulated while the keys are produced), and a __syncthreads() has made keys/hist
+// visible.  All NT threads must call.  Ends with __syncthreads().
+template <typename Key, int NT>
+__device__ __forceinline__ void block_radix_select(const Key* __restrict__ keys, int R, int k, uint32_t* hist,
+                                                   int32_t* misc, int32_t* out_idx, int base) {
+    constexpr int kBits = sizeof(Key) * 8;
+    constexpr int kVec = 16 / sizeof(Key);  // keys per 128-bit shared load
+    constexpr int NW = NT / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    uint32_t prefix = 0;  // the high `pbits` bits of the k-th key found so far
+    int pbits = 0;
+    uint32_t krem = (uint32_t)k;
+    // level 0: the fused 12-bit histogram
+    find_bin<NT>(hist, kHistBins, krem, misc);
+    prefix = (uint32_t)misc[kMiscBin];
+    krem -= (uint32_t)misc[kMiscBelow];
+    pbits = kHistBits;
+    // refinement levels over the remaining low bits
+    while (pbits < kBits) {
+        const int nb = (kBits - pbits) > kHistBits ? kHistBits : (kBits - pbits);
+        const int shift = kBits - pbits - nb;
+        const int nbins = 1 << nb;
+        for (int i = tid; i < nbins; i += NT) hist[i] = 0;
+        __syncthreads();
+        const int nvec = (R + kVec - 1) / kVec;
+        for (int v = tid; v < nvec; v += NT) {
+            const int4 raw = *reinterpret_cast<const int4*>(keys + (size_t)v * kVec);
+            const Key* kk = reinterpret_cast<const Key*>(&raw);
+#pragma unroll
+            for (int e = 0; e < kVec; ++e) {
+                const uint32_t key = kk[e];
+                if (v * kVec + e < R && (key >> (shift + nb)) == prefix)
+                    atomicAdd(&hist[(key >> shift) & (uint32_t)(nbins - 1)], 1u);
+            }
+        }
+        __syncthreads();
+        find_bin<NT>(hist, nbins, krem, misc);
+        prefix = (prefix << nb) | (uint32_t)misc[kMiscBin];
+        krem -= (uint32_t)misc[kMiscBelow];
+        pbits += nb;
+    }
+    // prefix == T, the k-th smallest key; take every key < T and the first `krem` keys == T.
+    const uint32_t T = prefix;
+    const int r = (int)krem;
+    const int chunk = (((R + NW - 1) / NW) + 31) & ~31;  // tokens per warp, multiple of 32
+    const int w_lo = warp * chunk;
+    const int w_hi = min(R, w_lo + chunk);
+    int lt = 0, eq = 0;
+    for (int i = w_lo + lane; i < w_hi; i += 32) {
+        const uint32_t key = keys[i];
+        lt += key < T;
+        eq += key == T;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lt += __shfl_xor_sync(0xffffffffu, lt, o);
+        eq += __shfl_xor_sync(0xffffffffu, eq, o);
+    }
+    __syncthreads();  // find_bin readers of misc[kMiscWarpA..] are done
+    if (lane == 0) {
+        misc[kMiscWarpA + warp] = lt;
+        misc[kMiscWarpB + warp] = eq;
+    }
+    __syncthreads();
+    int eq_before = 0, out_pos = 0;
+    for (int w = 0; w < warp; ++w) {
+        const int e = misc[kMiscWarpB + w];
+        out_pos += misc[kMiscWarpA + w] + max(0, min(e, r - eq_before));
+        eq_before += e;
+    }
+    const uint32_t lane_lt = (1u << lane) - 1u;
+    for (int i0 = w_lo; i0 < w_hi; i0 += 32) {
+        const int i = i0 + lane;
+        const bool in = i < w_hi;
+        const uint32_t key = in ? (uint32_t)keys[i] : 0xffffffffu;
+        const bool is_lt = in && key < T;
+        const bool is_eq = in && key == T;
+        const uint32_t eqb = __ballot_sync(0xffffffffu, is_eq);
+        const bool take = is_lt || (is_eq && (eq_before + __popc(eqb & lane_lt)) < r);
+        const uint32_t tb = __ballot_sync(0xffffffffu, take);
+        if (take) out_idx[out_pos + __popc(tb & lane_lt)] = base + i;
+        eq_before += __popc(eqb);
+        out_pos += __popc(tb);
+    }
+    __syncthreads();
+}
+
+}  // namespace kvc

@@ -1,0 +1,603 @@
+// kvc_sm100a.cu — kernels + C ABI (include/kvc.h) of the B200 KV-cache compression path.
+//
+// One launch compresses every layer of a call: grid = (B*H, n_layers); one CTA owns one
+// (layer, batch, head) unit and runs
+//   scan   (K1) stream the K rows of the selection region once, fp32 sum of squares, round the
+//               norm to the cache dtype (torch.norm semantics), build the radix key in shared
+//               memory and its 12-bit histogram on the fly;
+//   select (K2) radix select over the on-chip keys, ties -> lowest index, ascending indices;
+//   gather (K3) copy sink rows + selected rows + tail rows of K and V into the dense output.
+// Several CTAs are resident per SM, so one unit's select overlaps its neighbours' HBM phases.
+// Algorithmic HBM bytes per unit: e*D*(R + 4*C)  (SURVEY.md §8d).
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "kvc_device.cuh"
+
+#define KVC_STR2(x) #x
+#define KVC_STR(x) KVC_STR2(x)
+
+namespace kvc {
+
+struct LayerDev {
+    const char* k_in;
+    const char* v_in;
+    char* k_out;
+    char* v_out;
+    int32_t* idx_out;
+    const int32_t* idx_in;
+    int64_t ksb, ksh, kss;  // BYTE strides of K (batch, head, row)
+    int64_t vsb, vsh, vss;  // BYTE strides of V
+    int32_t S, sink, lo, hi, ksel, tail, score, pool;
+};
+static_assert(sizeof(LayerDev) == 128, "LayerDev is passed by value in kernel params");
+
+struct BatchDev {
+    int32_t B, H;
+    int32_t idx_cap;   // ints reserved for the kept-index list in shared memory
+    int32_t cpr;       // 16-byte chunks per row (generic path reads it at run time)
+    int32_t lpr, cpl;  // generic path: lanes per row (power of two) and chunks per lane
+    int32_t pad0, pad1;
+    LayerDev layers[KVC_MAX_LAYERS_PER_LAUNCH];
+};
+
+constexpr int kSmemFixed = kHistBins * 4 + kMiscInts * 4;
+
+// ------------------------------------------------------------------ fused kernel
+// CPR > 0: compile-time chunks per row with LPR lanes per row (CPR % LPR == 0).
+// CPR == 0: generic path, runtime cpr / lpr (power of two) / cpl.
+template <int DT, int CPR, int LPR, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) kvc_fused_kernel(const __grid_constant__ BatchDev bd) {
+    using Tr = Traits<DT>;
+    using Key = typename Tr::Key;
+    constexpr int NW = NT / 32;
+    constexpr bool kGeneric = (CPR == 0);
+    constexpr int kShift0 = Tr::kKeyBits - kHistBits;
+
+    const LayerDev& L = bd.layers[blockIdx.y];
+    const int bh = blockIdx.x;
+    const int b = bh / bd.H, h = bh - b * bd.H;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint32_t* hist = reinterpret_cast<uint32_t*>(smem);
+    int32_t* misc = reinterpret_cast<int32_t*>(smem + kHistBins * 4);
+    int32_t* sidx = reinterpret_cast<int32_t*>(smem + kSmemFixed);
+    Key* keys = reinterpret_cast<Key*>(smem + kSmemFixed + (size_t)bd.idx_cap * 4);
+
+    const int cpr = kGeneric ? bd.cpr : CPR;
+    const int lpr = kGeneric ? bd.lpr : LPR;
+    const int cpl = kGeneric ? bd.cpl : (CPR / (LPR > 0 ? LPR : 1));
+    const int rpw = 32 / lpr;  // rows per warp step
+
+    const int R = L.hi - L.lo;
+    const int ksel = L.ksel;
+    const int score = L.score;
+    const char* kbase = L.k_in + (int64_t)b * L.ksb + (int64_t)h * L.ksh;
+    const char* vbase = L.v_in + (int64_t)b * L.vsb + (int64_t)h * L.vsh;
+
+    if (ksel > 0 && score == KVC_SCORE_GIVEN_INDEX) {
+        const int32_t* src = L.idx_in + (int64_t)bh * ksel;
+        for (int i = tid; i < ksel; i += NT) sidx[i] = src[i];
+        __syncthreads();
+    } else if (ksel > 0) {
+        // ---------------------------------------------------------- K1: scan
+        for (int i = tid; i < kHistBins; i += NT) hist[i] = 0;
+        if (tid == 0) misc[kMiscMaxRaw] = 0;
+        __syncthreads();
+        const bool snap = (score == KVC_SCORE_SNAPKV_POOL);
+        const bool desc = (score == KVC_SCORE_L2_HIGH);
+        const int sub = lane % lpr, rw = lane / lpr;
+        const bool lane_ok = rw < rpw;
+        const char* rbase = kbase + (int64_t)L.lo * L.kss + (int64_t)sub * 16;
+        uint32_t local_max = 0;
+        if constexpr (!kGeneric) {
+            constexpr int CPL = CPR / LPR;
+            constexpr int U = (8 / CPL) > 0 ? (8 / CPL) : 1;
+            constexpr int RPW = 32 / LPR;
+            for (int base = 0; base < R; base += NW * RPW * U) {
+                int4 v[U][CPL];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int row = base + (u * NW + warp) * RPW + rw;
+                    const bool ok = lane_ok && row < R;
+                    const char* p = rbase + (int64_t)row * L.kss;
+#pragma unroll
+                    for (int c = 0; c < CPL; ++c)
+                        v[u][c] = ok ? ldg128_stream(p + c * (LPR * 16)) : make_int4(0, 0, 0, 0);
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int row = base + (u * NW + warp) * RPW + rw;
+                    float acc = 0.f;
+#pragma unroll
+                    for (int c = 0; c < CPL; ++c) acc = Tr::sumsq(v[u][c], acc);
+                    acc = group_sum<LPR>(acc);
+                    if (lane_ok && sub == 0 && row < R) {
+                        const uint32_t raw = Tr::to_raw(sqrtf(acc));
+                        if (snap) {
+                            keys[row] = (Key)raw;
+                            local_max = max(local_max, raw);
+                        } else {
+                            const Key key = ordered_key<Key>(raw, desc);
+                            keys[row] = key;
+                            atomicAdd(&hist[(uint32_t)key >> kShift0], 1u);
+                        }
+                    }
+                }
+            }
+        } else {
+            constexpr int U = 4;
+            for (int base = 0; base < R; base += NW * rpw * U) {
+                float acc[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int row = base + (u * NW + warp) * rpw + rw;
+                    const bool ok = lane_ok && row < R;
+                    const char* p = rbase + (int64_t)row * L.kss;
+                    acc[u] = 0.f;
+                    for (int c = 0; c < cpl; ++c) {
+                        const int4 x = ok ? ldg128_stream(p + (int64_t)c * lpr * 16) : make_int4(0, 0, 0, 0);
+                        acc[u] = Tr::sumsq(x, acc[u]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int row = base + (u * NW + warp) * rpw + rw;
+                    const float tot = group_sum_pow2(acc[u], lpr);
+                    if (lane_ok && sub == 0 && row < R) {
+                        const uint32_t raw = Tr::to_raw(sqrtf(tot));
+                        if (snap) {
+                            keys[row] = (Key)raw;
+                            local_max = max(local_max, raw);
+                        } else {
+                            const Key key = ordered_key<Key>(raw, desc);
+                            keys[row] = key;
+                            atomicAdd(&hist[(uint32_t)key >> kShift0], 1u);
+                        }
+                    }
+                }
+            }
+        }
+        if (snap) {
+            // norms are >= 0, so their raw bits order like unsigned integers
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
+            if (lane == 0) atomicMax(reinterpret_cast<uint32_t*>(&misc[kMiscMaxRaw]), local_max);
+        }
+        __syncthreads();
+
+        if (snap) {
+            // ------------------------------------------------------ snapkv score transform
+            // score_i = dt(dt(max + 1e-6) - norm_i); pooled_i = dt(fp32 left-to-right sum of the
+            // zero-padded window / kernel)  (snapkv_lite.py:96-121; avg_pool1d, count_include_pad).
+            // Done in place, tile by tile; the raw norms a later tile still needs from an
+            // already rewritten tile are parked in the halo.
+            const float mx = Tr::from_raw((uint32_t)misc[kMiscMaxRaw]);
+            const float mxe = round_dt<DT>(mx + 1e-6f);
+            const int pk = L.pool;
+            const bool pooling = pk > 1 && R >= pk;
+            const int pad = pooling ? pk / 2 : 0;
+            const float inv_den = (float)pk;
+            uint32_t* halo = reinterpret_cast<uint32_t*>(&misc[kMiscHalo]);
+            for (int t0 = 0; t0 < R; t0 += NT) {
+                const int i = t0 + tid;
+                uint32_t raw_i = 0;
+                float outv = 0.f;
+                if (i < R) {
+                    raw_i = (uint32_t)keys[i];
+                    if (pooling) {
+                        float acc = 0.f;
+                        for (int t = 0; t < pk; ++t) {
+                            const int j = i - pad + t;
+                            if (j >= 0 && j < R) {
+                                const uint32_t rj = (j < t0) ? halo[j - (t0 - pad)] : (uint32_t)keys[j];
+                                acc += round_dt<DT>(mxe - Tr::from_raw(rj));
+                            }
+                        }
+                        outv = round_dt<DT>(acc / inv_den);
+                    } else {
+                        outv = round_dt<DT>(mxe - Tr::from_raw(raw_i));
+                    }
+                }
+                __syncthreads();  // every read of this tile's inputs (keys + halo) is done
+                if (i < R) {
+                    if (pad > 0 && i >= t0 + NT - pad) halo[i - (t0 + NT - pad)] = raw_i;
+                    const Key key = ordered_key<Key>(Tr::to_raw(outv), /*descending=*/true);
+                    keys[i] = key;
+                    atomicAdd(&hist[(uint32_t)key >> kShift0], 1u);
+                }
+                __syncthreads();
+            }
+        }
+        // ---------------------------------------------------------- K2: select
+        block_radix_select<Key, NT>(keys, R, ksel, hist, misc, sidx, L.lo);
+    }
+
+    // -------------------------------------------------------------- K3: gather
+    const int sink = L.sink;
+    const int C = sink + ksel + L.tail;
+    const int tail0 = L.S - L.tail - sink - ksel;  // src row = j + tail0 for tail rows
+    if (L.idx_out != nullptr) {
+        int32_t* io = L.idx_out + (int64_t)bh * C;
+        for (int j = tid; j < C; j += NT) io[j] = j < sink ? j : (j < sink + ksel ? sidx[j - sink] : j + tail0);
+    }
+    const int Qh = C * cpr;  // chunks per tensor
+    const int Q = 2 * Qh;
+    char* ko = L.k_out + (int64_t)bh * Qh * 16;
+    char* vo = L.v_out + (int64_t)bh * Qh * 16;
+    constexpr int UG = 8;
+    for (int q0 = 0; q0 < Q; q0 += NT * UG) {
+        int4 v[UG];
+#pragma unroll
+        for (int u = 0; u < UG; ++u) {
+            const int q = q0 + u * NT + tid;
+            if (q < Q) {
+                const bool isv = q >= Qh;
+                const int qq = isv ? q - Qh : q;
+                const int j = kGeneric ? qq / cpr : qq / (CPR > 0 ? CPR : 1);
+                const int c = qq - j * cpr;
+                const int row = j < sink ? j : (j < sink + ksel ? sidx[j - sink] : j + tail0);
+                const char* src = isv ? vbase + (int64_t)row * L.vss : kbase + (int64_t)row * L.kss;
+                v[u] = ldg128_stream(src + c * 16);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < UG; ++u) {
+            const int q = q0 + u * NT + tid;
+            if (q < Q) {
+                const bool isv = q >= Qh;
+                const int qq = isv ? q - Qh : q;
+                stg128_stream((isv ? vo : ko) + (int64_t)qq * 16, v[u]);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ standalone K1
+// One warp step = 32/lpr rows; grid-stride over row groups of one [B,H,R] problem.
+template <int DT>
+__global__ void __launch_bounds__(256) kvc_norm_kernel(const char* __restrict__ k_in, int64_t sb, int64_t sh,
+                                                       int64_t ss, int H, int row_lo, int R, int64_t total_rows,
+                                                       int lpr, int cpl, typename Traits<DT>::Key* __restrict__ out) {
+    using Tr = Traits<DT>;
+    const int lane = threadIdx.x & 31;
+    const int rpw = 32 / lpr;
+    const int sub = lane % lpr, rw = lane / lpr;
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t g = warp_global * rpw; g < total_rows; g += n_warps * rpw) {
+        const int64_t idx = g + rw;  // flat (bh, r)
+        const bool ok = rw < rpw && idx < total_rows;
+        float acc = 0.f;
+        if (ok) {
+            const int64_t bh = idx / R;
+            const int r = (int)(idx - bh * R);
+            const int64_t b = bh / H, h = bh - b * H;
+            const char* p = k_in + b * sb + h * sh + (int64_t)(row_lo + r) * ss + (int64_t)sub * 16;
+            for (int c = 0; c < cpl; ++c) acc = Tr::sumsq(ldg128_stream(p + (int64_t)c * lpr * 16), acc);
+        }
+        acc = group_sum_pow2(acc, lpr);
+        if (ok && sub == 0) out[idx] = (typename Tr::Key)Tr::to_raw(sqrtf(acc));
+    }
+}
+
+// ------------------------------------------------------------------ standalone K2
+// One CTA per score row: load scores -> ordered keys + histogram in shared memory -> select.
+template <int DT, int NT>
+__global__ void __launch_bounds__(NT) kvc_select_kernel(const typename Traits<DT>::Key* __restrict__ scores, int n,
+                                                        int k, int largest, int32_t* __restrict__ idx_out) {
+    using Tr = Traits<DT>;
+    using Key = typename Tr::Key;
+    constexpr int kShift0 = Tr::kKeyBits - kHistBits;
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint32_t* hist = reinterpret_cast<uint32_t*>(smem);
+    int32_t* misc = reinterpret_cast<int32_t*>(smem + kHistBins * 4);
+    int32_t* sidx = reinterpret_cast<int32_t*>(smem + kSmemFixed);
+    Key* keys = reinterpret_cast<Key*>(smem + kSmemFixed + (size_t)((k + 3) & ~3) * 4);
+    const int tid = threadIdx.x;
+    const Key* src = scores + (int64_t)blockIdx.x * n;
+    for (int i = tid; i < kHistBins; i += NT) hist[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += NT) {
+        const Key key = ordered_key<Key>((uint32_t)src[i], largest != 0);
+        keys[i] = key;
+        atomicAdd(&hist[(uint32_t)key >> kShift0], 1u);
+    }
+    __syncthreads();
+    block_radix_select<Key, NT>(keys, n, k, hist, misc, sidx, 0);
+    int32_t* dst = idx_out + (int64_t)blockIdx.x * k;
+    for (int i = tid; i < k; i += NT) dst[i] = sidx[i];
+}
+
+// ------------------------------------------------------------------ host side
+static thread_local char g_last_error[256] = "";
+static std::atomic<int64_t> g_launches{0};
+constexpr int kMaxSmemOptin = 227 * 1024;
+
+static int cuda_fail(cudaError_t e, const char* what) {
+    snprintf(g_last_error, sizeof(g_last_error), "%s: %s", what, cudaGetErrorString(e));
+    return KVC_ERR_CUDA;
+}
+
+static int elem_bytes(int dtype) { return dtype == KVC_DTYPE_F32 ? 4 : 2; }
+static int key_bytes(int dtype) { return dtype == KVC_DTYPE_F32 ? 4 : 2; }
+
+using FusedFn = void (*)(const BatchDev);
+struct FusedVariant {
+    FusedFn fn;
+    int threads;
+};
+
+constexpr int kNT = 512;
+
+template <int DT>
+static FusedVariant pick_fused(int cpr) {
+    switch (cpr) {
+        case 8: return {kvc_fused_kernel<DT, 8, 8, kNT, 2>, kNT};
+        case 10: return {kvc_fused_kernel<DT, 10, 10, kNT, 2>, kNT};
+        case 16: return {kvc_fused_kernel<DT, 16, 8, kNT, 2>, kNT};
+        case 20: return {kvc_fused_kernel<DT, 20, 10, kNT, 2>, kNT};
+        case 32: return {kvc_fused_kernel<DT, 32, 16, kNT, 2>, kNT};
+        default: return {kvc_fused_kernel<DT, 0, 0, kNT, 2>, kNT};
+    }
+}
+
+static FusedVariant pick_fused_dt(int dtype, int cpr) {
+    switch (dtype) {
+        case KVC_DTYPE_F32: return pick_fused<KVC_DTYPE_F32>(cpr);
+        case KVC_DTYPE_F16: return pick_fused<KVC_DTYPE_F16>(cpr);
+        default: return pick_fused<KVC_DTYPE_BF16>(cpr);
+    }
+}
+
+static int set_device(int device) {
+    int cur = -1;
+    cudaError_t e = cudaGetDevice(&cur);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
+    if (cur != device) {
+        e = cudaSetDevice(device);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    }
+    return KVC_OK;
+}
+
+static int ensure_smem(const void* fn, size_t bytes) {
+    // The attribute is sticky per function and context; raising it again is cheap.
+    if (bytes > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmemOptin);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(max dynamic smem)");
+    }
+    return KVC_OK;
+}
+
+// Largest power of two dividing cpr, capped at 32 (generic-path lanes per row).
+static int pow2_lanes(int cpr) {
+    int l = 1;
+    while (l < 32 && (cpr % (l * 2)) == 0) l *= 2;
+    return l;
+}
+
+static size_t fused_smem_bytes(int dtype, int max_region, int idx_cap) {
+    const size_t keys = ((size_t)max_region * key_bytes(dtype) + 15) & ~(size_t)15;
+    return (size_t)kSmemFixed + (size_t)idx_cap * 4 + keys;
+}
+
+}  // namespace kvc
+
+using namespace kvc;
+
+extern "C" {
+
+int kvc_abi_version(void) { return KVC_ABI_VERSION; }
+
+const char* kvc_build_info(void) {
+    return "libkvc_sm100a: sm_100a, nvcc " KVC_STR(__CUDACC_VER_MAJOR__) "." KVC_STR(__CUDACC_VER_MINOR__);
+}
+
+const char* kvc_status_string(int status) {
+    switch (status) {
+        case KVC_OK: return "ok";
+        case KVC_ERR_INVALID_ARG: return "invalid argument";
+        case KVC_ERR_UNSUPPORTED: return "unsupported dtype / head_dim / alignment";
+        case KVC_ERR_TOO_LARGE: return "selection region too large for the on-chip score buffer";
+        case KVC_ERR_CUDA: return "CUDA error";
+        default: return "unknown status";
+    }
+}
+
+const char* kvc_last_cuda_error(void) { return g_last_error; }
+
+int64_t kvc_launch_count(void) { return g_launches.load(); }
+
+int32_t kvc_max_region_rows(int32_t dtype, int32_t k_sel) {
+    if (dtype < 0 || dtype > 2 || k_sel < 0) return 0;
+    const int64_t idx = ((int64_t)k_sel + 3) & ~(int64_t)3;
+    const int64_t left = (int64_t)kMaxSmemOptin - kSmemFixed - idx * 4;
+    if (left <= 0) return 0;
+    const int64_t rows = (left & ~(int64_t)15) / key_bytes(dtype);
+    return (int32_t)(rows > 0x7fffffff ? 0x7fffffff : rows);
+}
+
+int kvc_compress_layers(const kvc_shape* shape, int32_t n_layers, const kvc_layer_plan* plans,
+                        const kvc_layer_io* io, void* stream) {
+    if (!shape || n_layers < 0 || (n_layers > 0 && (!plans || !io))) return KVC_ERR_INVALID_ARG;
+    if (n_layers == 0) return KVC_OK;
+    const int B = shape->batch, H = shape->heads, D = shape->head_dim, dt = shape->dtype;
+    if (B <= 0 || H <= 0 || D <= 0) return KVC_ERR_INVALID_ARG;
+    if (dt != KVC_DTYPE_F32 && dt != KVC_DTYPE_F16 && dt != KVC_DTYPE_BF16) return KVC_ERR_UNSUPPORTED;
+    const int e = elem_bytes(dt);
+    if (((int64_t)D * e) % 16 != 0) return KVC_ERR_UNSUPPORTED;
+    if ((int64_t)B * H > 0x7fffffffLL) return KVC_ERR_INVALID_ARG;
+    const int cpr = D * e / 16;
+
+    // validate every layer before anything is enqueued
+    for (int l = 0; l < n_layers; ++l) {
+        const kvc_layer_plan& p = plans[l];
+        const kvc_layer_io& x = io[l];
+        const int64_t C = (int64_t)p.sink + p.k_sel + p.tail;
+        if (p.seq_len < 0 || p.sink < 0 || p.k_sel < 0 || p.tail < 0) return KVC_ERR_INVALID_ARG;
+        if (p.sink > p.seq_len || p.tail > p.seq_len) return KVC_ERR_INVALID_ARG;
+        if (p.k_sel > 0) {
+            if (p.sel_lo < 0 || p.sel_hi > p.seq_len || p.sel_lo > p.sel_hi) return KVC_ERR_INVALID_ARG;
+            if (p.k_sel > p.sel_hi - p.sel_lo) return KVC_ERR_INVALID_ARG;
+            if (p.score == KVC_SCORE_NONE) return KVC_ERR_INVALID_ARG;
+            if (p.score < KVC_SCORE_NONE || p.score > KVC_SCORE_GIVEN_INDEX) return KVC_ERR_INVALID_ARG;
+            if (p.score == KVC_SCORE_GIVEN_INDEX && !x.idx_in) return KVC_ERR_INVALID_ARG;
+            if (p.score == KVC_SCORE_SNAPKV_POOL && p.pool_kernel > 2 * kMaxPoolHalo) return KVC_ERR_UNSUPPORTED;
+        }
+        if (C == 0) continue;
+        if (!x.k_in || !x.v_in || !x.k_out || !x.v_out) return KVC_ERR_INVALID_ARG;
+        if (C * cpr * 2 > 0x7fffffffLL) return KVC_ERR_TOO_LARGE;
+        const uintptr_t a = (uintptr_t)x.k_in | (uintptr_t)x.v_in | (uintptr_t)x.k_out | (uintptr_t)x.v_out;
+        if (a & 15) return KVC_ERR_UNSUPPORTED;
+        const int64_t s = (x.k_stride_b | x.k_stride_h | x.k_stride_s | x.v_stride_b | x.v_stride_h | x.v_stride_s);
+        if ((s * e) & 15) return KVC_ERR_UNSUPPORTED;
+    }
+    int st = set_device(shape->device);
+    if (st != KVC_OK) return st;
+
+    const FusedVariant var = pick_fused_dt(dt, cpr);
+    for (int l0 = 0; l0 < n_layers; l0 += KVC_MAX_LAYERS_PER_LAUNCH) {
+        const int nl = (n_layers - l0) < KVC_MAX_LAYERS_PER_LAUNCH ? (n_layers - l0) : KVC_MAX_LAYERS_PER_LAUNCH;
+        BatchDev bd;
+        memset(&bd, 0, sizeof(bd));
+        bd.B = B;
+        bd.H = H;
+        bd.cpr = cpr;
+        bd.lpr = pow2_lanes(cpr);
+        bd.cpl = cpr / bd.lpr;
+        int n_active = 0, max_region = 0, max_ksel = 0;
+        bool any_select = false;
+        for (int l = 0; l < nl; ++l) {
+            const kvc_layer_plan& p = plans[l0 + l];
+            const kvc_layer_io& x = io[l0 + l];
+            if (p.sink + p.k_sel + p.tail == 0) continue;
+            LayerDev& d = bd.layers[n_active++];
+            d.k_in = (const char*)x.k_in;
+            d.v_in = (const char*)x.v_in;
+            d.k_out = (char*)x.k_out;
+            d.v_out = (char*)x.v_out;
+            d.idx_out = x.idx_out;
+            d.idx_in = x.idx_in;
+            d.ksb = x.k_stride_b * e;
+            d.ksh = x.k_stride_h * e;
+            d.kss = x.k_stride_s * e;
+            d.vsb = x.v_stride_b * e;
+            d.vsh = x.v_stride_h * e;
+            d.vss = x.v_stride_s * e;
+            d.S = p.seq_len;
+            d.sink = p.sink;
+            d.lo = p.sel_lo;
+            d.hi = p.sel_hi;
+            d.ksel = p.k_sel;
+            d.tail = p.tail;
+            d.score = p.k_sel > 0 ? p.score : KVC_SCORE_NONE;
+            d.pool = p.pool_kernel;
+            if (p.k_sel > 0) {
+                any_select = true;
+                if (p.k_sel > max_ksel) max_ksel = p.k_sel;
+                if (p.score != KVC_SCORE_GIVEN_INDEX && p.sel_hi - p.sel_lo > max_region)
+                    max_region = p.sel_hi - p.sel_lo;
+            }
+        }
+        if (n_active == 0) continue;
+        bd.idx_cap = (max_ksel + 3) & ~3;
+        size_t smem = any_select ? fused_smem_bytes(dt, max_region, bd.idx_cap) : 0;
+        if (smem > (size_t)kMaxSmemOptin) return KVC_ERR_TOO_LARGE;
+        st = ensure_smem((const void*)var.fn, smem);
+        if (st != KVC_OK) return st;
+        dim3 grid((unsigned)((int64_t)B * H), (unsigned)n_active, 1);
+        var.fn<<<grid, var.threads, smem, (cudaStream_t)stream>>>(bd);
+        cudaError_t err = cudaGetLastError();
+        if (err != cudaSuccess) return cuda_fail(err, "kvc_fused_kernel launch");
+        g_launches.fetch_add(1);
+    }
+    return KVC_OK;
+}
+
+int kvc_key_norms(const kvc_shape* shape, const void* k_in, int64_t stride_b, int64_t stride_h, int64_t stride_s,
+                  int32_t row_lo, int32_t row_hi, void* norms_out, void* stream) {
+    if (!shape || !k_in || !norms_out || row_lo < 0 || row_hi < row_lo) return KVC_ERR_INVALID_ARG;
+    const int B = shape->batch, H = shape->heads, D = shape->head_dim, dt = shape->dtype;
+    if (B <= 0 || H <= 0 || D <= 0) return KVC_ERR_INVALID_ARG;
+    if (dt != KVC_DTYPE_F32 && dt != KVC_DTYPE_F16 && dt != KVC_DTYPE_BF16) return KVC_ERR_UNSUPPORTED;
+    const int e = elem_bytes(dt);
+    if (((int64_t)D * e) % 16 != 0 || ((uintptr_t)k_in & 15)) return KVC_ERR_UNSUPPORTED;
+    if (((stride_b | stride_h | stride_s) * e) & 15) return KVC_ERR_UNSUPPORTED;
+    const int R = row_hi - row_lo;
+    const int64_t total = (int64_t)B * H * R;
+    if (total == 0) return KVC_OK;
+    int st = set_device(shape->device);
+    if (st != KVC_OK) return st;
+    const int cpr = D * e / 16;
+    const int lpr = pow2_lanes(cpr), cpl = cpr / lpr;
+    const int rpw = 32 / lpr;
+    const int64_t warps_needed = (total + rpw - 1) / rpw;
+    int64_t blocks = (warps_needed + 7) / 8;
+    const int64_t cap = 148LL * 8 * 4;
+    if (blocks > cap) blocks = cap;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t sb = stride_b * e, sh = stride_h * e, ss = stride_s * e;
+    switch (dt) {
+        case KVC_DTYPE_F32:
+            kvc_norm_kernel<KVC_DTYPE_F32><<<(unsigned)blocks, 256, 0, s>>>((const char*)k_in, sb, sh, ss, H, row_lo, R,
+                                                                           total, lpr, cpl, (uint32_t*)norms_out);
+            break;
+        case KVC_DTYPE_F16:
+            kvc_norm_kernel<KVC_DTYPE_F16><<<(unsigned)blocks, 256, 0, s>>>((const char*)k_in, sb, sh, ss, H, row_lo, R,
+                                                                           total, lpr, cpl, (uint16_t*)norms_out);
+            break;
+        default:
+            kvc_norm_kernel<KVC_DTYPE_BF16><<<(unsigned)blocks, 256, 0, s>>>((const char*)k_in, sb, sh, ss, H, row_lo,
+                                                                            R, total, lpr, cpl, (uint16_t*)norms_out);
+            break;
+    }
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return cuda_fail(err, "kvc_norm_kernel launch");
+    g_launches.fetch_add(1);
+    return KVC_OK;
+}
+
+int kvc_select(int32_t dtype, int32_t device, const void* scores, int64_t n_rows, int32_t n, int32_t k,
+               int32_t largest, int32_t* idx_out, void* stream) {
+    if (!scores || !idx_out || n_rows < 0 || n < 0 || k < 0 || k > n) return KVC_ERR_INVALID_ARG;
+    if (dtype != KVC_DTYPE_F32 && dtype != KVC_DTYPE_F16 && dtype != KVC_DTYPE_BF16) return KVC_ERR_UNSUPPORTED;
+    if (n_rows == 0 || k == 0) return KVC_OK;
+    if (n_rows > 0x7fffffffLL) return KVC_ERR_INVALID_ARG;
+    const size_t smem = fused_smem_bytes(dtype, n, (k + 3) & ~3);
+    if (smem > (size_t)kMaxSmemOptin) return KVC_ERR_TOO_LARGE;
+    int st = set_device(device);
+    if (st != KVC_OK) return st;
+    cudaStream_t s = (cudaStream_t)stream;
+    const void* fn = nullptr;
+    switch (dtype) {
+        case KVC_DTYPE_F32: fn = (const void*)kvc_select_kernel<KVC_DTYPE_F32, kNT>; break;
+        case KVC_DTYPE_F16: fn = (const void*)kvc_select_kernel<KVC_DTYPE_F16, kNT>; break;
+        default: fn = (const void*)kvc_select_kernel<KVC_DTYPE_BF16, kNT>; break;
+    }
+    st = ensure_smem(fn, smem);
+    if (st != KVC_OK) return st;
+    switch (dtype) {
+        case KVC_DTYPE_F32:
+            kvc_select_kernel<KVC_DTYPE_F32, kNT>
+                <<<(unsigned)n_rows, kNT, smem, s>>>((const uint32_t*)scores, n, k, largest, idx_out);
+            break;
+        case KVC_DTYPE_F16:
+            kvc_select_kernel<KVC_DTYPE_F16, kNT>
+                <<<(unsigned)n_rows, kNT, smem, s>>>((const uint16_t*)scores, n, k, largest, idx_out);
+            break;
+        default:
+            kvc_select_kernel<KVC_DTYPE_BF16, kNT>
+                <<<(unsigned)n_rows, kNT, smem, s>>>((const uint16_t*)scores, n, k, largest, idx_out);
+            break;
+    }
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return cuda_fail(err, "kvc_select_kernel launch");
+    g_launches.fetch_add(1);
+    return KVC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,220 @@
+"""ctypes binding to ``libkvc_sm100a.so`` (C ABI in ``include/kvc.h``) and plan execution.
+
+This is the only module that talks to the device library.  There is no CPU path and no
+fallback: if a plan needs data movement, the tensors must live on a CUDA device and the
+shared library must be present, otherwise a ``RuntimeError`` is raised.
+
+PyTorch is used for device memory (``torch.empty`` through the caching allocator) and for
+the current stream; all compute happens in the library's own sm_100a kernels.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import os
+import struct
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _planner as P
+
+_LIB_NAME = "libkvc_sm100a.so"
+_CSRC_DIR = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "csrc"))
+_LIB_PATH = os.path.join(_CSRC_DIR, _LIB_NAME)
+
+# struct layouts of include/kvc.h
+_PLAN = struct.Struct("8i")        # kvc_layer_plan: seq_len sink sel_lo sel_hi k_sel tail score pool_kernel
+_IO = struct.Struct("4P6q2P")      # kvc_layer_io: k_in v_in k_out v_out | 6 strides | idx_out idx_in
+_SHAPE = struct.Struct("5i")       # kvc_shape: batch heads head_dim dtype device
+assert _PLAN.size == 32 and _IO.size == 96 and _SHAPE.size == 20
+
+KVC_DTYPE = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+KVC_OK = 0
+_STATUS_EXC = {1: ValueError, 2: ValueError, 3: ValueError, 4: RuntimeError}
+
+_lib = None
+
+
+def library_path() -> str:
+    return _LIB_PATH
+
+
+def load_library():
+    """Load the device library once; raise loudly if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise RuntimeError(
+            f"{_LIB_NAME} not found at {_LIB_PATH}: build it with `python -c 'import __graft_entry__ as g; "
+            "g.build()'` (nvcc, sm_100a). kvcompress-b200 has no CPU or PyTorch fallback."
+        )
+    lib = ctypes.CDLL(_LIB_PATH)
+    lib.kvc_abi_version.restype = ctypes.c_int
+    lib.kvc_build_info.restype = ctypes.c_char_p
+    lib.kvc_status_string.restype = ctypes.c_char_p
+    lib.kvc_status_string.argtypes = [ctypes.c_int]
+    lib.kvc_last_cuda_error.restype = ctypes.c_char_p
+    lib.kvc_launch_count.restype = ctypes.c_int64
+    lib.kvc_max_region_rows.restype = ctypes.c_int32
+    lib.kvc_max_region_rows.argtypes = [ctypes.c_int32, ctypes.c_int32]
+    lib.kvc_compress_layers.restype = ctypes.c_int
+    lib.kvc_compress_layers.argtypes = [ctypes.c_char_p, ctypes.c_int32, ctypes.c_char_p, ctypes.c_char_p,
+                                        ctypes.c_void_p]
+    lib.kvc_key_norms.restype = ctypes.c_int
+    lib.kvc_key_norms.argtypes = [ctypes.c_char_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int64,
+                                  ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]
+    lib.kvc_select.restype = ctypes.c_int
+    lib.kvc_select.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32,
+                               ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]
+    if lib.kvc_abi_version() != 1:
+        raise RuntimeError(f"{_LIB_NAME}: ABI version {lib.kvc_abi_version()} != 1 — rebuild the library")
+    _lib = lib
+    return lib
+
+
+def launch_count() -> int:
+    """Kernels launched by the library so far in this process."""
+    return int(load_library().kvc_launch_count())
+
+
+def _check(status: int, what: str) -> None:
+    if status == KVC_OK:
+        return
+    lib = load_library()
+    msg = lib.kvc_status_string(status).decode()
+    if status == 4:
+        msg += ": " + lib.kvc_last_cuda_error().decode()
+    raise _STATUS_EXC.get(status, RuntimeError)(f"{what}: {msg}")
+
+
+def _require_cuda(t: torch.Tensor, what: str) -> None:
+    if not t.is_cuda:
+        raise RuntimeError(
+            f"{what}: tensor is on {t.device}; kvcompress-b200 runs on CUDA (sm_100a) only — there is no CPU path"
+        )
+    if t.dtype not in KVC_DTYPE:
+        raise ValueError(f"{what}: dtype {t.dtype} is not supported (float32, float16, bfloat16)")
+
+
+def _rows_ok(t: torch.Tensor) -> bool:
+    e = t.element_size()
+    return (t.stride(3) == 1 or t.size(3) == 1) and all((t.stride(i) * e) % 16 == 0 for i in range(3)) \
+        and t.data_ptr() % 16 == 0
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def run_plans(kv: Sequence[Tuple[torch.Tensor, torch.Tensor]], plans: Sequence[P.LayerPlan],
+              given_indices: Optional[dict] = None, return_indices: bool = False):
+    """Apply per-layer plans to a list of (K, V) pairs.
+
+    KEEP layers keep their tensor objects, VIEW layers become ``x[:, :, -n:, :]`` views (both
+    exactly as the reference does); all GATHER layers of the call go to the device library in
+    one ``kvc_compress_layers`` call per (device, dtype, B, H, D) group — normally one launch.
+
+    given_indices: {layer_idx: int32 CUDA tensor [B, H, k_sel]} for SCORE_GIVEN_INDEX plans.
+    return_indices: also return {layer_idx: int32 tensor [B, H, C]} of kept absolute rows.
+    """
+    out: List[Tuple[torch.Tensor, torch.Tensor]] = list(kv)
+    groups = {}
+    for li, plan in enumerate(plans):
+        if plan.kind == P.KEEP:
+            continue
+        keys, values = kv[li][0], kv[li][1]
+        if plan.kind == P.VIEW:
+            n = plan.view_n
+            out[li] = (keys[:, :, -n:, :], values[:, :, -n:, :])
+            continue
+        _require_cuda(keys, f"layer {li} keys")
+        _require_cuda(values, f"layer {li} values")
+        if keys.dim() != 4 or values.shape != keys.shape or values.dtype != keys.dtype or values.device != keys.device:
+            raise ValueError(f"layer {li}: keys/values must be matching [B, H, S, D] tensors")
+        if keys.size(2) != plan.seq_len:
+            raise ValueError(f"layer {li}: plan built for seq_len {plan.seq_len}, tensor has {keys.size(2)}")
+        B, H, _, D = keys.shape
+        if (D * keys.element_size()) % 16 != 0:
+            raise ValueError(f"layer {li}: head_dim*itemsize = {D * keys.element_size()} B is not a multiple of 16")
+        groups.setdefault((keys.device, keys.dtype, B, H, D), []).append(li)
+
+    indices = {}
+    keepalive = []
+    for (device, dtype, B, H, D), layer_ids in groups.items():
+        lib = load_library()
+        plan_buf = bytearray(_PLAN.size * len(layer_ids))
+        io_buf = bytearray(_IO.size * len(layer_ids))
+        for n, li in enumerate(layer_ids):
+            plan = plans[li]
+            keys, values = kv[li][0], kv[li][1]
+            if not _rows_ok(keys):
+                keys = keys.contiguous()
+                keepalive.append(keys)
+            if not _rows_ok(values):
+                values = values.contiguous()
+                keepalive.append(values)
+            C = plan.out_len
+            k_out = torch.empty((B, H, C, D), dtype=dtype, device=device)
+            v_out = torch.empty((B, H, C, D), dtype=dtype, device=device)
+            out[li] = (k_out, v_out)
+            idx_out_ptr = 0
+            if return_indices:
+                idx = torch.empty((B, H, C), dtype=torch.int32, device=device)
+                indices[li] = idx
+                idx_out_ptr = idx.data_ptr()
+            idx_in_ptr = 0
+            if plan.score == P.SCORE_GIVEN_INDEX and plan.k_sel > 0:
+                gi = None if given_indices is None else given_indices.get(li)
+                if gi is None:
+                    raise ValueError(f"layer {li}: plan needs caller-supplied indices")
+                if gi.dtype != torch.int32 or not gi.is_contiguous() or tuple(gi.shape) != (B, H, plan.k_sel) \
+                        or gi.device != device:
+                    raise ValueError(f"layer {li}: indices must be a contiguous int32 [B, H, k_sel] tensor on {device}")
+                idx_in_ptr = gi.data_ptr()
+                keepalive.append(gi)
+            _PLAN.pack_into(plan_buf, n * _PLAN.size, plan.seq_len, plan.sink, plan.sel_lo, plan.sel_hi, plan.k_sel,
+                            plan.tail, plan.score, plan.pool_kernel)
+            _IO.pack_into(io_buf, n * _IO.size, keys.data_ptr(), values.data_ptr(), k_out.data_ptr(),
+                          v_out.data_ptr(), keys.stride(0), keys.stride(1), keys.stride(2), values.stride(0),
+                          values.stride(1), values.stride(2), idx_out_ptr, idx_in_ptr)
+        dev_index = device.index if device.index is not None else torch.cuda.current_device()
+        shape = _SHAPE.pack(B, H, D, KVC_DTYPE[dtype], dev_index)
+        status = lib.kvc_compress_layers(shape, len(layer_ids), bytes(plan_buf), bytes(io_buf),
+                                         ctypes.c_void_p(_stream_ptr(device)))
+        _check(status, "kvc_compress_layers")
+    if return_indices:
+        return out, indices
+    return out
+
+
+def key_norms(keys: torch.Tensor, row_lo: int = 0, row_hi: Optional[int] = None) -> torch.Tensor:
+    """``torch.norm(keys[:, :, row_lo:row_hi], p=2, dim=-1)`` on the device library (K1)."""
+    _require_cuda(keys, "keys")
+    if keys.dim() != 4:
+        raise ValueError("keys must be [B, H, S, D]")
+    if not _rows_ok(keys):
+        keys = keys.contiguous()
+    B, H, S, D = keys.shape
+    row_hi = S if row_hi is None else row_hi
+    out = torch.empty((B, H, max(row_hi - row_lo, 0)), dtype=keys.dtype, device=keys.device)
+    shape = _SHAPE.pack(B, H, D, KVC_DTYPE[keys.dtype], keys.device.index)
+    status = load_library().kvc_key_norms(shape, keys.data_ptr(), keys.stride(0), keys.stride(1), keys.stride(2),
+                                          row_lo, row_hi, out.data_ptr(), ctypes.c_void_p(_stream_ptr(keys.device)))
+    _check(status, "kvc_key_norms")
+    return out
+
+
+def select(scores: torch.Tensor, k: int, largest: bool = False) -> torch.Tensor:
+    """Ascending indices of the k smallest (largest) scores per row, ties to the lowest index (K2)."""
+    _require_cuda(scores, "scores")
+    scores = scores.contiguous()
+    n = scores.size(-1)
+    rows = scores.numel() // max(n, 1)
+    out = torch.empty(tuple(scores.shape[:-1]) + (k,), dtype=torch.int32, device=scores.device)
+    status = load_library().kvc_select(KVC_DTYPE[scores.dtype], scores.device.index, scores.data_ptr(), rows, n, k,
+                                       1 if largest else 0, out.data_ptr(),
+                                       ctypes.c_void_p(_stream_ptr(scores.device)))
+    _check(status, "kvc_select")
+    return out

@@ -1,0 +1,127 @@
+/*
+ * kvc.h — C ABI of libkvc_sm100a.so: the B200 (sm_100a) per-step KV-cache
+ * compression hot path of `kvcompress`.
+ *
+ * The reference has no FFI layer: its plugin boundary is the Python callable
+ *   fn(past_key_values, <method kwargs>, skip_layers=..., **kwargs)
+ *       -> List[Tuple[Tensor, Tensor]]
+ * (reference kvcompress/methods/base.py:12-33, registry methods/__init__.py:21-78).
+ * Every one of the eight hot-path methods reduces, per layer, to one descriptor
+ *   keep [0,sink)  U  (k_sel rows of [sel_lo,sel_hi) chosen by a key)  U  [S-tail,S)
+ * emitted in ascending token order for K and V.  The Python
+ * planner computes the integers exactly as the reference does; this library does
+ * all device work.  Entry points and the reference code they replace:
+ *
+ *   kvc_compress_layers  per-layer  torch.norm -> argsort/topk -> sort -> expand ->
+ *                        gather x2 -> cat x2, for every layer of the call in ONE launch
+ *                        (l2_compress.py:70-88, fix_size_l2.py:104-147,
+ *                         streaming_llm.py:99-107, h2o_l2.py:116-149,
+ *                         snapkv_lite.py:93-150, pyramid_kv.py:150-181,
+ *                         adaptive_l2.py:116-143,176-197)
+ *   kvc_key_norms        torch.norm(K, p=2, dim=-1)            (e.g. l2_compress.py:70)
+ *   kvc_select           argsort()[..., :k] + torch.sort / torch.topk + torch.sort
+ *                        over caller-supplied scores           (e.g. h2o_l2.py:128-132,
+ *                         snapkv_lite.py:134-137)
+ *
+ * Conventions: plain pointers and sizes only; the library allocates nothing and
+ * never synchronises; all work is enqueued on `stream` (a cudaStream_t passed as
+ * void*); every function returns a kvc_status (0 = ok).  Tensors are device
+ * pointers to [B, H, S, D] arrays whose last dimension is dense (stride 1) and
+ * whose rows are 16-byte aligned; B/H/S strides are given in ELEMENTS.  Outputs are
+ * dense [B, H, C, D] with C = sink + k_sel + tail.  There is no CPU path.
+ */
+#ifndef KVC_H_
+#define KVC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KVC_ABI_VERSION 1
+
+typedef enum kvc_status {
+    KVC_OK = 0,
+    KVC_ERR_INVALID_ARG = 1, /* null pointer, negative size, inconsistent plan */
+    KVC_ERR_UNSUPPORTED = 2, /* dtype / head_dim / alignment the kernels do not cover */
+    KVC_ERR_TOO_LARGE = 3,   /* selection region does not fit the on-chip score buffer */
+    KVC_ERR_CUDA = 4         /* launch or runtime failure; see kvc_last_cuda_error() */
+} kvc_status;
+
+typedef enum kvc_dtype {
+    KVC_DTYPE_F32 = 0,
+    KVC_DTYPE_F16 = 1,
+    KVC_DTYPE_BF16 = 2
+} kvc_dtype;
+
+/* How rows of [sel_lo, sel_hi) are ranked. Ties always go to the lowest token index. */
+typedef enum kvc_score_kind {
+    KVC_SCORE_NONE = 0,        /* k_sel must be 0: pure sink + tail slice (streaming_llm.py:99-107) */
+    KVC_SCORE_L2_LOW = 1,      /* keep the k_sel lowest  ||K||_2  (norm().argsort()[:k])            */
+    KVC_SCORE_L2_HIGH = 2,     /* keep the k_sel highest ||K||_2  (argsort(descending=True)[:k])    */
+    KVC_SCORE_SNAPKV_POOL = 3, /* (max norm + 1e-6 - norm) -> avg_pool1d -> topk (snapkv_lite.py:96-134) */
+    KVC_SCORE_GIVEN_INDEX = 4  /* caller supplies ascending absolute row indices (fix_size_l2 "random") */
+} kvc_score_kind;
+
+/* One layer's keep-plan: integers computed by the host planner (reference arithmetic). */
+typedef struct kvc_layer_plan {
+    int32_t seq_len;     /* S of this layer's input                           */
+    int32_t sink;        /* rows [0, sink) are kept                            */
+    int32_t sel_lo;      /* selection region [sel_lo, sel_hi)                  */
+    int32_t sel_hi;
+    int32_t k_sel;       /* rows to keep from the region, 0 <= k_sel <= sel_hi - sel_lo */
+    int32_t tail;        /* rows [S - tail, S) are kept                        */
+    int32_t score;       /* kvc_score_kind                                     */
+    int32_t pool_kernel; /* SNAPKV_POOL: avg_pool1d kernel size (<=1: no pooling) */
+} kvc_layer_plan;
+
+/* One layer's device buffers. */
+typedef struct kvc_layer_io {
+    const void* k_in;  /* [B,H,S,D] keys                         */
+    const void* v_in;  /* [B,H,S,D] values                       */
+    void* k_out;       /* [B,H,C,D] dense                        */
+    void* v_out;       /* [B,H,C,D] dense                        */
+    int64_t k_stride_b, k_stride_h, k_stride_s; /* elements      */
+    int64_t v_stride_b, v_stride_h, v_stride_s; /* elements      */
+    int32_t* idx_out;      /* optional [B,H,C] kept absolute row indices, ascending; may be NULL */
+    const int32_t* idx_in; /* GIVEN_INDEX only: [B,H,k_sel] ascending absolute rows inside the region */
+} kvc_layer_io;
+
+typedef struct kvc_shape {
+    int32_t batch;    /* B */
+    int32_t heads;    /* H (KV heads) */
+    int32_t head_dim; /* D; D * sizeof(dtype) must be a multiple of 16 */
+    int32_t dtype;    /* kvc_dtype */
+    int32_t device;   /* CUDA device ordinal all pointers live on */
+} kvc_shape;
+
+/* ABI / build information. */
+int kvc_abi_version(void);
+const char* kvc_build_info(void);      /* e.g. "sm_100a nvcc 12.9" */
+const char* kvc_status_string(int status);
+const char* kvc_last_cuda_error(void); /* text of the last CUDA failure seen by this thread */
+/* Number of kernels this library has launched in this process (monotonic). */
+int64_t kvc_launch_count(void);
+/* Largest selection region (rows) kvc_compress_layers can score on chip for this dtype / k_sel. */
+int32_t kvc_max_region_rows(int32_t dtype, int32_t k_sel);
+
+/* Compress n_layers layers in one launch (chunks of KVC_MAX_LAYERS_PER_LAUNCH). */
+#define KVC_MAX_LAYERS_PER_LAUNCH 64
+int kvc_compress_layers(const kvc_shape* shape, int32_t n_layers, const kvc_layer_plan* plans,
+                        const kvc_layer_io* io, void* stream);
+
+/* norms[b,h,r] = dtype( sqrt( sum_d fp32(K[b,h,row_lo+r,d])^2 ) ), r in [0,row_hi-row_lo);
+ * fp32 accumulation, result rounded once to the input dtype (torch.norm semantics). */
+int kvc_key_norms(const kvc_shape* shape, const void* k_in, int64_t stride_b, int64_t stride_h,
+                  int64_t stride_s, int32_t row_lo, int32_t row_hi, void* norms_out, void* stream);
+
+/* Per (b,h) row of `scores` ([n_rows, n] of `dtype`, dense): the k smallest (largest if
+ * `largest`) entries, ties to the lowest index, written as ascending int32 indices [n_rows, k]. */
+int kvc_select(int32_t dtype, int32_t device, const void* scores, int64_t n_rows, int32_t n,
+               int32_t k, int32_t largest, int32_t* idx_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KVC_H_ */

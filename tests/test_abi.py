@@ -1,0 +1,49 @@
+"""The C-ABI library loads and exports every function include/kvc.h declares (no compute here)."""
+
+import ctypes
+import os
+import re
+
+import pytest
+
+from kvcompress import _engine
+
+ROOT = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+
+
+def declared_functions():
+    text = open(os.path.join(ROOT, "include", "kvc.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(kvc_[a-z_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = declared_functions()
+    assert {"kvc_compress_layers", "kvc_key_norms", "kvc_select", "kvc_abi_version"} <= set(names)
+    lib = ctypes.CDLL(_engine.library_path())
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in include/kvc.h but not exported"
+
+
+def test_library_metadata_and_argument_checks():
+    lib = _engine.load_library()
+    assert lib.kvc_abi_version() == 1
+    assert b"sm_100a" in lib.kvc_build_info()
+    assert lib.kvc_status_string(0) == b"ok"
+    assert lib.kvc_launch_count() >= 0
+    # bf16 keys are 2 bytes: a 32K-token region fits on chip with room to spare; fp32 up to ~52K rows
+    assert lib.kvc_max_region_rows(2, 512) >= 65536
+    assert 49152 <= lib.kvc_max_region_rows(0, 512) < 65536
+    # argument validation happens before any CUDA call, so it is testable without a GPU
+    assert lib.kvc_compress_layers(None, 1, None, None, None) == 1
+    shape = _engine._SHAPE.pack(1, 1, 12, 2, 0)  # D=12 bf16 -> 24-byte rows: not 16-byte aligned
+    plan = _engine._PLAN.pack(10, 1, 0, 0, 0, 1, 0, 1)
+    io = _engine._IO.pack(16, 16, 16, 16, 120, 120, 12, 120, 120, 12, 0, 0)
+    assert lib.kvc_compress_layers(shape, 1, plan, io, None) == 2
+    shape = _engine._SHAPE.pack(1, 1, 16, 2, 0)
+    bad_plan = _engine._PLAN.pack(10, 1, 0, 20, 3, 1, 1, 1)  # sel_hi > seq_len
+    assert lib.kvc_compress_layers(shape, 1, bad_plan, io, None) == 1
+
+
+def test_structs_match_header_sizes():
+    assert _engine._PLAN.size == 32 and _engine._IO.size == 96 and _engine._SHAPE.size == 20
