@@ -1,0 +1,511 @@
+#!/usr/bin/env python
+"""bench.py — the compress-step benchmark (BASELINE.json metric) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c2] [--impl ours|reference]
+
+One *step* = one pass of the compress hot path over one batch of synthetic KV cache: every call the
+config names (for the default c2: ``streaming_llm_compress(4, 508)`` then
+``fix_size_l2_compress(512, 0.2, keep_low)``) on a Pythia-2.8B-shaped bf16 cache, batch 32, 4K
+context, resident in HBM.  ``value`` = algorithmic bytes of a step (e*B*H*D*(R + 4C) per compressed
+layer) / device time, summed over ranks; weak scaling (each rank owns 32 streams).
+
+The printed JSON line follows the driver contract and adds ``roofline`` (dominant kernel vs the
+measured HBM copy peak), ``cpu_baseline`` (oracle/kvc_oracle.c, OpenMP, bounded sample) and
+``e2e`` (same step with HOST-resident caches: H2D + compress + D2H inside the timed region).
+``--impl reference`` times the CPU port alone on all host threads.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "cs3602-llm-inference-acceleration_b200"))
+
+PYTHIA = dict(model_shape="pythia-2.8b", L=32, H=32, D=80)
+LLAMA = dict(model_shape="llama-3-8b-gqa", L=32, H=8, D=128)
+CONFIGS = {
+    # BASELINE.json configs[1] — the configuration the metric is quoted on (fits one GPU: 42.9 GB)
+    "c2": dict(PYTHIA, B=32, S=4096, dtype="bf16", calls=[
+        ("streaming_llm", dict(start_size=4, recent_size=508)),
+        ("fix_size_l2", dict(fix_kv_size=512, keep_ratio=0.2, strategy="keep_low")),
+    ]),
+    # the same two calls at decode steady state (S = cap + 1)
+    "c2_steady": dict(PYTHIA, B=32, S=513, dtype="bf16", calls=[
+        ("streaming_llm", dict(start_size=4, recent_size=508)),
+        ("fix_size_l2", dict(fix_kv_size=512, keep_ratio=0.2, strategy="keep_low")),
+    ]),
+    # configs[2]: B=256 total = 8 ranks x 32 streams (86 GB per rank)
+    "c3": dict(PYTHIA, B=32, S=8192, dtype="bf16", calls=[
+        ("h2o_l2", dict(start_size=4, heavy_hitter_size=64, recent_size=444)),
+    ]),
+    # configs[3]
+    "c4": dict(LLAMA, B=16, S=32768, dtype="bf16", calls=[
+        ("snapkv_lite", dict(observation_window=32, keep_size=512)),
+    ]),
+    # configs[4]: B=64 total = 8 ranks x 8 streams (34 GB per rank)
+    "c5": dict(LLAMA, B=8, S=32768, dtype="bf16", calls=[
+        ("pyramid_kv", dict(base_size=512)),
+        ("adaptive_l2", dict(target_size=512)),
+    ]),
+    # configs[0] on the GPU for reference: fp32, batch 1
+    "c1": dict(PYTHIA, B=1, S=2048, dtype="f32", calls=[
+        ("l2_compress", dict(keep_ratio=0.8, prune_after=1000, skip_layers=[0, 1])),
+    ]),
+}
+FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=0, help="override the per-rank batch")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-slab", type=int, default=4, help="streams per host<->device slab in the e2e leg")
+    ap.add_argument("--cpu-sample-batch", type=int, default=0,
+                    help="streams in the CPU sample (0: enough (b,h) rows to occupy every host thread, at most 8)")
+    return ap.parse_args()
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def profiled_traffic(config: str):
+    """dram read+write bytes per launch of the dominant kernel from the committed ncu capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            return json.load(f).get(config)
+    except Exception:
+        return None
+
+
+# --------------------------------------------------------------------------- plans / bytes
+def plans_for(method, seq_lens, kw):
+    from kvcompress import _planner as P
+
+    kw = dict(kw)
+    if method == "streaming_llm":
+        return P.plan_streaming(seq_lens, kw.get("start_size", 4), kw.get("recent_size", 508), kw.get("skip_layers", []))
+    if method == "fix_size_l2":
+        return P.plan_fix_size(seq_lens, kw.get("fix_kv_size", 1024), kw.get("keep_ratio", 0.0),
+                               kw.get("strategy", "keep_low"), kw.get("skip_layers", [0, 1]))
+    if method == "h2o_l2":
+        return P.plan_h2o(seq_lens, kw.get("start_size", 4), kw.get("heavy_hitter_size", 64), kw.get("recent_size", 444),
+                          kw.get("skip_layers", []))
+    if method == "snapkv_lite":
+        return P.plan_snapkv(seq_lens, kw.get("observation_window", 32), kw.get("keep_size", 512),
+                             kw.get("pooling_kernel", 5), kw.get("skip_layers", []))
+    if method == "pyramid_kv":
+        return P.plan_pyramid(seq_lens, kw.get("base_size", 512), kw.get("layer_decay", 0.9), kw.get("min_size", 64),
+                              kw.get("profile", "exponential"), kw.get("skip_layers", []))
+    if method == "adaptive_l2":
+        return P.plan_adaptive(seq_lens, kw.get("target_size", 512), kw.get("soft_limit", 256),
+                               kw.get("hard_limit", 1024), kw.get("keep_ratio_min", 0.3), kw.get("keep_ratio_max", 0.9),
+                               kw.get("skip_layers", []))
+    if method == "l2_compress":
+        return P.plan_l2(seq_lens, kw.get("keep_ratio", 1.0), kw.get("prune_after", 1000), kw.get("skip_layers", [0, 1]))
+    raise KeyError(method)
+
+
+def call_bytes(cfg, batch):
+    from kvcompress import _planner as P
+
+    e = 4 if cfg["dtype"] == "f32" else 2
+    out = []
+    for method, kw in cfg["calls"]:
+        plans = plans_for(method, [cfg["S"]] * cfg["L"], kw)
+        out.append(P.algorithmic_bytes(plans, batch, cfg["H"], cfg["D"], e))
+    return out
+
+
+# --------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(prefix="kvc_clocks_", suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu_index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        try:
+            self.proc.terminate()
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, reasons = [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1]))
+                    out["sm_max_mhz"] = float(f[2])
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val == "Active":
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out["sm_mhz"] = statistics.median(sm)
+            out["samples"] = len(sm)
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+# --------------------------------------------------------------------------- synthetic cache
+def make_cache(cfg, batch, device, seed):
+    """BASELINE.md §3 spread-norm synthetic cache, generated on the device, layer by layer."""
+    import torch
+
+    dt = {"bf16": torch.bfloat16, "f16": torch.float16, "f32": torch.float32}[cfg["dtype"]]
+    H, S, D = cfg["H"], cfg["S"], cfg["D"]
+    kv = []
+    for layer in range(cfg["L"]):
+        g = torch.Generator(device=device).manual_seed(seed + layer)
+        k = torch.randn(batch, H, S, D, generator=g, device=device)
+        k *= torch.exp(0.35 * torch.randn(batch, H, S, 1, generator=g, device=device))
+        k[:, :, :4] *= 0.1
+        v = torch.randn(batch, H, S, D, generator=g, device=device)
+        kv.append((k.to(dt), v.to(dt)))
+        del k, v
+    return kv
+
+
+# --------------------------------------------------------------------------- CPU port (oracle) leg
+def cpu_sample_batch(cfg, requested, cap):
+    from oracle import kvc_oracle_c as OC
+
+    if requested > 0:
+        return min(requested, cap)
+    return max(1, min(cap, 8, -(-OC.max_threads() // cfg["H"])))
+
+
+def cpu_port_run(cfg, sample_batch, steps, warmup, host_layers=None, threads=0):
+    """Time oracle/kvc_oracle.c (the reference's algorithm, OpenMP over (b,h)) on a bounded sample."""
+    import numpy as np
+    import torch
+
+    from oracle import kvc_oracle as O
+    from oracle import kvc_oracle_c as OC
+
+    threads = threads or OC.max_threads()
+    dtype = cfg["dtype"]
+    if host_layers is None:
+        tdt = {"bf16": torch.bfloat16, "f16": torch.float16, "f32": torch.float32}[dtype]
+        g = torch.Generator().manual_seed(1234)
+        host_layers = []
+        for _ in range(cfg["L"]):
+            k = torch.randn(sample_batch, cfg["H"], cfg["S"], cfg["D"], generator=g)
+            k *= torch.exp(0.35 * torch.randn(sample_batch, cfg["H"], cfg["S"], 1, generator=g))
+            k[:, :, :4] *= 0.1
+            v = torch.randn(sample_batch, cfg["H"], cfg["S"], cfg["D"], generator=g)
+            host_layers.append((k.to(tdt), v.to(tdt)))
+
+    def as_np(t):
+        return t.view(torch.int16).numpy().view(np.uint16) if dtype == "bf16" else t.numpy()
+
+    layers = [(as_np(k), as_np(v)) for k, v in host_layers]
+    e = 4 if dtype == "f32" else 2
+    step_bytes = 0
+    for method, kw in cfg["calls"]:
+        step_bytes += O.algorithmic_bytes(O.METHODS[method](layers, dtype, select=None, **kw), e)
+    times = []
+    for it in range(warmup + steps):
+        t = 0.0
+        for method, kw in cfg["calls"]:
+            _, _, dt_s = OC.run_method(method, layers, dtype, nthreads=threads, **kw)
+            t += dt_s
+        if it >= warmup:
+            times.append(t)
+    mean_s = sum(times) / len(times)
+    return dict(gbs=step_bytes / mean_s / 1e9, seconds_per_step=mean_s, threads=threads, step_bytes=step_bytes,
+                sample=f"{cfg['L']} layers x (B={sample_batch}, H={cfg['H']}, S={cfg['S']}, D={cfg['D']}) {dtype}, "
+                       f"{len(times)} timed passes of the same calls")
+
+
+# --------------------------------------------------------------------------- reference arm
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = dict(CONFIGS[args.config])
+    steps = max(1, min(args.steps, 5))
+    sb = cpu_sample_batch(cfg, args.cpu_sample_batch, cfg["B"])
+    res = cpu_port_run(cfg, sb, steps, min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": "kv_compress_step_throughput", "value": round(res["gbs"], 3), "unit": "GB/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
+        "ms_per_step": round(res["seconds_per_step"] * 1e3, 3), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": cfg["dtype"], "data": "synthetic",
+        "config": workload_config(cfg, args.config, sb, 1),
+        "cpu_baseline": {"value": round(res["gbs"], 3), "unit": "GB/s", "cores": res["threads"], "kind": "port",
+                         "sample": res["sample"]},
+        "e2e": {"value": round(res["gbs"], 3), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "the reference is pure Python on torch (no native sources to compile): this arm times the C port of "
+                "its algorithm (oracle/kvc_oracle.c: norm -> full sort -> take k -> sort -> gather) on all host threads",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(cfg, name, batch, n_gpus):
+    calls = "; ".join(f"{m}({', '.join(f'{k}={v}' for k, v in kw.items())})" for m, kw in cfg["calls"])
+    return {
+        "workload": f"{name}: {calls} on a synthetic {cfg['model_shape']}-shaped {cfg['dtype']} KV cache, "
+                    f"{cfg['L']} layers x (B={batch}, H={cfg['H']}, S={cfg['S']}, D={cfg['D']}) per GPU",
+        "global_batch": batch * n_gpus, "seq_len": cfg["S"], "layers": cfg["L"], "kv_heads": cfg["H"],
+        "head_dim": cfg["D"], "parallelism": f"batch-sharded x{n_gpus}, no collective on the hot path",
+        "l2_policy": "inputs (>= 5 GB per step) are far larger than the 126 MB L2; no explicit flush",
+    }
+
+
+# --------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import kvcompress
+    from kvcompress import _engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the compress path has no CPU fallback")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    _engine.load_library()
+
+    cfg = dict(CONFIGS[args.config])
+    B = args.batch or cfg["B"]
+    e = 4 if cfg["dtype"] == "f32" else 2
+    fns = [(kvcompress.get_compress_fn(m), kw) for m, kw in cfg["calls"]]
+    per_call_bytes = call_bytes(cfg, B)
+    step_bytes = sum(per_call_bytes)
+
+    kv = make_cache(cfg, B, device, seed=1234 + 1000 * rank)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def one_step(events=None):
+        outs = []
+        for i, (fn, kw) in enumerate(fns):
+            if events is not None:
+                events[i][0].record()
+            outs.append(fn(kv, **kw))
+            if events is not None:
+                events[i][1].record()
+        return outs
+
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+    barrier()
+
+    K = args.steps
+    ev = [[(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in fns] for _ in range(K)]
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches0 = _engine.launch_count()
+    barrier()
+    t_begin.record()
+    for s in range(K):
+        one_step(ev[s])
+    t_end.record()
+    barrier()
+    launches = _engine.launch_count() - launches0
+    clocks = sampler.stop()
+    total_ms = t_begin.elapsed_time(t_end)
+    per_call_ms = [[a.elapsed_time(b) for (a, b) in step] for step in ev]
+    if world > 1:
+        t = torch.tensor([total_ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / K
+    value = step_bytes * world / (ms_per_step * 1e-3) / 1e9
+
+    # dominant kernel: the call with the most device time
+    mean_call_ms = [statistics.mean(x[i] for x in per_call_ms) for i in range(len(fns))]
+    min_call_ms = [min(x[i] for x in per_call_ms) for i in range(len(fns))]
+    dom = max(range(len(fns)), key=lambda i: mean_call_ms[i])
+    peak, peak_src = measured_peak()
+    achieved = per_call_bytes[dom] / (mean_call_ms[dom] * 1e-3) / 1e9
+    traffic = profiled_traffic(args.config)
+    roofline = {
+        "bound": "hbm", "kernel": f"kvc_fused_kernel ({cfg['calls'][dom][0]})", "achieved": round(achieved, 1),
+        "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "frac_of_nominal_8000": round(achieved / 8000.0, 4),
+        "peak_source": peak_src, "algorithmic_bytes_per_launch": per_call_bytes[dom],
+        "launch_us_mean": round(mean_call_ms[dom] * 1e3, 1), "launch_us_min": round(min_call_ms[dom] * 1e3, 1),
+        "traffic": traffic,
+    }
+    per_call = {
+        cfg["calls"][i][0]: {
+            "us_mean": round(mean_call_ms[i] * 1e3, 1), "us_min": round(min_call_ms[i] * 1e3, 1),
+            "algorithmic_bytes": per_call_bytes[i],
+            "gbs": round(per_call_bytes[i] / (mean_call_ms[i] * 1e-3) / 1e9, 1),
+            "frac_of_peak": round(per_call_bytes[i] / (mean_call_ms[i] * 1e-3) / 1e9 / peak, 4),
+        } for i in range(len(fns))
+    }
+
+    # ------------------------------------------------------------------ e2e: host-resident cache
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(cfg, B, kv, fns, step_bytes, args, device, world, barrier)
+    # ------------------------------------------------------------------ CPU baseline (rank 0, N=1)
+    cpu = None
+    if not args.no_cpu_baseline and world == 1 and rank == 0:
+        sb = cpu_sample_batch(cfg, args.cpu_sample_batch, B)
+        host_layers = [(k[:sb].cpu(), v[:sb].cpu()) for k, v in kv]
+        del kv
+        torch.cuda.empty_cache()
+        res = cpu_port_run(cfg, sb, steps=2, warmup=1, host_layers=host_layers)
+        cpu = {"value": round(res["gbs"], 3), "unit": "GB/s", "cores": res["threads"], "kind": "port",
+               "sample": res["sample"], "seconds_per_sample_step": round(res["seconds_per_step"], 4)}
+
+    if rank == 0:
+        line = {
+            "metric": "kv_compress_step_throughput", "value": round(value, 1), "unit": "GB/s", "n_gpus": world,
+            "steps": K, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": cfg["dtype"], "data": "synthetic",
+            "config": workload_config(cfg, args.config, B, world),
+            "us_per_step": round(ms_per_step * 1e3, 1), "tok_per_s": round(B * world / (ms_per_step * 1e-3), 1),
+            "algorithmic_bytes_per_step": step_bytes * world, "per_call": per_call, "roofline": roofline,
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "library": os.path.relpath(_engine.library_path(), ROOT),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_e2e(cfg, B, kv, fns, step_bytes, args, device, world, barrier):
+    """The same step with the cache resident in (pinned) HOST memory: every step copies each slab of
+    `slab` streams to the GPU, compresses it through the public API and copies the compressed cache
+    back; H2D of slab i+1 and D2H of slab i-1 overlap the compress of slab i (three streams)."""
+    import torch
+    import torch.distributed as dist
+
+    slab = max(1, min(args.e2e_slab, B))
+    n_slabs = B // slab
+    if n_slabs * slab != B:
+        slab, n_slabs = B, 1
+    # one pinned slab is reused for every slab of the step (same bytes cross PCIe; the content is synthetic)
+    host_in = [(k[:slab].cpu().pin_memory(), v[:slab].cpu().pin_memory()) for k, v in kv]
+    dev_in = [[(torch.empty_like(k[:slab]), torch.empty_like(v[:slab])) for k, v in kv] for _ in range(2)]
+    probe = [fn([(k[:slab], v[:slab]) for k, v in kv], **kw) for fn, kw in fns]
+    host_out = [[[(torch.empty(k.shape, dtype=k.dtype).pin_memory(), torch.empty(v.shape, dtype=v.dtype).pin_memory())
+                  for k, v in out] for out in probe] for _ in range(2)]
+    h2d_bytes = n_slabs * sum(k.numel() * k.element_size() + v.numel() * v.element_size() for k, v in host_in)
+    d2h_bytes = n_slabs * sum(k.numel() * k.element_size() + v.numel() * v.element_size()
+                              for out in probe for k, v in out)
+    del probe
+    s_h2d, s_comp, s_d2h = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+
+    def step():
+        keep = []
+        comp_done = [None] * n_slabs
+        d2h_done = [None] * n_slabs
+        for i in range(n_slabs):
+            buf = dev_in[i % 2]
+            with torch.cuda.stream(s_h2d):
+                if i >= 2:
+                    s_h2d.wait_event(comp_done[i - 2])  # the device slab is free again
+                for (hk, hv), (dk, dv) in zip(host_in, buf):
+                    dk.copy_(hk, non_blocking=True)
+                    dv.copy_(hv, non_blocking=True)
+                up = torch.cuda.Event()
+                up.record()
+            with torch.cuda.stream(s_comp):
+                s_comp.wait_event(up)
+                outs = [fn(buf, **kw) for fn, kw in fns]
+                comp_done[i] = torch.cuda.Event()
+                comp_done[i].record()
+            keep.append(outs)
+            with torch.cuda.stream(s_d2h):
+                s_d2h.wait_event(comp_done[i])
+                if i >= 2:
+                    s_d2h.wait_event(d2h_done[i - 2])
+                for out, hout in zip(outs, host_out[i % 2]):
+                    for (k, v), (hk, hv) in zip(out, hout):
+                        hk.copy_(k, non_blocking=True)
+                        hv.copy_(v, non_blocking=True)
+                d2h_done[i] = torch.cuda.Event()
+                d2h_done[i].record()
+        torch.cuda.synchronize()
+        return keep
+
+    for _ in range(2):
+        step()
+    barrier()
+    steps = max(2, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    barrier()
+    dt_s = (time.perf_counter() - t0) / steps
+    if world > 1:
+        t = torch.tensor([dt_s], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt_s = float(t.item())
+    return {"value": round(step_bytes * world / dt_s / 1e9, 2), "unit": "GB/s", "h2d_bytes_per_step": h2d_bytes,
+            "d2h_bytes_per_step": d2h_bytes, "ms_per_step": round(dt_s * 1e3, 2), "steps": steps,
+            "how": f"pinned host cache -> {n_slabs} slabs of {slab} streams: H2D, compress via the public API, "
+                   f"D2H of the compressed cache; 3-stream pipeline; wall clock around synchronised steps"}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -169,17 +169,6 @@ def selection_is_valid(sel: np.ndarray, lo: np.ndarray, hi: np.ndarray, largest:
 
 
 # ----------------------------------------------------------------------------- row builders
-def _rows(B: int, H: int, *parts) -> np.ndarray:
-    """Concatenate row-index parts (1-D shared across (b,h), or [B,H,n]) -> int64 [B,H,C]."""
-    out = []
-    for p in parts:
-        p = np.asarray(p, dtype=np.int64)
-        if p.ndim == 1:
-            p = np.broadcast_to(p, (B, H, p.shape[0]))
-        out.append(p)
-    return np.concatenate(out, axis=-1) if out else np.zeros((B, H, 0), dtype=np.int64)
-
-
 def _head(S: int, n: int) -> np.ndarray:
     return np.arange(S)[:n]  # x[:, :, :n]
 
@@ -188,22 +177,70 @@ def _last(S: int, n: int) -> np.ndarray:
     return np.arange(S)[-n:]  # x[:, :, -n:]   (-0: is everything)
 
 
-class LayerResult:
-    """What a method did to one layer: untouched (rows is None), or the kept rows; `is_view` marks
-    the paths where the reference returns a slice view instead of a fresh tensor."""
+_NONE = np.zeros(0, dtype=np.int64)
 
-    def __init__(self, rows: Optional[np.ndarray], is_view: bool = False, region: Tuple[int, int] = (0, 0),
-                 k_sel: int = 0, mode: str = "none", pool_kernel: int = 1):
-        self.rows = rows
-        self.is_view = is_view
-        self.region = region    # [lo, hi) the selection ran over
+
+class LayerResult:
+    """What a method does to one layer: untouched, or   head rows + selected rows + tail rows.
+
+    `head` / `tail` are 1-D row lists shared by every (b,h) (a prefix and a suffix of the layer);
+    `sel` is the [B,H,k_sel] selection in absolute rows (None while deferred); `is_view` marks the
+    paths where the reference returns a slice view instead of a fresh tensor."""
+
+    def __init__(self, shape=None, head=_NONE, tail=_NONE, sel=None, region=(0, 0), k_sel=0, mode="none",
+                 pool_kernel=1, is_view=False, untouched=False):
+        self.untouched = untouched
+        self.shape = shape          # (B, H, S, D)
+        self.head = np.asarray(head, dtype=np.int64)
+        self.tail = np.asarray(tail, dtype=np.int64)
+        self.sel = sel
+        self.region = region        # [lo, hi) the selection runs over
         self.k_sel = k_sel
-        self.mode = mode        # "none" | "low" | "high" | "snapkv" | "random"
+        self.mode = mode            # "none" | "low" | "high" | "snapkv" | "random"
         self.pool_kernel = pool_kernel
+        self.is_view = is_view
 
     @property
-    def untouched(self) -> bool:
-        return self.rows is None
+    def out_len(self) -> int:
+        return self.shape[2] if self.untouched else len(self.head) + self.k_sel + len(self.tail)
+
+    @property
+    def rows(self) -> Optional[np.ndarray]:
+        """int64 [B, H, C] kept rows, ascending by construction."""
+        if self.untouched:
+            return None
+        B, H = self.shape[0], self.shape[1]
+        parts = [np.broadcast_to(self.head, (B, H, len(self.head)))]
+        if self.k_sel > 0:
+            if self.sel is None:
+                raise RuntimeError("selection deferred: run it with a backend first")
+            parts.append(np.asarray(self.sel, dtype=np.int64))
+        parts.append(np.broadcast_to(self.tail, (B, H, len(self.tail))))
+        return np.concatenate(parts, axis=-1)
+
+
+def _same(K) -> LayerResult:
+    return LayerResult(shape=K.shape, untouched=True)
+
+
+def numpy_select(K: np.ndarray, dtype: str, lo: int, hi: int, k: int, mode: str, pool_kernel: int = 1) -> np.ndarray:
+    """norm -> (score) -> k best of rows [lo, hi), ascending absolute rows [B,H,k]."""
+    norms = key_norms(K[:, :, lo:hi], dtype)
+    if mode == "low":
+        return lowest_k(norms, k) + lo
+    if mode == "high":
+        return highest_k(norms, k) + lo
+    if mode == "snapkv":
+        return highest_k(snapkv_scores(norms, dtype, pool_kernel), k) + lo
+    raise ValueError(mode)
+
+
+def _selected(K, dtype, head, lo, hi, k, tail, mode, select, pool_kernel=1) -> LayerResult:
+    sel = None
+    if k > 0 and select is not None:
+        sel = select(K, dtype, lo, hi, k, mode, pool_kernel)
+    return LayerResult(shape=K.shape, head=head, tail=tail, sel=sel, region=(lo, hi), k_sel=k,
+                       mode=mode if k > 0 else "none", pool_kernel=pool_kernel)
 
 
 def _shape(K: np.ndarray):
@@ -211,129 +248,127 @@ def _shape(K: np.ndarray):
 
 
 # ----------------------------------------------------------------------------- the eight methods
-def l2_compress(layers, dtype, keep_ratio=1.0, prune_after=1000, skip_layers=(0, 1)) -> List[LayerResult]:
+# Every method takes `select=`: the routine that ranks the selection region (default: numpy above).
+# `select=None` defers the ranking and returns only the per-layer descriptors (used to drive the C
+# port in oracle/kvc_oracle.c and to compute output lengths without touching the data).
+def l2_compress(layers, dtype, keep_ratio=1.0, prune_after=1000, skip_layers=(0, 1), select=numpy_select):
     """reference methods/l2_compress.py:18-92."""
     out = []
     for li, (K, _V) in enumerate(layers):
-        B, H, S, _ = _shape(K)
+        S = K.shape[2]
         keep = ceil(keep_ratio * S)
         if keep_ratio >= 1.0 or S <= prune_after or li in skip_layers or keep >= S:  # :48-65
-            out.append(LayerResult(None))
+            out.append(_same(K))
             continue
-        sel = lowest_k(key_norms(K, dtype), keep)  # :70-79
-        out.append(LayerResult(sel, region=(0, S), k_sel=keep, mode="low"))
+        out.append(_selected(K, dtype, _NONE, 0, S, keep, _NONE, "low", select))  # :70-88
     return out
 
 
 def fix_size_l2_compress(layers, dtype, fix_kv_size=1024, keep_ratio=0.0, strategy="keep_low", skip_layers=(0, 1),
-                         random_rows=None) -> List[LayerResult]:
+                         random_rows=None, select=numpy_select):
     """reference methods/fix_size_l2.py:15-154.  For strategy="random" the caller passes the rows the
     torch generator produced (``random_rows[layer] = [B,H,k]``) — RNG streams are torch's."""
     out = []
     for li, (K, _V) in enumerate(layers):
-        B, H, S, _ = _shape(K)
+        S = K.shape[2]
         if S <= fix_kv_size or li in skip_layers:  # :69-74
-            out.append(LayerResult(None))
+            out.append(_same(K))
             continue
         protected = min(int(fix_kv_size * keep_ratio), S)  # :79-80
         zone_end = S - protected
         budget = fix_kv_size - protected
         if budget <= 0:  # :88-93
-            out.append(LayerResult(_rows(B, H, _last(S, protected)), is_view=True))
+            out.append(LayerResult(shape=K.shape, tail=_last(S, protected), is_view=True))
             continue
         if zone_end <= budget:  # :95-97
-            out.append(LayerResult(None))
+            out.append(_same(K))
             continue
-        zone = K[:, :, :zone_end]
+        tail = _last(S, protected) if protected > 0 else _NONE  # :141-150
         if strategy == "keep_low":  # :104-108
-            sel, mode = lowest_k(key_norms(zone, dtype), budget), "low"
+            out.append(_selected(K, dtype, _NONE, 0, zone_end, budget, tail, "low", select))
         elif strategy == "keep_high":  # :110-114
-            sel, mode = highest_k(key_norms(zone, dtype), budget), "high"
-        elif strategy == "random":  # :116-124
-            sel, mode = np.sort(np.asarray(random_rows[li], dtype=np.int64), axis=-1), "random"
+            out.append(_selected(K, dtype, _NONE, 0, zone_end, budget, tail, "high", select))
+        elif strategy == "random":  # :116-124, :129
+            rows = np.sort(np.asarray(random_rows[li], dtype=np.int64), axis=-1)
+            out.append(LayerResult(shape=K.shape, tail=tail, sel=rows, region=(0, zone_end), k_sel=budget, mode="random"))
         else:
             raise ValueError(f"Unknown strategy: {strategy}")  # :126
-        tail = _last(S, protected) if protected > 0 else np.zeros(0, dtype=np.int64)  # :141-150
-        out.append(LayerResult(_rows(B, H, sel, tail), region=(0, zone_end), k_sel=budget, mode=mode))
     return out
 
 
-def streaming_llm_compress(layers, dtype, start_size=4, recent_size=508, skip_layers=()) -> List[LayerResult]:
+def streaming_llm_compress(layers, dtype, start_size=4, recent_size=508, skip_layers=(), select=None):
     """reference methods/streaming_llm.py:19-111."""
     out = []
     for li, (K, _V) in enumerate(layers):
-        B, H, S, _ = _shape(K)
+        S = K.shape[2]
         if S <= start_size + recent_size or li in skip_layers:  # :88-93
-            out.append(LayerResult(None))
+            out.append(_same(K))
             continue
-        out.append(LayerResult(_rows(B, H, _head(S, start_size), _last(S, recent_size))))  # :99-107
+        out.append(LayerResult(shape=K.shape, head=_head(S, start_size), tail=_last(S, recent_size)))  # :99-107
     return out
 
 
-def evict_for_space(layers, dtype, num_coming, start_size=4, recent_size=508, skip_layers=()) -> List[LayerResult]:
+def evict_for_space(layers, dtype, num_coming, start_size=4, recent_size=508, skip_layers=(), select=None):
     """reference methods/streaming_llm.py:114-170."""
     out = []
     for li, (K, _V) in enumerate(layers):
-        B, H, S, _ = _shape(K)
+        S = K.shape[2]
         if S + num_coming <= start_size + recent_size or li in skip_layers:  # :147-152
-            out.append(LayerResult(None))
+            out.append(_same(K))
             continue
         recent = recent_size - num_coming  # :155-157
         if recent <= 0:
             recent = recent_size
-        out.append(LayerResult(_rows(B, H, _head(S, start_size), _last(S, recent))))
+        out.append(LayerResult(shape=K.shape, head=_head(S, start_size), tail=_last(S, recent)))
     return out
 
 
-def recent_only_compress(layers, dtype, window_size=512, skip_layers=(0, 1)) -> List[LayerResult]:
+def recent_only_compress(layers, dtype, window_size=512, skip_layers=(0, 1), select=None):
     """reference methods/recent_only.py:16-70 (returns views)."""
     out = []
     for li, (K, _V) in enumerate(layers):
-        B, H, S, _ = _shape(K)
+        S = K.shape[2]
         if S <= window_size or li in skip_layers:  # :57-62
-            out.append(LayerResult(None))
+            out.append(_same(K))
             continue
-        out.append(LayerResult(_rows(B, H, _last(S, window_size)), is_view=True))  # :65-66
+        out.append(LayerResult(shape=K.shape, tail=_last(S, window_size), is_view=True))  # :65-66
     return out
 
 
-def h2o_l2_compress(layers, dtype, start_size=4, heavy_hitter_size=64, recent_size=444, skip_layers=()) -> List[LayerResult]:
+def h2o_l2_compress(layers, dtype, start_size=4, heavy_hitter_size=64, recent_size=444, skip_layers=(),
+                    select=numpy_select):
     """reference methods/h2o_l2.py:25-153."""
     out = []
     for li, (K, _V) in enumerate(layers):
-        B, H, S, _ = _shape(K)
+        S = K.shape[2]
         if S <= start_size + heavy_hitter_size + recent_size or li in skip_layers:  # :81-86
-            out.append(LayerResult(None))
+            out.append(_same(K))
             continue
         lo, hi = start_size, S - recent_size  # :95-96
         if hi <= lo:  # :99-109
-            out.append(LayerResult(_rows(B, H, _head(S, start_size), _last(S, recent_size))))
+            out.append(LayerResult(shape=K.shape, head=_head(S, start_size), tail=_last(S, recent_size)))
             continue
         k = min(heavy_hitter_size, hi - lo)  # :125
-        sel = lowest_k(key_norms(K[:, :, lo:hi], dtype), k) + lo  # :122-132
-        out.append(LayerResult(_rows(B, H, _head(S, start_size), sel, _last(S, recent_size)),
-                               region=(lo, hi), k_sel=k, mode="low"))
+        out.append(_selected(K, dtype, _head(S, start_size), lo, hi, k, _last(S, recent_size), "low", select))
     return out
 
 
-def snapkv_lite_compress(layers, dtype, observation_window=32, keep_size=512, pooling_kernel=5,
-                         skip_layers=()) -> List[LayerResult]:
+def snapkv_lite_compress(layers, dtype, observation_window=32, keep_size=512, pooling_kernel=5, skip_layers=(),
+                         select=numpy_select):
     """reference methods/snapkv_lite.py:24-154."""
     out = []
     for li, (K, _V) in enumerate(layers):
-        B, H, S, _ = _shape(K)
+        S = K.shape[2]
         P = S - observation_window  # :83
         if S <= keep_size or li in skip_layers or P <= 0:  # :70-86
-            out.append(LayerResult(None))
+            out.append(_same(K))
             continue
         k = min(keep_size - observation_window, P)  # :125-126
         if k <= 0:  # :128-131
-            out.append(LayerResult(_rows(B, H, _last(S, observation_window)), is_view=True))
+            out.append(LayerResult(shape=K.shape, tail=_last(S, observation_window), is_view=True))
             continue
-        scores = snapkv_scores(key_norms(K[:, :, :P], dtype), dtype, pooling_kernel)  # :96-121
-        sel = highest_k(scores, k)  # :134-137
-        out.append(LayerResult(_rows(B, H, sel, _last(S, observation_window)), region=(0, P), k_sel=k,
-                               mode="snapkv", pool_kernel=pooling_kernel))
+        out.append(_selected(K, dtype, _NONE, 0, P, k, _last(S, observation_window), "snapkv", select,
+                             pool_kernel=pooling_kernel))  # :96-150
     return out
 
 
@@ -351,23 +386,22 @@ def pyramid_layer_sizes(num_layers, base_size=512, layer_decay=0.9, min_size=64,
     return sizes
 
 
-def _sinks_middle_recent(K, dtype, target, start) -> LayerResult:
+def _sinks_middle_recent(K, dtype, target, start, select) -> LayerResult:
     """pyramid_kv.py:115-181 and the hard branch of adaptive_l2.py:86-143 share this shape."""
-    B, H, S, _ = _shape(K)
+    S = K.shape[2]
     recent = target // 2
     middle_budget = target - start - recent
     if middle_budget <= 0:  # pyramid :119-124, adaptive :93-98
-        return LayerResult(_rows(B, H, _last(S, target)), is_view=True)
+        return LayerResult(shape=K.shape, tail=_last(S, target), is_view=True)
     lo, hi = start, S - recent
     if hi <= lo:  # pyramid :130-140, adaptive :104-113
-        return LayerResult(_rows(B, H, _head(S, start), _last(S, target - start)))
+        return LayerResult(shape=K.shape, head=_head(S, start), tail=_last(S, target - start))
     k = min(middle_budget, hi - lo)
-    sel = lowest_k(key_norms(K[:, :, lo:hi], dtype), k) + lo
-    return LayerResult(_rows(B, H, _head(S, start), sel, _last(S, recent)), region=(lo, hi), k_sel=k, mode="low")
+    return _selected(K, dtype, _head(S, start), lo, hi, k, _last(S, recent), "low", select)
 
 
 def pyramid_kv_compress(layers, dtype, base_size=512, layer_decay=0.9, min_size=64, profile="exponential",
-                        skip_layers=()) -> List[LayerResult]:
+                        skip_layers=(), select=numpy_select):
     """reference methods/pyramid_kv.py:26-185."""
     sizes = pyramid_layer_sizes(len(layers), base_size, layer_decay, min_size, profile)
     out = []
@@ -375,41 +409,40 @@ def pyramid_kv_compress(layers, dtype, base_size=512, layer_decay=0.9, min_size=
         S = K.shape[2]
         target = sizes[li]
         if S <= target or li in skip_layers:  # :104-109
-            out.append(LayerResult(None))
+            out.append(_same(K))
             continue
-        out.append(_sinks_middle_recent(K, dtype, target, min(4, target // 8)))
+        out.append(_sinks_middle_recent(K, dtype, target, min(4, target // 8), select))
     return out
 
 
 def adaptive_l2_compress(layers, dtype, target_size=512, soft_limit=256, hard_limit=1024, keep_ratio_min=0.3,
-                         keep_ratio_max=0.9, skip_layers=()) -> List[LayerResult]:
+                         keep_ratio_max=0.9, skip_layers=(), select=numpy_select):
     """reference methods/adaptive_l2.py:20-201."""
     out = []
     for li, (K, _V) in enumerate(layers):
-        B, H, S, _ = _shape(K)
+        S = K.shape[2]
         if li in skip_layers or S <= soft_limit:  # :71-77
-            out.append(LayerResult(None))
+            out.append(_same(K))
             continue
         if S > hard_limit:  # :81-145
-            out.append(LayerResult(None) if S <= target_size else _sinks_middle_recent(K, dtype, target_size, 4))
+            out.append(_same(K) if S <= target_size else _sinks_middle_recent(K, dtype, target_size, 4, select))
             continue
         progress = (S - soft_limit) / (hard_limit - soft_limit)  # :150
         ratio = keep_ratio_max - progress * (keep_ratio_max - keep_ratio_min)  # :151
         n = max(int(S * ratio), soft_limit)  # :153-154
         if n >= S:
-            out.append(LayerResult(None))
+            out.append(_same(K))
             continue
         recent = int(n * 0.2)  # :160
         k = n - recent
         if k <= 0:  # :163-168
-            out.append(LayerResult(_rows(B, H, _last(S, n)), is_view=True))
+            out.append(LayerResult(shape=K.shape, tail=_last(S, n), is_view=True))
             continue
         hi = S - recent
         if hi <= k:  # :173-174
-            out.append(LayerResult(None))
+            out.append(_same(K))
             continue
-        sel = lowest_k(key_norms(K[:, :, :hi], dtype), k)  # :180-183
-        out.append(LayerResult(_rows(B, H, sel, _last(S, recent)), region=(0, hi), k_sel=k, mode="low"))
+        out.append(_selected(K, dtype, _NONE, 0, hi, k, _last(S, recent), "low", select))  # :176-197
     return out
 
 
@@ -440,16 +473,19 @@ def apply(layers, results: Sequence[LayerResult]):
 
 
 def out_lengths(layers, results: Sequence[LayerResult]) -> List[int]:
-    return [K.shape[2] if r.untouched else r.rows.shape[-1] for (K, _), r in zip(layers, results)]
+    return [r.out_len for r in results]
 
 
-def selected_part(res: LayerResult, rows: np.ndarray) -> np.ndarray:
-    """The selected (non sink / non tail) positions of `rows`, relative to the region start.
-    The selected block sits right after the sinks: count them as rows < region lo at the front."""
-    lo, hi = res.region
-    n_sink = int(np.sum(res.rows[0, 0] < lo)) if lo > 0 else 0
-    # sinks are the leading rows [0, n_sink) by construction (all < lo)
-    return rows[..., n_sink:n_sink + res.k_sel] - lo
+def algorithmic_bytes(results: Sequence[LayerResult], elem_bytes: int) -> int:
+    """e*B*H*D*(R + 4*C) summed over layers that move data."""
+    total = 0
+    for r in results:
+        if r.untouched or r.is_view:
+            continue
+        B, H, _S, D = r.shape
+        region = (r.region[1] - r.region[0]) if (r.k_sel > 0 and r.mode != "random") else 0
+        total += elem_bytes * B * H * D * (region + 4 * r.out_len)
+    return total
 
 
 def key_interval(K: np.ndarray, dtype: str, res: LayerResult, rel_tol: float = REL_TOL):
@@ -471,23 +507,23 @@ def check_layer(K: np.ndarray, dtype: str, res: LayerResult, got_rows: np.ndarra
              "identical_heads": heads whose rows equal the oracle's exactly, "heads": B*H}."""
     want = res.rows
     got_rows = np.asarray(got_rows, dtype=np.int64)
-    if got_rows.shape != want.shape:
-        return {"valid": False, "identical_heads": 0, "heads": want.shape[0] * want.shape[1], "why": "shape"}
     heads = want.shape[0] * want.shape[1]
+    if got_rows.shape != want.shape:
+        return {"valid": False, "identical_heads": 0, "heads": heads, "why": "shape"}
     same = np.all(got_rows == want, axis=-1)
     info = {"valid": True, "identical_heads": int(same.sum()), "heads": heads}
     if res.mode in ("none", "random") or res.k_sel == 0:
         info["valid"] = bool(same.all())
         return info
     lo, _hi = res.region
-    n_sink = int(np.sum(want[0, 0] < lo)) if lo > 0 else 0
+    n_head = len(res.head)
     fixed = np.ones(want.shape[-1], dtype=bool)
-    fixed[n_sink:n_sink + res.k_sel] = False
+    fixed[n_head:n_head + res.k_sel] = False
     if not np.array_equal(got_rows[..., fixed], want[..., fixed]):
         info.update(valid=False, why="sink/tail rows differ")
         return info
     a, b = key_interval(K, dtype, res, rel_tol)
-    sel = got_rows[..., n_sink:n_sink + res.k_sel] - lo
+    sel = got_rows[..., n_head:n_head + res.k_sel] - lo
     ok = selection_is_valid(sel, a, b, largest=res.mode in ("high", "snapkv"))
     info["valid"] = bool(ok.all())
     if not info["valid"]:

@@ -1,0 +1,310 @@
+"""-m gpu: the sm_100a path (through the drop-in Python API and the C ABI) against the oracle,
+the committed reference golden vectors, and size-independent properties at BASELINE shapes."""
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+import kvcompress
+from gpu_util import TORCH_DTYPE, kv_to_torch, to_numpy, to_torch
+from kvcompress import _engine
+from kvcompress import _planner as P
+from oracle import kvc_oracle as O
+from test_planner import plan_for
+
+pytestmark = pytest.mark.gpu
+
+ALL = cases.all_cases()
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _needs_cuda():
+    assert torch.cuda.is_available(), "-m gpu tests need a CUDA device"
+    _engine.load_library()
+
+
+def gather_rows(x: torch.Tensor, rows: torch.Tensor) -> torch.Tensor:
+    return torch.gather(x, 2, rows.long().unsqueeze(-1).expand(-1, -1, -1, x.size(3)))
+
+
+@pytest.mark.parametrize("case", ALL, ids=[c["name"] for c in ALL])
+def test_golden_case(case, golden):
+    """Every golden case: lengths / aliasing as the reference, kept rows valid under the tie-aware rule
+    (identical to the oracle for fp32), K/V bit-exact gathers of the input."""
+    data, manifest = golden
+    meta = manifest[case["name"]]
+    dtype = case["dtype"]
+    layers = cases.case_cache(case)
+    kv = kv_to_torch(layers, dtype)
+    launches0 = _engine.launch_count()
+    out = kvcompress.get_compress_fn(case["method"])(kv, **case["kwargs"])
+    n_launch = _engine.launch_count() - launches0
+    results = O.METHODS[case["method"]](layers, dtype, **case["kwargs"])
+    assert [k.size(2) for k, _ in out] == meta["lengths"]
+    n_gather = 0
+    for li, ((k_in, v_in), (k_out, v_out), res) in enumerate(zip(kv, out, results)):
+        if meta["untouched"][li]:
+            assert k_out is k_in and v_out is v_in
+            continue
+        if meta["view"][li]:
+            assert k_out._is_view() and v_out._is_view()  # aliases the input like the reference
+        else:
+            n_gather += 1
+            assert k_out.is_contiguous() and v_out.is_contiguous()
+            assert k_out.dtype == k_in.dtype and k_out.device == k_in.device
+        want = torch.from_numpy(res.rows).cuda()
+        if res.mode in ("none",) or res.k_sel == 0:
+            assert torch.equal(k_out, gather_rows(k_in, want)) and torch.equal(v_out, gather_rows(v_in, want))
+    assert n_launch == (1 if n_gather else 0), "all gathered layers of a call must share ONE launch"
+
+    # kept rows, through the C ABI's idx_out
+    plans = plan_for(case["method"], case["seq_lens"], case["kwargs"])
+    out2, idx = _engine.run_plans(kv, plans, return_indices=True)
+    for li, res in enumerate(results):
+        if plans[li].kind != P.GATHER:
+            continue
+        rows = idx[li]
+        k_in, v_in = kv[li]
+        # gathered K/V are bit-exact copies of the rows the kernel reports
+        assert torch.equal(out2[li][0], gather_rows(k_in, rows)) and torch.equal(out2[li][1], gather_rows(v_in, rows))
+        assert torch.equal(out2[li][0], out[li][0]) and torch.equal(out2[li][1], out[li][1])  # deterministic
+        info = O.check_layer(layers[li][0], dtype, res, rows.cpu().numpy())
+        assert info["valid"], (case["name"], li, info)
+        if dtype == "f32" and case["style"] != "ties":
+            assert info["identical_heads"] == info["heads"], (case["name"], li, info)
+            ref_rows = data[f"{case['name']}|L{li}"].astype(np.int64)
+            assert np.array_equal(rows.cpu().numpy(), ref_rows)  # == the reference's own kept rows
+        else:
+            # ties -> lowest index is exactly the oracle's rule; allow only rounding-boundary differences
+            assert info["identical_heads"] >= 0.98 * info["heads"], (case["name"], li, info)
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16", "f16"])
+@pytest.mark.parametrize("D", [16, 24, 64, 80, 96, 128, 256])
+def test_key_norms(dtype, D):
+    """K1: fp32 norms within 1e-6 relative of the float64 norm (north_star), rounded once to the dtype."""
+    if (D * (4 if dtype == "f32" else 2)) % 16:
+        pytest.skip("row not 16-byte aligned")
+    layers = cases.make_cache(7 + D, [777], 2, 3, D, dtype, "spread")
+    K = layers[0][0]
+    k = to_torch(K, dtype)
+    got = _engine.key_norms(k)
+    assert got.dtype == k.dtype and got.shape == (2, 3, 777)
+    exact = O.exact_norms(K, dtype)
+    gotf = got.float().cpu().numpy()
+    if dtype == "f32":
+        assert np.max(np.abs(gotf - exact) / exact) <= 1e-6
+    else:
+        want = O.key_norms(K, dtype)
+        assert np.mean(gotf == want) > 0.999
+        lo, hi = O.key_norm_interval(K, dtype)
+        assert np.all((gotf >= lo) & (gotf <= hi))
+    # sub-range + strided (transposed [B,S,H,D] storage) input
+    base = k.permute(0, 2, 1, 3).contiguous().permute(0, 2, 1, 3)
+    assert not base.is_contiguous()
+    got2 = _engine.key_norms(base, 5, 700)
+    assert torch.equal(got2, got[:, :, 5:700])
+
+
+@pytest.mark.parametrize("dtype", ["f32", "bf16", "f16"])
+@pytest.mark.parametrize("n,k", [(1, 1), (33, 5), (1000, 1), (1000, 999), (1000, 1000), (4097, 512), (32768, 480),
+                                 (50000, 3000)])
+def test_select_matches_stable_sort(dtype, n, k):
+    """K2: exactly the stable-sort answer, for both directions, with heavy ties and negative scores."""
+    rng = np.random.default_rng(n * 31 + k)
+    rows = 5
+    base = rng.standard_normal((rows, n)).astype(np.float32)
+    base[1] = np.round(base[1] * 2) / 2          # few distinct values -> many ties
+    base[2] = 1.25                               # all equal
+    base[3] = np.abs(base[3]) * 1e-3             # tiny positives
+    base[4, ::7] = -0.0                          # signed zeros mixed with values
+    scores_np = O.store(base, dtype)
+    vals = O.to_f32(scores_np, dtype)
+    t = to_torch(scores_np, dtype)
+    for largest in (False, True):
+        got = _engine.select(t, k, largest=largest).cpu().numpy()
+        # -0.0 sorts below +0.0 in the kernel's total order; mirror that in the oracle keys
+        keyed = np.where(np.signbit(vals) & (vals == 0), -1e-45, vals).astype(np.float64)
+        want = O.highest_k(keyed, k) if largest else O.lowest_k(keyed, k)
+        assert np.array_equal(got, want), (dtype, n, k, largest)
+
+
+def test_strided_and_noncontiguous_inputs():
+    """Inputs living in a larger pre-allocated cache slab (stride_h != S*D) and [B,S,H,D]-stored caches."""
+    torch.manual_seed(0)
+    B, H, S, D, cap = 2, 4, 900, 80, 1024
+    slab_k = torch.randn(B, H, cap, D, device="cuda").to(torch.bfloat16)
+    slab_v = torch.randn(B, H, cap, D, device="cuda").to(torch.bfloat16)
+    kv_view = [(slab_k[:, :, :S], slab_v[:, :, :S])]
+    kv_dense = [(slab_k[:, :, :S].contiguous(), slab_v[:, :, :S].contiguous())]
+    for fn, kw in ((kvcompress.h2o_l2_compress, {}), (kvcompress.streaming_llm_compress, {}),
+                   (kvcompress.snapkv_lite_compress, {})):
+        a, b = fn(kv_view, **kw), fn(kv_dense, **kw)
+        assert torch.equal(a[0][0], b[0][0]) and torch.equal(a[0][1], b[0][1])
+    bshd_k = torch.randn(B, S, H, D, device="cuda").to(torch.bfloat16)
+    bshd_v = torch.randn(B, S, H, D, device="cuda").to(torch.bfloat16)
+    kv_t = [(bshd_k.permute(0, 2, 1, 3), bshd_v.permute(0, 2, 1, 3))]
+    kv_c = [(kv_t[0][0].contiguous(), kv_t[0][1].contiguous())]
+    a, b = kvcompress.h2o_l2_compress(kv_t), kvcompress.h2o_l2_compress(kv_c)
+    assert torch.equal(a[0][0], b[0][0]) and torch.equal(a[0][1], b[0][1])
+    # different K and V strides in the same layer
+    kv_mixed = [(kv_t[0][0], kv_c[0][1])]
+    c = kvcompress.h2o_l2_compress(kv_mixed)
+    assert torch.equal(c[0][0], b[0][0]) and torch.equal(c[0][1], b[0][1])
+
+
+def test_random_strategy_follows_torch_rng_stream():
+    """fix_size_l2 strategy="random": same torch.randperm calls in the same order as the reference
+    (fix_size_l2.py:118-124), so the same generator state gives the same kept rows."""
+    B, H, S, D = 2, 3, 700, 64
+    kv = [(torch.randn(B, H, S, D, device="cuda"), torch.randn(B, H, S, D, device="cuda")) for _ in range(3)]
+    torch.manual_seed(123)
+    out = kvcompress.fix_size_l2_compress(kv, fix_kv_size=256, keep_ratio=0.25, strategy="random", skip_layers=[0])
+    torch.manual_seed(123)
+    for li in (1, 2):
+        zone_end, take = S - 64, 256 - 64
+        picked = torch.stack([torch.stack([torch.randperm(zone_end, device="cuda")[:take] for _ in range(H)])
+                              for _ in range(B)])
+        rows = torch.cat([torch.sort(picked, dim=-1)[0], torch.arange(S - 64, S, device="cuda").expand(B, H, 64)], -1)
+        assert torch.equal(out[li][0], gather_rows(kv[li][0], rows))
+        assert torch.equal(out[li][1], gather_rows(kv[li][1], rows))
+    assert out[0][0] is kv[0][0]
+
+
+def test_more_layers_than_one_launch_holds_and_mixed_groups():
+    """> KVC_MAX_LAYERS_PER_LAUNCH layers are chunked; layers of different shape/dtype are grouped."""
+    S, D = 300, 32
+    kv = [(torch.randn(1, 2, S, D, device="cuda"), torch.randn(1, 2, S, D, device="cuda")) for _ in range(70)]
+    kv.append((torch.randn(2, 1, S, 64, device="cuda").half(), torch.randn(2, 1, S, 64, device="cuda").half()))
+    n0 = _engine.launch_count()
+    out = kvcompress.streaming_llm_compress(kv, start_size=4, recent_size=60)
+    assert _engine.launch_count() - n0 == 3  # 64 + 6 fp32 layers, then the fp16 group
+    for (k, v), (ko, vo) in zip(kv, out):
+        assert torch.equal(ko, torch.cat([k[:, :, :4], k[:, :, -60:]], 2))
+        assert torch.equal(vo, torch.cat([v[:, :, :4], v[:, :, -60:]], 2))
+
+
+def test_runs_on_the_current_stream_without_sync():
+    kv = [(torch.randn(2, 4, 2000, 80, device="cuda").bfloat16(), torch.randn(2, 4, 2000, 80, device="cuda").bfloat16())]
+    want = kvcompress.h2o_l2_compress(kv)
+    torch.cuda.synchronize()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        got = kvcompress.h2o_l2_compress(kv)
+    s.synchronize()
+    assert torch.equal(got[0][0], want[0][0]) and torch.equal(got[0][1], want[0][1])
+
+
+def test_errors():
+    kv = [(torch.randn(1, 2, 700, 12, device="cuda").bfloat16(), torch.randn(1, 2, 700, 12, device="cuda").bfloat16())]
+    with pytest.raises(ValueError, match="multiple of 16"):
+        kvcompress.streaming_llm_compress(kv)
+    kv = [(torch.randn(1, 2, 700, 16, device="cuda").double(), torch.randn(1, 2, 700, 16, device="cuda").double())]
+    with pytest.raises(ValueError, match="not supported"):
+        kvcompress.streaming_llm_compress(kv)
+    kv = [(torch.randn(1, 2, 2000, 16, device="cuda"), torch.randn(1, 2, 2000, 16, device="cuda"))]
+    with pytest.raises(ValueError, match="Unknown strategy: nope"):
+        kvcompress.fix_size_l2_compress(kv, fix_kv_size=512, strategy="nope", skip_layers=[])
+    # fp32 region beyond the on-chip score buffer is reported, not silently mis-handled
+    big = [(torch.zeros(1, 1, 70000, 16, device="cuda"), torch.zeros(1, 1, 70000, 16, device="cuda"))]
+    with pytest.raises(ValueError, match="too large"):
+        kvcompress.h2o_l2_compress(big)
+
+
+# ----------------------------------------------------------------------------------------------
+# BASELINE.json shapes (full head_dim and context, reduced batch): size-independent properties
+def spread_cache(L, B, H, S, D, dtype, seed=1234):
+    """BASELINE.md §3 synthetic input, generated on device."""
+    out = []
+    for layer in range(L):
+        g = torch.Generator(device="cuda").manual_seed(seed + layer)
+        k = torch.randn(B, H, S, D, generator=g, device="cuda")
+        k *= torch.exp(0.35 * torch.randn(B, H, S, 1, generator=g, device="cuda"))
+        k[:, :, :4] *= 0.1
+        v = torch.randn(B, H, S, D, generator=g, device="cuda")
+        out.append((k.to(dtype), v.to(dtype)))
+    return out
+
+
+def torch_key_interval(keys: torch.Tensor, rel=1e-6):
+    n = torch.linalg.vector_norm(keys.double(), dim=-1)
+    lo = (n * (1 - rel)).float().to(keys.dtype).float()
+    hi = (n * (1 + rel)).float().to(keys.dtype).float()
+    return lo, hi
+
+
+def assert_valid_lowest(keys_region: torch.Tensor, sel: torch.Tensor, largest=False):
+    """Tie-aware rule on device: max(lo[selected]) <= min(hi[unselected]) per (b,h); sel ascending."""
+    assert torch.all(sel[..., 1:] > sel[..., :-1])
+    lo, hi = torch_key_interval(keys_region)
+    mask = torch.zeros_like(lo, dtype=torch.bool).scatter_(-1, sel.long(), True)
+    inf = float("inf")
+    if largest:
+        assert torch.all(torch.where(mask, hi, inf).amin(-1) >= torch.where(mask, -inf, lo).amax(-1))
+    else:
+        assert torch.all(torch.where(mask, lo, -inf).amax(-1) <= torch.where(mask, inf, hi).amin(-1))
+
+
+FULL = [
+    ("c2_fix_size", "fix_size_l2", dict(fix_kv_size=512, keep_ratio=0.2, strategy="keep_low"), 4, 2, 32, 4096, 80, torch.bfloat16),
+    ("c2_fix_size_steady", "fix_size_l2", dict(fix_kv_size=512, keep_ratio=0.2), 4, 2, 32, 513, 80, torch.bfloat16),
+    ("c3_h2o", "h2o_l2", dict(start_size=4, heavy_hitter_size=64, recent_size=444), 3, 2, 32, 8192, 80, torch.bfloat16),
+    ("c5_pyramid", "pyramid_kv", dict(base_size=512), 8, 2, 8, 32768, 128, torch.bfloat16),
+    ("c5_adaptive", "adaptive_l2", dict(target_size=512), 2, 2, 8, 32768, 128, torch.bfloat16),
+    ("c1_l2_gpu", "l2_compress", dict(keep_ratio=0.8, prune_after=1000, skip_layers=[0, 1]), 4, 1, 32, 2048, 80, torch.float32),
+    ("fp32_48k", "h2o_l2", dict(start_size=4, heavy_hitter_size=64, recent_size=444), 1, 1, 4, 49152, 64, torch.float32),
+]
+
+
+@pytest.mark.parametrize("name,method,kwargs,L,B,H,S,D,dtype", FULL, ids=[f[0] for f in FULL])
+def test_full_shape_properties(name, method, kwargs, L, B, H, S, D, dtype):
+    kv = spread_cache(L, B, H, S, D, dtype)
+    fn = kvcompress.get_compress_fn(method)
+    out = fn(kv, **kwargs)
+    plans = plan_for(method, [S] * L, kwargs)
+    out2, idx = _engine.run_plans(kv, plans, return_indices=True)
+    for li, p in enumerate(plans):
+        if p.kind == P.KEEP:
+            assert out[li][0] is kv[li][0]
+            continue
+        rows = idx[li]
+        k_in, v_in = kv[li]
+        assert out[li][0].shape == (B, H, p.out_len, D)
+        assert torch.equal(out[li][0], gather_rows(k_in, rows)) and torch.equal(out[li][1], gather_rows(v_in, rows))
+        assert torch.equal(rows[..., :p.sink], torch.arange(p.sink, device="cuda", dtype=torch.int32).expand(B, H, -1))
+        tail = torch.arange(S - p.tail, S, device="cuda", dtype=torch.int32).expand(B, H, -1)
+        assert torch.equal(rows[..., p.sink + p.k_sel:], tail)
+        sel = rows[..., p.sink:p.sink + p.k_sel] - p.sel_lo
+        assert sel.min() >= 0 and sel.max() < p.sel_hi - p.sel_lo
+        assert_valid_lowest(k_in[:, :, p.sel_lo:p.sel_hi], sel)
+    # idempotence: the compressed cache is within budget, a second call returns the same objects
+    again = fn(out, **kwargs)
+    if method not in ("l2_compress", "adaptive_l2"):  # ratio / gradual-zone compression keeps shrinking by design
+        assert all(a[0] is b[0] for a, b in zip(again, out))
+
+
+def test_full_shape_streaming_and_snapkv():
+    kv = spread_cache(3, 2, 32, 4096, 80, torch.bfloat16)
+    out = kvcompress.streaming_llm_compress(kv, start_size=4, recent_size=508)
+    for (k, v), (ko, vo) in zip(kv, out):
+        assert torch.equal(ko, torch.cat([k[:, :, :4], k[:, :, -508:]], 2))
+        assert torch.equal(vo, torch.cat([v[:, :, :4], v[:, :, -508:]], 2))
+    # c4: snapkv_lite at 32K context, Llama-3-8B KV shape; scores restated with torch ops on device
+    kv = spread_cache(2, 2, 8, 32768, 128, torch.bfloat16)
+    plans = plan_for("snapkv_lite", [32768] * 2, dict(observation_window=32, keep_size=512))
+    out, idx = _engine.run_plans(kv, plans, return_indices=True)
+    for li, p in enumerate(plans):
+        k_in, v_in = kv[li]
+        rows = idx[li]
+        assert torch.equal(out[li][0], gather_rows(k_in, rows)) and torch.equal(out[li][1], gather_rows(v_in, rows))
+        pre = torch.linalg.vector_norm(k_in[:, :, :p.sel_hi].float(), dim=-1).to(k_in.dtype)
+        imp = (pre.max(dim=-1, keepdim=True)[0] + 1e-6) - pre
+        pooled = torch.nn.functional.avg_pool1d(imp.reshape(-1, 1, p.sel_hi), 5, 1, 2).reshape(imp.shape).float()
+        sel = rows[..., :p.k_sel].long()
+        mask = torch.zeros_like(pooled, dtype=torch.bool).scatter_(-1, sel, True)
+        lowest_taken = torch.where(mask, pooled, float("inf")).amin(-1)
+        highest_left = torch.where(mask, -float("inf"), pooled).amax(-1)
+        # allow one bf16 ulp: torch's CUDA avg_pool may sum in a different order than the CPU reference
+        assert torch.all(lowest_taken >= highest_left * (1 - 2 ** -7))
+        assert torch.equal(rows[..., p.k_sel:], torch.arange(32768 - 32, 32768, device="cuda", dtype=torch.int32).expand(2, 8, -1))
