@@ -21,9 +21,7 @@ import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
-import tempfile
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -67,11 +65,12 @@ FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="override the per-rank batch")
+    ap.add_argument("--seq-len", type=int, default=0, help="override the context length (diagnostics)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-slab", type=int, default=4, help="streams per host<->device slab in the e2e leg")
@@ -139,55 +138,81 @@ def call_bytes(cfg, batch):
 
 # --------------------------------------------------------------------------- clocks sampler
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock + throttle reasons DURING the timed region, sampled in-process through NVML every few
+    milliseconds (the timed region is tens of milliseconds: an `nvidia-smi -lms` child would not even
+    have started).  Same fields as the profiling recipe's nvidia-smi line."""
 
-    def __init__(self, gpu_index: int):
-        self.gpu_index = gpu_index
-        self.proc = None
-        self.path = None
+    REASONS = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"),
+               ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+               ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"),
+               ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap"),
+               ("hw_power_brake", "nvmlClocksEventReasonHwPowerBrakeSlowdown"))
+
+    def __init__(self, cuda_index: int, period_s: float = 0.002):
+        self.cuda_index = cuda_index
+        self.period_s = period_s
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self.power_w = []
+        self._stop = None
+        self._thread = None
+        self._err = None
+
+    def _handle(self, nv):
+        import torch
+
+        try:  # CUDA_VISIBLE_DEVICES renumbers CUDA devices; NVML does not — go through the UUID
+            uuid = str(torch.cuda.get_device_properties(self.cuda_index).uuid)
+            return nv.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            return nv.nvmlDeviceGetHandleByIndex(self.cuda_index)
 
     def start(self):
+        import threading
+
         try:
-            fd, self.path = tempfile.mkstemp(prefix="kvc_clocks_", suffix=".csv")
-            os.close(fd)
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
-                 "-i", str(self.gpu_index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
-        except Exception:
-            self.proc = None
+            import pynvml as nv
+
+            nv.nvmlInit()
+            h = self._handle(nv)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+        except Exception as exc:  # no NVML: report empty clocks rather than fail the bench
+            self._err = repr(exc)
+            return
+        self._stop = threading.Event()
+
+        def loop():
+            while not self._stop.is_set():
+                try:
+                    self.samples.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                    for name, attr in self.REASONS:
+                        if mask & getattr(nv, attr):
+                            self.reasons.add(name)
+                    self.power_w.append(nv.nvmlDeviceGetPowerUsage(h) / 1000.0)
+                except Exception as exc:
+                    self._err = repr(exc)
+                    return
+                self._stop.wait(self.period_s)
+
+        self._thread = threading.Thread(target=loop, daemon=True)
+        self._thread.start()
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
-            return out
-        try:
-            self.proc.terminate()
-            self.proc.wait(timeout=5)
-        except Exception:
-            pass
-        sm, reasons = [], set()
-        try:
-            for line in open(self.path):
-                f = [x.strip() for x in line.split(",")]
-                if len(f) < 9:
-                    continue
-                try:
-                    sm.append(float(f[1]))
-                    out["sm_max_mhz"] = float(f[2])
-                except ValueError:
-                    continue
-                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                    if val == "Active":
-                        reasons.add(name)
-            os.unlink(self.path)
-        except Exception:
-            pass
-        if sm:
-            out["sm_mhz"] = statistics.median(sm)
-            out["samples"] = len(sm)
-        out["reasons"] = sorted(reasons)
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join(timeout=5)
+        if self.samples:
+            out["sm_mhz"] = statistics.median(self.samples)
+            out["sm_mhz_min"] = min(self.samples)
+            out["samples"] = len(self.samples)
+            out["power_w_max"] = round(max(self.power_w), 1) if self.power_w else None
+        out["reasons"] = sorted(self.reasons)
+        out["how"] = "NVML in-process, every 2 ms, during the timed region only"
+        if self._err:
+            out["error"] = self._err
         return out
 
 
@@ -318,6 +343,8 @@ def run_ours(args):
     _engine.load_library()
 
     cfg = dict(CONFIGS[args.config])
+    if args.seq_len:
+        cfg["S"] = args.seq_len
     B = args.batch or cfg["B"]
     e = 4 if cfg["dtype"] == "f32" else 2
     fns = [(kvcompress.get_compress_fn(m), kw) for m, kw in cfg["calls"]]

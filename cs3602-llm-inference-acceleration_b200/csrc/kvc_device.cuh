@@ -3,7 +3,7 @@
 //   K1  row_sumsq / group_sum     128-bit coalesced loads of key rows, fp32 sum of squares,
 //                                 warp-shuffle reduction over the lanes that share a row
 //                                 (replaces torch.norm(K, p=2, dim=-1), e.g. l2_compress.py:70)
-//   K2  block_radix_select        per-(b,h) radix select in shared memory: 12-bit histogram
+//   K2  block_radix_select        per-(b,h) radix select in shared memory: 11-bit histogram
 //                                 fused into the scan, then refinement passes over the
 //                                 on-chip keys; ties go to the lowest token index; indices
 //                                 are emitted already ascending (replaces argsort + [:k] +
@@ -24,8 +24,8 @@
 
 namespace kvc {
 
-constexpr int kHistBits = 12;
-constexpr int kHistBins = 1 << kHistBits;  // 4096 bins * 4 B = 16 KB
+constexpr int kHistBits = 11;
+constexpr int kHistBins = 1 << kHistBits;  // 2048 bins * 4 B = 8 KB
 constexpr int kMiscInts = 128;             // 512 B of per-CTA scalars / per-warp counters
 constexpr int kMaxPoolHalo = 32;           // pooling_kernel <= 64
 
@@ -36,6 +36,31 @@ constexpr int kMiscMaxRaw = 2;  // snapkv: max norm (raw dtype bits, positive =>
 constexpr int kMiscWarpA = 32;  // 32 ints: per-warp counter A (scan totals / lt counts)
 constexpr int kMiscWarpB = 64;  // 32 ints: per-warp counter B (eq counts)
 constexpr int kMiscHalo = 96;   // 32 ints: snapkv pooling halo (raw norms of the previous tile's tail)
+
+// ---------------------------------------------------------------- launch descriptors
+struct LayerDev {
+    const char* k_in;
+    const char* v_in;
+    char* k_out;
+    char* v_out;
+    int32_t* idx_out;
+    const int32_t* idx_in;
+    int64_t ksb, ksh, kss;  // BYTE strides of K (batch, head, row)
+    int64_t vsb, vsh, vss;  // BYTE strides of V
+    int32_t S, sink, lo, hi, ksel, tail, score, pool;
+};
+static_assert(sizeof(LayerDev) == 128, "LayerDev is passed by value in kernel params");
+
+struct BatchDev {
+    int32_t B, H;
+    int32_t idx_cap;   // ints reserved for the kept-index list in shared memory
+    int32_t cpr;       // 16-byte chunks per row (generic path reads it at run time)
+    int32_t lpr, cpl;  // LDG form, generic path: lanes per row (power of two) and chunks per lane
+    int32_t nsw;       // TMA form: warps that own a staging slot (<= warps per CTA)
+    int32_t off_hist, off_idx, off_keys, off_stage;  // TMA form: shared-memory layout (bytes)
+    int32_t pad0;
+    LayerDev layers[KVC_MAX_LAYERS_PER_LAUNCH];
+};
 
 // ---------------------------------------------------------------- dtype traits
 template <int DT>
@@ -221,7 +246,7 @@ __device__ __forceinline__ void block_radix_select(const Key* __restrict__ keys,
     uint32_t prefix = 0;  // the high `pbits` bits of the k-th key found so far
     int pbits = 0;
     uint32_t krem = (uint32_t)k;
-    // level 0: the fused 12-bit histogram
+    // level 0: the fused 11-bit histogram
     find_bin<NT>(hist, kHistBins, krem, misc);
     prefix = (uint32_t)misc[kMiscBin];
     krem -= (uint32_t)misc[kMiscBelow];
@@ -292,6 +317,65 @@ __device__ __forceinline__ void block_radix_select(const Key* __restrict__ keys,
         if (take) out_idx[out_pos + __popc(tb & lane_lt)] = base + i;
         eq_before += __popc(eqb);
         out_pos += __popc(tb);
+    }
+    __syncthreads();
+}
+
+
+// ---------------------------------------------------------------- snapkv score transform
+// keys[0..R) hold the RAW norms (dtype bits) and misc[kMiscMaxRaw] their maximum.  Rewrites them
+// in place as descending-order radix keys of
+//   score_i = dt(dt(max + 1e-6) - norm_i);  pooled_i = dt(fp32 left-to-right sum of the zero-padded
+//   window / kernel)                        (snapkv_lite.py:96-121; avg_pool1d, count_include_pad)
+// and accumulates the level-0 histogram.  Every warp owns a contiguous segment and walks it 32 rows
+// at a time holding the previous / current / next 32 raw norms in registers (window taps are warp
+// shuffles), so the rewrite is in place without per-tile barriers; only the two segment-boundary
+// windows are read before a single __syncthreads().  All NT threads must call; ends synchronised.
+template <int DT, int NT>
+__device__ __forceinline__ void snapkv_transform(typename Traits<DT>::Key* keys, int R, int pk, uint32_t* hist,
+                                                 int32_t* misc) {
+    using Tr = Traits<DT>;
+    using Key = typename Tr::Key;
+    constexpr int kShift0 = Tr::kKeyBits - kHistBits;
+    constexpr int NW = NT / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float mx = Tr::from_raw((uint32_t)misc[kMiscMaxRaw]);
+    const float mxe = round_dt<DT>(mx + 1e-6f);
+    const bool pooling = pk > 1 && R >= pk;
+    const int pad = pooling ? pk / 2 : 0;
+    const int taps = pooling ? pk : 1;
+    const float den = (float)pk;
+    const int steps = (R + 31) >> 5;
+    const int spw = (steps + NW - 1) / NW;
+    const int w_lo = warp * spw * 32;
+    const int w_hi = min(R, w_lo + spw * 32);
+    auto raw_at = [&](int i) -> uint32_t { return (i >= 0 && i < R) ? (uint32_t)keys[i] : 0u; };
+    uint32_t prev = raw_at(w_lo - 32 + lane);
+    const uint32_t after = raw_at(w_hi + lane);
+    uint32_t cur = raw_at(w_lo + lane);
+    __syncthreads();  // boundary windows are in registers before any segment is rewritten
+    for (int i0 = w_lo; i0 < w_hi; i0 += 32) {
+        const uint32_t next = (i0 + 32 >= w_hi) ? after : raw_at(i0 + 32 + lane);
+        const int i = i0 + lane;
+        float acc = 0.f;
+        for (int t = 0; t < taps; ++t) {
+            const int d = t - pad;
+            const int sl = lane + d;
+            const uint32_t vp = __shfl_sync(0xffffffffu, prev, sl & 31);
+            const uint32_t vc = __shfl_sync(0xffffffffu, cur, sl & 31);
+            const uint32_t vn = __shfl_sync(0xffffffffu, next, sl & 31);
+            const uint32_t rj = sl < 0 ? vp : (sl >= 32 ? vn : vc);
+            const int j = i + d;
+            if (j >= 0 && j < R) acc += round_dt<DT>(mxe - Tr::from_raw(rj));
+        }
+        if (i < R) {
+            const float outv = pooling ? round_dt<DT>(acc / den) : acc;
+            const Key key = ordered_key<Key>(Tr::to_raw(outv), /*descending=*/true);
+            keys[i] = key;
+            atomicAdd(&hist[(uint32_t)key >> kShift0], 1u);
+        }
+        prev = cur;
+        cur = next;
     }
     __syncthreads();
 }

@@ -4,44 +4,24 @@
 // (layer, batch, head) unit and runs
 //   scan   (K1) stream the K rows of the selection region once, fp32 sum of squares, round the
 //               norm to the cache dtype (torch.norm semantics), build the radix key in shared
-//               memory and its 12-bit histogram on the fly;
+//               memory and its 11-bit histogram on the fly;
 //   select (K2) radix select over the on-chip keys, ties -> lowest index, ascending indices;
 //   gather (K3) copy sink rows + selected rows + tail rows of K and V into the dense output.
 // Several CTAs are resident per SM, so one unit's select overlaps its neighbours' HBM phases.
 // Algorithmic HBM bytes per unit: e*D*(R + 4*C)  (SURVEY.md §8d).
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
 #include "kvc_device.cuh"
+#include "kvc_fused_tma.cuh"
 
 #define KVC_STR2(x) #x
 #define KVC_STR(x) KVC_STR2(x)
 
 namespace kvc {
-
-struct LayerDev {
-    const char* k_in;
-    const char* v_in;
-    char* k_out;
-    char* v_out;
-    int32_t* idx_out;
-    const int32_t* idx_in;
-    int64_t ksb, ksh, kss;  // BYTE strides of K (batch, head, row)
-    int64_t vsb, vsh, vss;  // BYTE strides of V
-    int32_t S, sink, lo, hi, ksel, tail, score, pool;
-};
-static_assert(sizeof(LayerDev) == 128, "LayerDev is passed by value in kernel params");
-
-struct BatchDev {
-    int32_t B, H;
-    int32_t idx_cap;   // ints reserved for the kept-index list in shared memory
-    int32_t cpr;       // 16-byte chunks per row (generic path reads it at run time)
-    int32_t lpr, cpl;  // generic path: lanes per row (power of two) and chunks per lane
-    int32_t pad0, pad1;
-    LayerDev layers[KVC_MAX_LAYERS_PER_LAUNCH];
-};
 
 constexpr int kSmemFixed = kHistBins * 4 + kMiscInts * 4;
 
@@ -49,7 +29,7 @@ constexpr int kSmemFixed = kHistBins * 4 + kMiscInts * 4;
 // CPR > 0: compile-time chunks per row with LPR lanes per row (CPR % LPR == 0).
 // CPR == 0: generic path, runtime cpr / lpr (power of two) / cpl.
 template <int DT, int CPR, int LPR, int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB) kvc_fused_kernel(const __grid_constant__ BatchDev bd) {
+__global__ void __launch_bounds__(NT, MINB) kvc_fused_ldg_kernel(const __grid_constant__ BatchDev bd) {
     using Tr = Traits<DT>;
     using Key = typename Tr::Key;
     constexpr int NW = NT / 32;
@@ -61,7 +41,7 @@ __global__ void __launch_bounds__(NT, MINB) kvc_fused_kernel(const __grid_consta
     const int b = bh / bd.H, h = bh - b * bd.H;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
     uint32_t* hist = reinterpret_cast<uint32_t*>(smem);
     int32_t* misc = reinterpret_cast<int32_t*>(smem + kHistBins * 4);
     int32_t* sidx = reinterpret_cast<int32_t*>(smem + kSmemFixed);
@@ -169,49 +149,7 @@ __global__ void __launch_bounds__(NT, MINB) kvc_fused_kernel(const __grid_consta
         }
         __syncthreads();
 
-        if (snap) {
-            // ------------------------------------------------------ snapkv score transform
-            // score_i = dt(dt(max + 1e-6) - norm_i); pooled_i = dt(fp32 left-to-right sum of the
-            // zero-padded window / kernel)  (snapkv_lite.py:96-121; avg_pool1d, count_include_pad).
-            // Done in place, tile by tile; the raw norms a later tile still needs from an
-            // already rewritten tile are parked in the halo.
-            const float mx = Tr::from_raw((uint32_t)misc[kMiscMaxRaw]);
-            const float mxe = round_dt<DT>(mx + 1e-6f);
-            const int pk = L.pool;
-            const bool pooling = pk > 1 && R >= pk;
-            const int pad = pooling ? pk / 2 : 0;
-            const float inv_den = (float)pk;
-            uint32_t* halo = reinterpret_cast<uint32_t*>(&misc[kMiscHalo]);
-            for (int t0 = 0; t0 < R; t0 += NT) {
-                const int i = t0 + tid;
-                uint32_t raw_i = 0;
-                float outv = 0.f;
-                if (i < R) {
-                    raw_i = (uint32_t)keys[i];
-                    if (pooling) {
-                        float acc = 0.f;
-                        for (int t = 0; t < pk; ++t) {
-                            const int j = i - pad + t;
-                            if (j >= 0 && j < R) {
-                                const uint32_t rj = (j < t0) ? halo[j - (t0 - pad)] : (uint32_t)keys[j];
-                                acc += round_dt<DT>(mxe - Tr::from_raw(rj));
-                            }
-                        }
-                        outv = round_dt<DT>(acc / inv_den);
-                    } else {
-                        outv = round_dt<DT>(mxe - Tr::from_raw(raw_i));
-                    }
-                }
-                __syncthreads();  // every read of this tile's inputs (keys + halo) is done
-                if (i < R) {
-                    if (pad > 0 && i >= t0 + NT - pad) halo[i - (t0 + NT - pad)] = raw_i;
-                    const Key key = ordered_key<Key>(Tr::to_raw(outv), /*descending=*/true);
-                    keys[i] = key;
-                    atomicAdd(&hist[(uint32_t)key >> kShift0], 1u);
-                }
-                __syncthreads();
-            }
-        }
+        if (snap) snapkv_transform<DT, NT>(keys, R, L.pool, hist, misc);
         // ---------------------------------------------------------- K2: select
         block_radix_select<Key, NT>(keys, R, ksel, hist, misc, sidx, L.lo);
     }
@@ -292,7 +230,7 @@ __global__ void __launch_bounds__(NT) kvc_select_kernel(const typename Traits<DT
     using Tr = Traits<DT>;
     using Key = typename Tr::Key;
     constexpr int kShift0 = Tr::kKeyBits - kHistBits;
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(128) unsigned char smem[];
     uint32_t* hist = reinterpret_cast<uint32_t*>(smem);
     int32_t* misc = reinterpret_cast<int32_t*>(smem + kHistBins * 4);
     int32_t* sidx = reinterpret_cast<int32_t*>(smem + kSmemFixed);
@@ -336,12 +274,12 @@ constexpr int kNT = 512;
 template <int DT>
 static FusedVariant pick_fused(int cpr) {
     switch (cpr) {
-        case 8: return {kvc_fused_kernel<DT, 8, 8, kNT, 2>, kNT};
-        case 10: return {kvc_fused_kernel<DT, 10, 10, kNT, 2>, kNT};
-        case 16: return {kvc_fused_kernel<DT, 16, 8, kNT, 2>, kNT};
-        case 20: return {kvc_fused_kernel<DT, 20, 10, kNT, 2>, kNT};
-        case 32: return {kvc_fused_kernel<DT, 32, 16, kNT, 2>, kNT};
-        default: return {kvc_fused_kernel<DT, 0, 0, kNT, 2>, kNT};
+        case 8: return {kvc_fused_ldg_kernel<DT, 8, 8, kNT, 2>, kNT};
+        case 10: return {kvc_fused_ldg_kernel<DT, 10, 10, kNT, 2>, kNT};
+        case 16: return {kvc_fused_ldg_kernel<DT, 16, 8, kNT, 2>, kNT};
+        case 20: return {kvc_fused_ldg_kernel<DT, 20, 10, kNT, 2>, kNT};
+        case 32: return {kvc_fused_ldg_kernel<DT, 32, 16, kNT, 2>, kNT};
+        default: return {kvc_fused_ldg_kernel<DT, 0, 0, kNT, 2>, kNT};
     }
 }
 
@@ -383,6 +321,102 @@ static int pow2_lanes(int cpr) {
 static size_t fused_smem_bytes(int dtype, int max_region, int idx_cap) {
     const size_t keys = ((size_t)max_region * key_bytes(dtype) + 15) & ~(size_t)15;
     return (size_t)kSmemFixed + (size_t)idx_cap * 4 + keys;
+}
+
+
+// ------------------------------------------------------------------ TMA form: variant + smem plan
+constexpr int kSmemPerSM = 228 * 1024;  // per-SM shared memory; every resident CTA reserves 1 KB of it
+constexpr int kTmaHead = kMiscInts * 4 + 32 * 8;  // misc scalars + one mbarrier per warp
+
+struct TmaPlan {
+    bool ok = false;
+    int nt = 0, ctas = 0, nsw = 0;
+    int off_hist = 0, off_idx = 0, off_keys = 0, off_stage = 0;
+    size_t smem = 0;
+};
+
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+// Choose threads per CTA, resident CTAs per SM and staging warps so that (a) the on-chip key
+// buffer fits, (b) as close to 128 KB of rows as possible are in flight per SM, (c) as many CTAs as possible are
+// resident so one unit's select phase hides under its neighbours' HBM phases.
+static TmaPlan plan_tma(int dtype, int cpr, int max_region, int idx_cap, bool any_select) {
+    TmaPlan best;
+    const int stage = 32 * cpr * 16;
+    int end = kTmaHead;
+    TmaPlan base;
+    base.off_hist = base.off_idx = base.off_keys = kTmaHead;
+    if (any_select) {
+        base.off_hist = kTmaHead;
+        base.off_idx = base.off_hist + kHistBins * 4;
+        base.off_keys = base.off_idx + ((idx_cap * 4 + 15) & ~15);
+        end = base.off_keys + (int)(((size_t)max_region * key_bytes(dtype) + 15) & ~(size_t)15);
+    }
+    base.off_stage = (end + 127) & ~127;
+    const int force_nt = env_int("KVC_TMA_NT", 0), force_ctas = env_int("KVC_TMA_CTAS", 0),
+              force_nsw = env_int("KVC_TMA_NSW", 0);
+    static const int cand[][2] = {{256, 3}, {256, 2}, {512, 1}, {256, 1}};
+    long best_score = -1;
+    for (const auto& c : cand) {
+        const int nt = c[0], ctas = c[1];
+        if (force_nt && nt != force_nt) continue;
+        if (force_ctas && ctas != force_ctas) continue;
+        int limit = kSmemPerSM / ctas - 1024;
+        if (limit > kMaxSmemOptin) limit = kMaxSmemOptin;
+        const int avail = limit - base.off_stage;
+        if (avail < stage) continue;
+        int nsw = avail / stage;
+        if (nsw > nt / 32) nsw = nt / 32;
+        if (force_nsw && force_nsw < nsw) nsw = force_nsw;
+        const long inflight = (long)ctas * nsw * stage;
+        // saturating score: bytes in flight up to 128 KB matter most (measured: c5 +8% from 64 -> 128 KB), then residency
+        const long score = (inflight < 131072 ? inflight : 131072) * 8 + ctas * 4096 + (inflight >> 6);
+        if (score > best_score) {
+            best_score = score;
+            best = base;
+            best.ok = true;
+            best.nt = nt;
+            best.ctas = ctas;
+            best.nsw = nsw;
+            best.smem = (size_t)base.off_stage + (size_t)nsw * stage;
+        }
+    }
+    return best;
+}
+
+template <int DT, int NT, int MINB>
+static FusedFn pick_tma_cpr(int cpr) {
+    switch (cpr) {
+        case 8: return kvc_fused_tma_kernel<DT, 8, NT, MINB>;
+        case 10: return kvc_fused_tma_kernel<DT, 10, NT, MINB>;
+        case 16: return kvc_fused_tma_kernel<DT, 16, NT, MINB>;
+        case 20: return kvc_fused_tma_kernel<DT, 20, NT, MINB>;
+        case 32: return kvc_fused_tma_kernel<DT, 32, NT, MINB>;
+        default: return nullptr;
+    }
+}
+template <int DT>
+static FusedFn pick_tma_nt(int cpr, int nt) {
+    return nt == 512 ? pick_tma_cpr<DT, 512, 1>(cpr) : pick_tma_cpr<DT, 256, 3>(cpr);
+}
+static FusedFn pick_tma(int dtype, int cpr, int nt) {
+    switch (dtype) {
+        case KVC_DTYPE_F32: return pick_tma_nt<KVC_DTYPE_F32>(cpr, nt);
+        case KVC_DTYPE_F16: return pick_tma_nt<KVC_DTYPE_F16>(cpr, nt);
+        default: return pick_tma_nt<KVC_DTYPE_BF16>(cpr, nt);
+    }
+}
+static bool tma_supported_cpr(int cpr) { return cpr == 8 || cpr == 10 || cpr == 16 || cpr == 20 || cpr == 32; }
+
+static int ensure_tma_attrs(const void* fn) {
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmemOptin);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(max dynamic smem)");
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(carveout)");
+    return KVC_OK;
 }
 
 }  // namespace kvc
@@ -505,14 +539,32 @@ int kvc_compress_layers(const kvc_shape* shape, int32_t n_layers, const kvc_laye
         }
         if (n_active == 0) continue;
         bd.idx_cap = (max_ksel + 3) & ~3;
-        size_t smem = any_select ? fused_smem_bytes(dt, max_region, bd.idx_cap) : 0;
-        if (smem > (size_t)kMaxSmemOptin) return KVC_ERR_TOO_LARGE;
-        st = ensure_smem((const void*)var.fn, smem);
-        if (st != KVC_OK) return st;
         dim3 grid((unsigned)((int64_t)B * H), (unsigned)n_active, 1);
-        var.fn<<<grid, var.threads, smem, (cudaStream_t)stream>>>(bd);
-        cudaError_t err = cudaGetLastError();
-        if (err != cudaSuccess) return cuda_fail(err, "kvc_fused_kernel launch");
+        TmaPlan tp;
+        if (tma_supported_cpr(cpr) && !env_int("KVC_FORCE_LDG", 0)) tp = plan_tma(dt, cpr, max_region, bd.idx_cap, any_select);
+        if (tp.ok) {
+            // bulk-copy form: rows are staged through shared memory by the TMA unit
+            FusedFn fn = pick_tma(dt, cpr, tp.nt);
+            bd.nsw = tp.nsw;
+            bd.off_hist = tp.off_hist;
+            bd.off_idx = tp.off_idx;
+            bd.off_keys = tp.off_keys;
+            bd.off_stage = tp.off_stage;
+            st = ensure_tma_attrs((const void*)fn);
+            if (st != KVC_OK) return st;
+            fn<<<grid, tp.nt, tp.smem, (cudaStream_t)stream>>>(bd);
+            cudaError_t err = cudaGetLastError();
+            if (err != cudaSuccess) return cuda_fail(err, "kvc_fused_tma_kernel launch");
+        } else {
+            // LDG form: head dims without a compiled row width, or key buffers that leave no room to stage
+            size_t smem = any_select ? fused_smem_bytes(dt, max_region, bd.idx_cap) : 0;
+            if (smem > (size_t)kMaxSmemOptin) return KVC_ERR_TOO_LARGE;
+            st = ensure_smem((const void*)var.fn, smem);
+            if (st != KVC_OK) return st;
+            var.fn<<<grid, var.threads, smem, (cudaStream_t)stream>>>(bd);
+            cudaError_t err = cudaGetLastError();
+            if (err != cudaSuccess) return cuda_fail(err, "kvc_fused_ldg_kernel launch");
+        }
         g_launches.fetch_add(1);
     }
     return KVC_OK;
