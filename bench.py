@@ -73,7 +73,7 @@ def parse_args():
     ap.add_argument("--seq-len", type=int, default=0, help="override the context length (diagnostics)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-slab", type=int, default=4, help="streams per host<->device slab in the e2e leg")
+    ap.add_argument("--e2e-slab", type=int, default=8, help="streams per host<->device slab in the e2e leg")
     ap.add_argument("--cpu-sample-batch", type=int, default=0,
                     help="streams in the CPU sample (0: enough (b,h) rows to occupy every host thread, at most 8)")
     return ap.parse_args()
@@ -402,13 +402,14 @@ def run_ours(args):
     dom = max(range(len(fns)), key=lambda i: mean_call_ms[i])
     peak, peak_src = measured_peak()
     achieved = per_call_bytes[dom] / (mean_call_ms[dom] * 1e-3) / 1e9
-    traffic = profiled_traffic(args.config)
+    prof = profiled_traffic(args.config) if (B == CONFIGS[args.config]["B"] and not args.seq_len) else None
+    traffic = prof["bytes_per_launch"] if prof else None
     roofline = {
-        "bound": "hbm", "kernel": f"kvc_fused_kernel ({cfg['calls'][dom][0]})", "achieved": round(achieved, 1),
+        "bound": "hbm", "kernel": f"kvc_fused_tma_kernel ({cfg['calls'][dom][0]})", "achieved": round(achieved, 1),
         "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "frac_of_nominal_8000": round(achieved / 8000.0, 4),
         "peak_source": peak_src, "algorithmic_bytes_per_launch": per_call_bytes[dom],
         "launch_us_mean": round(mean_call_ms[dom] * 1e3, 1), "launch_us_min": round(min_call_ms[dom] * 1e3, 1),
-        "traffic": traffic,
+        "traffic": traffic, "traffic_source": prof["source"] if prof else None,
     }
     per_call = {
         cfg["calls"][i][0]: {
@@ -452,9 +453,15 @@ def run_ours(args):
 
 
 def run_e2e(cfg, B, kv, fns, step_bytes, args, device, world, barrier):
-    """The same step with the cache resident in (pinned) HOST memory: every step copies each slab of
-    `slab` streams to the GPU, compresses it through the public API and copies the compressed cache
-    back; H2D of slab i+1 and D2H of slab i-1 overlap the compress of slab i (three streams)."""
+    """The same step with the cache resident in pinned HOST memory, through the public API, host <-> device
+    traffic inside the timed region.  Two ways are timed and the faster is reported:
+
+    zero_copy  the pinned (K, V) tensors are handed straight to the compress functions: the kernels pull the
+               rows they need over PCIe (scan: the selection region of K once; gather: the kept rows of K and
+               V) and write the compressed cache into pinned host tensors — ONE launch per call, no copy engine;
+    staged     cudaMemcpyAsync of every slab to the GPU, compress on the device, copy the result back
+               (three streams: H2D of slab i+1 and D2H of slab i-1 overlap the compress of slab i).
+    """
     import torch
     import torch.distributed as dist
 
@@ -464,17 +471,48 @@ def run_e2e(cfg, B, kv, fns, step_bytes, args, device, world, barrier):
         slab, n_slabs = B, 1
     # one pinned slab is reused for every slab of the step (same bytes cross PCIe; the content is synthetic)
     host_in = [(k[:slab].cpu().pin_memory(), v[:slab].cpu().pin_memory()) for k, v in kv]
+    itemsize = host_in[0][0].element_size()
+    full_in_bytes = n_slabs * sum(k.numel() * itemsize + v.numel() * itemsize for k, v in host_in)
+    steps = max(2, min(args.steps, 5))
+
+    def timed(step_fn):
+        for _ in range(2):
+            step_fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step_fn()
+        barrier()
+        dt_s = (time.perf_counter() - t0) / steps
+        if world > 1:
+            t = torch.tensor([dt_s], device=device, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt_s = float(t.item())
+        return dt_s
+
+    # ---------------------------------------------------------------- zero-copy through the public API
+    def zc_step():
+        outs = None
+        for _ in range(n_slabs):
+            outs = [fn(host_in, **kw) for fn, kw in fns]  # pinned in -> pinned out, synchronous like the reference
+        return outs
+
+    probe = zc_step()
+    d2h_bytes = n_slabs * sum(k.numel() * itemsize + v.numel() * itemsize for out in probe for k, v in out)
+    # rows the kernels read over PCIe: R (scan) + 2C (gather) per compressed layer = algorithmic bytes minus the writes
+    zc_h2d = step_bytes - d2h_bytes
+    del probe
+    zc_s = timed(zc_step)
+
+    # ---------------------------------------------------------------- staged (copy engines + device compress)
     dev_in = [[(torch.empty_like(k[:slab]), torch.empty_like(v[:slab])) for k, v in kv] for _ in range(2)]
-    probe = [fn([(k[:slab], v[:slab]) for k, v in kv], **kw) for fn, kw in fns]
+    probe = [fn(dev_in[0], **kw) for fn, kw in fns]
     host_out = [[[(torch.empty(k.shape, dtype=k.dtype).pin_memory(), torch.empty(v.shape, dtype=v.dtype).pin_memory())
                   for k, v in out] for out in probe] for _ in range(2)]
-    h2d_bytes = n_slabs * sum(k.numel() * k.element_size() + v.numel() * v.element_size() for k, v in host_in)
-    d2h_bytes = n_slabs * sum(k.numel() * k.element_size() + v.numel() * v.element_size()
-                              for out in probe for k, v in out)
     del probe
     s_h2d, s_comp, s_d2h = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
 
-    def step():
+    def staged_step():
         keep = []
         comp_done = [None] * n_slabs
         d2h_done = [None] * n_slabs
@@ -507,23 +545,21 @@ def run_e2e(cfg, B, kv, fns, step_bytes, args, device, world, barrier):
         torch.cuda.synchronize()
         return keep
 
-    for _ in range(2):
-        step()
-    barrier()
-    steps = max(2, min(args.steps, 5))
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        step()
-    barrier()
-    dt_s = (time.perf_counter() - t0) / steps
-    if world > 1:
-        t = torch.tensor([dt_s], device=device, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt_s = float(t.item())
-    return {"value": round(step_bytes * world / dt_s / 1e9, 2), "unit": "GB/s", "h2d_bytes_per_step": h2d_bytes,
-            "d2h_bytes_per_step": d2h_bytes, "ms_per_step": round(dt_s * 1e3, 2), "steps": steps,
-            "how": f"pinned host cache -> {n_slabs} slabs of {slab} streams: H2D, compress via the public API, "
-                   f"D2H of the compressed cache; 3-stream pipeline; wall clock around synchronised steps"}
+    st_s = timed(staged_step)
+
+    def entry(dt_s, h2d, how):
+        return {"value": round(step_bytes * world / dt_s / 1e9, 2), "unit": "GB/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h_bytes, "ms_per_step": round(dt_s * 1e3, 2), "steps": steps, "how": how}
+
+    zc = entry(zc_s, zc_h2d,
+               f"zero_copy: pinned host (K, V) of {slab} streams x {n_slabs} slabs passed to the public API; the kernels "
+               f"read the rows they need over PCIe and write the compressed cache to pinned host memory; wall clock")
+    st = entry(st_s, full_in_bytes,
+               f"staged: pinned host cache -> {n_slabs} slabs of {slab} streams: H2D, compress via the public API, "
+               f"D2H of the compressed cache; 3-stream pipeline; wall clock around synchronised steps")
+    best, other = (zc, st) if zc_s <= st_s else (st, zc)
+    best["alternative"] = other
+    return best
 
 
 def main():

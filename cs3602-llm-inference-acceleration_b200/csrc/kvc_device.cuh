@@ -58,7 +58,7 @@ struct BatchDev {
     int32_t lpr, cpl;  // LDG form, generic path: lanes per row (power of two) and chunks per lane
     int32_t nsw;       // TMA form: warps that own a staging slot (<= warps per CTA)
     int32_t off_hist, off_idx, off_keys, off_stage;  // TMA form: shared-memory layout (bytes)
-    int32_t pad0;
+    int32_t upc;       // TMA form: consecutive (batch, head) units walked by one CTA
     LayerDev layers[KVC_MAX_LAYERS_PER_LAUNCH];
 };
 

@@ -82,8 +82,6 @@ __global__ void __launch_bounds__(NT, MINB) kvc_fused_tma_kernel(const __grid_co
     constexpr int kShift0 = Tr::kKeyBits - kHistBits;
 
     const LayerDev& L = bd.layers[blockIdx.y];
-    const int bh = blockIdx.x;
-    const int b = bh / bd.H, h = bh - b * bd.H;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     extern __shared__ __align__(128) unsigned char smem[];
@@ -100,8 +98,6 @@ __global__ void __launch_bounds__(NT, MINB) kvc_fused_tma_kernel(const __grid_co
     const int R = L.hi - L.lo;
     const int ksel = L.ksel;
     const int score = L.score;
-    const char* kbase = L.k_in + (int64_t)b * L.ksb + (int64_t)h * L.ksh;
-    const char* vbase = L.v_in + (int64_t)b * L.vsb + (int64_t)h * L.vsh;
     const bool kdense = L.kss == RB, vdense = L.vss == RB;
     const bool scan = ksel > 0 && score != KVC_SCORE_GIVEN_INDEX;
 
@@ -112,6 +108,14 @@ __global__ void __launch_bounds__(NT, MINB) kvc_fused_tma_kernel(const __grid_co
         }
         __syncwarp();
     }
+    // A CTA walks `upc` consecutive (batch, head) units: neighbours in memory, so the SM keeps
+    // touching the same 2 MB pages (matters when only a sparse slice of each unit is read).
+    const int n_units = bd.B * bd.H;
+    const int bh_end = min(n_units, ((int)blockIdx.x + 1) * bd.upc);
+    for (int bh = (int)blockIdx.x * bd.upc; bh < bh_end; ++bh) {
+    const int b = bh / bd.H, h = bh - b * bd.H;
+    const char* kbase = L.k_in + (int64_t)b * L.ksb + (int64_t)h * L.ksh;
+    const char* vbase = L.v_in + (int64_t)b * L.vsb + (int64_t)h * L.vsh;
     const char* kreg = kbase + (int64_t)L.lo * L.kss;
     const int nblk = (R + 31) >> 5;
     if (scan && stager && warp < nblk)  // first block is in flight while the histogram is cleared
@@ -197,6 +201,8 @@ __global__ void __launch_bounds__(NT, MINB) kvc_fused_tma_kernel(const __grid_co
             __syncwarp();
         }
     }
+    __syncthreads();  // every warp is done with sidx / keys before the next unit reuses them
+    }  // unit loop
 }
 
 }  // namespace kvc

@@ -330,7 +330,7 @@ constexpr int kTmaHead = kMiscInts * 4 + 32 * 8;  // misc scalars + one mbarrier
 
 struct TmaPlan {
     bool ok = false;
-    int nt = 0, ctas = 0, nsw = 0;
+    int nt = 0, ctas = 0, nsw = 0, upc = 1;
     int off_hist = 0, off_idx = 0, off_keys = 0, off_stage = 0;
     size_t smem = 0;
 };
@@ -384,6 +384,8 @@ static TmaPlan plan_tma(int dtype, int cpr, int max_region, int idx_cap, bool an
             best.smem = (size_t)base.off_stage + (size_t)nsw * stage;
         }
     }
+    best.upc = env_int("KVC_TMA_UPC", 1);
+    if (best.upc < 1) best.upc = 1;
     return best;
 }
 
@@ -550,6 +552,8 @@ int kvc_compress_layers(const kvc_shape* shape, int32_t n_layers, const kvc_laye
             bd.off_idx = tp.off_idx;
             bd.off_keys = tp.off_keys;
             bd.off_stage = tp.off_stage;
+            bd.upc = tp.upc;
+            grid.x = (unsigned)(((int64_t)B * H + tp.upc - 1) / tp.upc);
             st = ensure_tma_attrs((const void*)fn);
             if (st != KVC_OK) return st;
             fn<<<grid, tp.nt, tp.smem, (cudaStream_t)stream>>>(bd);

@@ -1,8 +1,10 @@
 """ctypes binding to ``libkvc_sm100a.so`` (C ABI in ``include/kvc.h``) and plan execution.
 
 This is the only module that talks to the device library.  There is no CPU path and no
-fallback: if a plan needs data movement, the tensors must live on a CUDA device and the
-shared library must be present, otherwise a ``RuntimeError`` is raised.
+fallback: if a plan needs data movement, the tensors must be reachable by the GPU — CUDA
+tensors, or page-locked (pinned) host tensors, which the kernels read and write in place over
+PCIe (an offloaded cache: only the rows a method needs ever cross the link) — and the shared
+library must be present, otherwise a ``RuntimeError`` is raised.
 
 PyTorch is used for device memory (``torch.empty`` through the caching allocator) and for
 the current stream; all compute happens in the library's own sm_100a kernels.
@@ -98,6 +100,17 @@ def _require_cuda(t: torch.Tensor, what: str) -> None:
         raise ValueError(f"{what}: dtype {t.dtype} is not supported (float32, float16, bfloat16)")
 
 
+def _require_gpu_reachable(t: torch.Tensor, what: str) -> None:
+    """CUDA tensors, or pinned host tensors (mapped into the device address space under UVA)."""
+    if not t.is_cuda and not (t.device.type == "cpu" and t.is_pinned()):
+        raise RuntimeError(
+            f"{what}: tensor is on {t.device} in pageable memory; kvcompress-b200 runs on CUDA (sm_100a) only — "
+            "there is no CPU path (pin host-resident caches with .pin_memory() to have the GPU compress them in place)"
+        )
+    if t.dtype not in KVC_DTYPE:
+        raise ValueError(f"{what}: dtype {t.dtype} is not supported (float32, float16, bfloat16)")
+
+
 def _rows_ok(t: torch.Tensor) -> bool:
     e = t.element_size()
     return (t.stride(3) == 1 or t.size(3) == 1) and all((t.stride(i) * e) % 16 == 0 for i in range(3)) \
@@ -129,8 +142,8 @@ def run_plans(kv: Sequence[Tuple[torch.Tensor, torch.Tensor]], plans: Sequence[P
             n = plan.view_n
             out[li] = (keys[:, :, -n:, :], values[:, :, -n:, :])
             continue
-        _require_cuda(keys, f"layer {li} keys")
-        _require_cuda(values, f"layer {li} values")
+        _require_gpu_reachable(keys, f"layer {li} keys")
+        _require_gpu_reachable(values, f"layer {li} values")
         if keys.dim() != 4 or values.shape != keys.shape or values.dtype != keys.dtype or values.device != keys.device:
             raise ValueError(f"layer {li}: keys/values must be matching [B, H, S, D] tensors")
         if keys.size(2) != plan.seq_len:
@@ -144,24 +157,29 @@ def run_plans(kv: Sequence[Tuple[torch.Tensor, torch.Tensor]], plans: Sequence[P
     keepalive = []
     for (device, dtype, B, H, D), layer_ids in groups.items():
         lib = load_library()
+        on_host = device.type == "cpu"
+        if on_host and not torch.cuda.is_available():
+            raise RuntimeError("pinned host tensors need a CUDA device to run on: there is no CPU path")
+        run_device = torch.device("cuda", torch.cuda.current_device()) if on_host else device
+        alloc = dict(dtype=dtype, pin_memory=True) if on_host else dict(dtype=dtype, device=device)
         plan_buf = bytearray(_PLAN.size * len(layer_ids))
         io_buf = bytearray(_IO.size * len(layer_ids))
         for n, li in enumerate(layer_ids):
             plan = plans[li]
             keys, values = kv[li][0], kv[li][1]
             if not _rows_ok(keys):
-                keys = keys.contiguous()
+                keys = keys.contiguous().pin_memory() if on_host else keys.contiguous()
                 keepalive.append(keys)
             if not _rows_ok(values):
-                values = values.contiguous()
+                values = values.contiguous().pin_memory() if on_host else values.contiguous()
                 keepalive.append(values)
             C = plan.out_len
-            k_out = torch.empty((B, H, C, D), dtype=dtype, device=device)
-            v_out = torch.empty((B, H, C, D), dtype=dtype, device=device)
+            k_out = torch.empty((B, H, C, D), **alloc)
+            v_out = torch.empty((B, H, C, D), **alloc)
             out[li] = (k_out, v_out)
             idx_out_ptr = 0
             if return_indices:
-                idx = torch.empty((B, H, C), dtype=torch.int32, device=device)
+                idx = torch.empty((B, H, C), **dict(alloc, dtype=torch.int32))
                 indices[li] = idx
                 idx_out_ptr = idx.data_ptr()
             idx_in_ptr = 0
@@ -172,6 +190,8 @@ def run_plans(kv: Sequence[Tuple[torch.Tensor, torch.Tensor]], plans: Sequence[P
                 if gi.dtype != torch.int32 or not gi.is_contiguous() or tuple(gi.shape) != (B, H, plan.k_sel) \
                         or gi.device != device:
                     raise ValueError(f"layer {li}: indices must be a contiguous int32 [B, H, k_sel] tensor on {device}")
+                if on_host and not gi.is_pinned():
+                    gi = gi.pin_memory()
                 idx_in_ptr = gi.data_ptr()
                 keepalive.append(gi)
             _PLAN.pack_into(plan_buf, n * _PLAN.size, plan.seq_len, plan.sink, plan.sel_lo, plan.sel_hi, plan.k_sel,
@@ -179,11 +199,15 @@ def run_plans(kv: Sequence[Tuple[torch.Tensor, torch.Tensor]], plans: Sequence[P
             _IO.pack_into(io_buf, n * _IO.size, keys.data_ptr(), values.data_ptr(), k_out.data_ptr(),
                           v_out.data_ptr(), keys.stride(0), keys.stride(1), keys.stride(2), values.stride(0),
                           values.stride(1), values.stride(2), idx_out_ptr, idx_in_ptr)
-        dev_index = device.index if device.index is not None else torch.cuda.current_device()
+        dev_index = run_device.index if run_device.index is not None else torch.cuda.current_device()
         shape = _SHAPE.pack(B, H, D, KVC_DTYPE[dtype], dev_index)
         status = lib.kvc_compress_layers(shape, len(layer_ids), bytes(plan_buf), bytes(io_buf),
-                                         ctypes.c_void_p(_stream_ptr(device)))
+                                         ctypes.c_void_p(_stream_ptr(run_device)))
         _check(status, "kvc_compress_layers")
+        if on_host:
+            # host tensors are read by the caller with plain loads: finish before returning,
+            # as the reference's (synchronous) CPU path does
+            torch.cuda.current_stream(run_device).synchronize()
     if return_indices:
         return out, indices
     return out

@@ -308,3 +308,47 @@ def test_full_shape_streaming_and_snapkv():
         # allow one bf16 ulp: torch's CUDA avg_pool may sum in a different order than the CPU reference
         assert torch.all(lowest_taken >= highest_left * (1 - 2 ** -7))
         assert torch.equal(rows[..., p.k_sel:], torch.arange(32768 - 32, 32768, device="cuda", dtype=torch.int32).expand(2, 8, -1))
+
+
+# ----------------------------------------------------------------------------------------------
+# Offloaded caches: pinned host tensors are compressed in place by the GPU (zero-copy over PCIe)
+@pytest.mark.parametrize("method,kwargs", [
+    ("streaming_llm", dict(start_size=4, recent_size=124)),
+    ("fix_size_l2", dict(fix_kv_size=256, keep_ratio=0.2, skip_layers=[0])),
+    ("fix_size_l2", dict(fix_kv_size=256, keep_ratio=0.25, strategy="random", skip_layers=[])),
+    ("h2o_l2", dict(start_size=4, heavy_hitter_size=32, recent_size=92)),
+    ("snapkv_lite", dict(observation_window=16, keep_size=128)),
+    ("pyramid_kv", dict(base_size=128, min_size=32)),
+])
+def test_pinned_host_cache_matches_device_cache(method, kwargs):
+    """Same bytes out whether the cache lives in HBM or in pinned host memory; host in -> pinned host out,
+    results complete on return (the reference's CPU path is synchronous); pageable host tensors are refused."""
+    torch.manual_seed(5)
+    L, B, H, S, D = 3, 2, 4, 700, 80
+    host = [(torch.randn(B, H, S, D).bfloat16().pin_memory(), torch.randn(B, H, S, D).bfloat16().pin_memory())
+            for _ in range(L)]
+    dev = [(k.cuda(), v.cuda()) for k, v in host]
+    fn = kvcompress.get_compress_fn(method)
+    torch.manual_seed(99)
+    out_h = fn(host, **kwargs)
+    torch.manual_seed(99)
+    out_d = fn(dev, **kwargs)
+    if kwargs.get("strategy") == "random":  # CPU and CUDA generators differ: check structure only
+        for (kh, vh), (kd, vd) in zip(out_h, out_d):
+            assert kh.shape == kd.shape and kh.device.type == "cpu"
+        return
+    for li, ((kh, vh), (kd, vd)) in enumerate(zip(out_h, out_d)):
+        assert kh.device.type == "cpu" and vh.device.type == "cpu"
+        if kd is dev[li][0]:
+            assert kh is host[li][0]
+            continue
+        assert kh.is_pinned() and vh.is_pinned()
+        assert torch.equal(kh, kd.cpu()) and torch.equal(vh, vd.cpu())
+    # a [B,S,H,D]-stored pinned cache (row stride != row bytes: per-row bulk copies)
+    t = [(k.permute(0, 2, 1, 3).contiguous().pin_memory().permute(0, 2, 1, 3),
+          v.permute(0, 2, 1, 3).contiguous().pin_memory().permute(0, 2, 1, 3)) for k, v in host]
+    out_t = fn(t, **kwargs)
+    for (kt, vt), (kh, vh) in zip(out_t, out_h):
+        assert torch.equal(kt, kh) and torch.equal(vt, vh)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        fn([(k.clone(), v.clone()) for k, v in host], **kwargs)
