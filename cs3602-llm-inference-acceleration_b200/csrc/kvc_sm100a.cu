@@ -14,6 +14,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <utility>
+#include <vector>
 
 #include "kvc_device.cuh"
 #include "kvc_fused_tma.cuh"
@@ -413,11 +415,21 @@ static FusedFn pick_tma(int dtype, int cpr, int nt) {
 }
 static bool tma_supported_cpr(int cpr) { return cpr == 8 || cpr == 10 || cpr == 16 || cpr == 20 || cpr == 32; }
 
-static int ensure_tma_attrs(const void* fn) {
+static int ensure_tma_attrs(const void* fn, int device) {
+    // Function attributes are sticky per (function, device): set them once, not on every decode step.
+    static std::mutex mu;
+    static std::vector<std::pair<const void*, int>> done;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        for (const auto& d : done)
+            if (d.first == fn && d.second == device) return KVC_OK;
+    }
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxSmemOptin);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(max dynamic smem)");
     e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(carveout)");
+    std::lock_guard<std::mutex> lock(mu);
+    done.emplace_back(fn, device);
     return KVC_OK;
 }
 
@@ -554,7 +566,7 @@ int kvc_compress_layers(const kvc_shape* shape, int32_t n_layers, const kvc_laye
             bd.off_stage = tp.off_stage;
             bd.upc = tp.upc;
             grid.x = (unsigned)(((int64_t)B * H + tp.upc - 1) / tp.upc);
-            st = ensure_tma_attrs((const void*)fn);
+            st = ensure_tma_attrs((const void*)fn, shape->device);
             if (st != KVC_OK) return st;
             fn<<<grid, tp.nt, tp.smem, (cudaStream_t)stream>>>(bd);
             cudaError_t err = cudaGetLastError();

@@ -113,73 +113,124 @@ def _require_gpu_reachable(t: torch.Tensor, what: str) -> None:
 
 def _rows_ok(t: torch.Tensor) -> bool:
     e = t.element_size()
-    return (t.stride(3) == 1 or t.size(3) == 1) and all((t.stride(i) * e) % 16 == 0 for i in range(3)) \
-        and t.data_ptr() % 16 == 0
+    st = t.stride()
+    return (st[3] == 1 or t.size(3) == 1) and (st[0] * e) % 16 == 0 and (st[1] * e) % 16 == 0 \
+        and (st[2] * e) % 16 == 0 and t.data_ptr() % 16 == 0
 
 
 def _stream_ptr(device: torch.device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
-def run_plans(kv: Sequence[Tuple[torch.Tensor, torch.Tensor]], plans: Sequence[P.LayerPlan],
-              given_indices: Optional[dict] = None, return_indices: bool = False):
-    """Apply per-layer plans to a list of (K, V) pairs.
+class PlanSet:
+    """The per-layer plans of one call with everything the launch needs precomputed (which layers
+    gather, which become views, the packed ``kvc_layer_plan`` records).  Built once per distinct
+    (method arguments, sequence lengths) and cached by the method wrappers: a decode loop calls the
+    same plan every step, so the per-step host work is pointers and one allocation."""
+
+    __slots__ = ("plans", "gather", "views", "packed", "out_lens")
+
+    def __init__(self, plans: Sequence[P.LayerPlan]):
+        self.plans = list(plans)
+        self.gather = [i for i, p in enumerate(self.plans) if p.kind == P.GATHER]
+        self.views = [(i, p.view_n) for i, p in enumerate(self.plans) if p.kind == P.VIEW]
+        self.packed = {i: _PLAN.pack(p.seq_len, p.sink, p.sel_lo, p.sel_hi, p.k_sel, p.tail, p.score, p.pool_kernel)
+                       for i, p in ((i, self.plans[i]) for i in self.gather)}
+        self.out_lens = {i: self.plans[i].out_len for i in self.gather}
+
+    def __len__(self):
+        return len(self.plans)
+
+    def __getitem__(self, i):
+        return self.plans[i]
+
+    def __iter__(self):
+        return iter(self.plans)
+
+
+def run_plans(kv: Sequence[Tuple[torch.Tensor, torch.Tensor]], plans, given_indices: Optional[dict] = None,
+              return_indices: bool = False):
+    """Apply per-layer plans (a list of ``LayerPlan`` or a cached :class:`PlanSet`) to a list of (K, V) pairs.
 
     KEEP layers keep their tensor objects, VIEW layers become ``x[:, :, -n:, :]`` views (both
     exactly as the reference does); all GATHER layers of the call go to the device library in
     one ``kvc_compress_layers`` call per (device, dtype, B, H, D) group — normally one launch.
+    The outputs of a group with one common length are carved out of ONE allocation.
 
-    given_indices: {layer_idx: int32 CUDA tensor [B, H, k_sel]} for SCORE_GIVEN_INDEX plans.
+    given_indices: {layer_idx: int32 tensor [B, H, k_sel]} for SCORE_GIVEN_INDEX plans.
     return_indices: also return {layer_idx: int32 tensor [B, H, C]} of kept absolute rows.
     """
+    ps = plans if isinstance(plans, PlanSet) else PlanSet(plans)
     out: List[Tuple[torch.Tensor, torch.Tensor]] = list(kv)
-    groups = {}
-    for li, plan in enumerate(plans):
-        if plan.kind == P.KEEP:
-            continue
+    for li, n in ps.views:
         keys, values = kv[li][0], kv[li][1]
-        if plan.kind == P.VIEW:
-            n = plan.view_n
-            out[li] = (keys[:, :, -n:, :], values[:, :, -n:, :])
-            continue
+        out[li] = (keys[:, :, -n:, :], values[:, :, -n:, :])
+    indices = {}
+    if not ps.gather:
+        return (out, indices) if return_indices else out
+
+    groups = {}
+    for li in ps.gather:
+        keys, values = kv[li][0], kv[li][1]
         _require_gpu_reachable(keys, f"layer {li} keys")
         _require_gpu_reachable(values, f"layer {li} values")
-        if keys.dim() != 4 or values.shape != keys.shape or values.dtype != keys.dtype or values.device != keys.device:
+        shape = keys.shape
+        if len(shape) != 4 or values.shape != shape or values.dtype != keys.dtype or values.device != keys.device:
             raise ValueError(f"layer {li}: keys/values must be matching [B, H, S, D] tensors")
-        if keys.size(2) != plan.seq_len:
-            raise ValueError(f"layer {li}: plan built for seq_len {plan.seq_len}, tensor has {keys.size(2)}")
-        B, H, _, D = keys.shape
-        if (D * keys.element_size()) % 16 != 0:
-            raise ValueError(f"layer {li}: head_dim*itemsize = {D * keys.element_size()} B is not a multiple of 16")
-        groups.setdefault((keys.device, keys.dtype, B, H, D), []).append(li)
+        if shape[2] != ps.plans[li].seq_len:
+            raise ValueError(f"layer {li}: plan built for seq_len {ps.plans[li].seq_len}, tensor has {shape[2]}")
+        if (shape[3] * keys.element_size()) % 16 != 0:
+            raise ValueError(f"layer {li}: head_dim*itemsize = {shape[3] * keys.element_size()} B is not a multiple of 16")
+        groups.setdefault((keys.device, keys.dtype, shape[0], shape[1], shape[3]), []).append((li, keys, values))
 
-    indices = {}
     keepalive = []
-    for (device, dtype, B, H, D), layer_ids in groups.items():
-        lib = load_library()
+    lib = load_library()
+    for (device, dtype, B, H, D), members in groups.items():
         on_host = device.type == "cpu"
         if on_host and not torch.cuda.is_available():
             raise RuntimeError("pinned host tensors need a CUDA device to run on: there is no CPU path")
         run_device = torch.device("cuda", torch.cuda.current_device()) if on_host else device
         alloc = dict(dtype=dtype, pin_memory=True) if on_host else dict(dtype=dtype, device=device)
-        plan_buf = bytearray(_PLAN.size * len(layer_ids))
-        io_buf = bytearray(_IO.size * len(layer_ids))
-        for n, li in enumerate(layer_ids):
-            plan = plans[li]
-            keys, values = kv[li][0], kv[li][1]
+        n = len(members)
+        lens = [ps.out_lens[li] for li, _, _ in members]
+        C0 = lens[0]
+        uniform = all(c == C0 for c in lens)
+        # one allocation for every output of the group; per-layer tensors are views of it
+        if uniform:
+            big = torch.empty((2 * n, B, H, C0, D), **alloc)
+            parts = big.unbind(0)
+            base = big.data_ptr()
+            step = B * H * C0 * D * big.element_size()
+        else:  # per-layer budgets (pyramid_kv): one flat buffer split into [K0, V0, K1, V1, ...]
+            sizes = [B * H * c * D for c in lens for _ in (0, 1)]
+            flat = torch.empty((sum(sizes),), **alloc)
+            chunks = flat.split_with_sizes(sizes)
+            base = flat.data_ptr()
+            esz = flat.element_size()
+            offs = [0]
+            for sz in sizes:
+                offs.append(offs[-1] + sz * esz)
+        plan_buf = bytearray(_PLAN.size * n)
+        io_buf = bytearray(_IO.size * n)
+        for m, (li, keys, values) in enumerate(members):
+            plan = ps.plans[li]
             if not _rows_ok(keys):
                 keys = keys.contiguous().pin_memory() if on_host else keys.contiguous()
                 keepalive.append(keys)
             if not _rows_ok(values):
                 values = values.contiguous().pin_memory() if on_host else values.contiguous()
                 keepalive.append(values)
-            C = plan.out_len
-            k_out = torch.empty((B, H, C, D), **alloc)
-            v_out = torch.empty((B, H, C, D), **alloc)
+            if uniform:
+                k_out, v_out = parts[2 * m], parts[2 * m + 1]
+                k_out_ptr, v_out_ptr = base + 2 * m * step, base + (2 * m + 1) * step
+            else:
+                k_out = chunks[2 * m].view(B, H, lens[m], D)
+                v_out = chunks[2 * m + 1].view(B, H, lens[m], D)
+                k_out_ptr, v_out_ptr = base + offs[2 * m], base + offs[2 * m + 1]
             out[li] = (k_out, v_out)
             idx_out_ptr = 0
             if return_indices:
-                idx = torch.empty((B, H, C), **dict(alloc, dtype=torch.int32))
+                idx = torch.empty((B, H, lens[m]), **dict(alloc, dtype=torch.int32))
                 indices[li] = idx
                 idx_out_ptr = idx.data_ptr()
             idx_in_ptr = 0
@@ -194,14 +245,13 @@ def run_plans(kv: Sequence[Tuple[torch.Tensor, torch.Tensor]], plans: Sequence[P
                     gi = gi.pin_memory()
                 idx_in_ptr = gi.data_ptr()
                 keepalive.append(gi)
-            _PLAN.pack_into(plan_buf, n * _PLAN.size, plan.seq_len, plan.sink, plan.sel_lo, plan.sel_hi, plan.k_sel,
-                            plan.tail, plan.score, plan.pool_kernel)
-            _IO.pack_into(io_buf, n * _IO.size, keys.data_ptr(), values.data_ptr(), k_out.data_ptr(),
-                          v_out.data_ptr(), keys.stride(0), keys.stride(1), keys.stride(2), values.stride(0),
-                          values.stride(1), values.stride(2), idx_out_ptr, idx_in_ptr)
+            plan_buf[m * _PLAN.size:(m + 1) * _PLAN.size] = ps.packed[li]
+            ks, vs = keys.stride(), values.stride()
+            _IO.pack_into(io_buf, m * _IO.size, keys.data_ptr(), values.data_ptr(), k_out_ptr, v_out_ptr,
+                          ks[0], ks[1], ks[2], vs[0], vs[1], vs[2], idx_out_ptr, idx_in_ptr)
         dev_index = run_device.index if run_device.index is not None else torch.cuda.current_device()
-        shape = _SHAPE.pack(B, H, D, KVC_DTYPE[dtype], dev_index)
-        status = lib.kvc_compress_layers(shape, len(layer_ids), bytes(plan_buf), bytes(io_buf),
+        shape_rec = _SHAPE.pack(B, H, D, KVC_DTYPE[dtype], dev_index)
+        status = lib.kvc_compress_layers(shape_rec, n, bytes(plan_buf), bytes(io_buf),
                                          ctypes.c_void_p(_stream_ptr(run_device)))
         _check(status, "kvc_compress_layers")
         if on_host:

@@ -1,11 +1,14 @@
 """Shared entry sequence of the eight compress functions."""
 
-from typing import List, Sequence, Tuple
+from typing import Callable, List, Sequence, Tuple
 
 import torch
 
 from .. import _engine
 from ..utils import normalize_kv_cache
+
+_PLAN_CACHE = {}
+_PLAN_CACHE_MAX = 512
 
 
 def as_layer_list(past_key_values) -> List[Tuple[torch.Tensor, torch.Tensor]]:
@@ -16,6 +19,24 @@ def as_layer_list(past_key_values) -> List[Tuple[torch.Tensor, torch.Tensor]]:
 
 def seq_lens(layers: Sequence[Tuple[torch.Tensor, torch.Tensor]]) -> List[int]:
     return [layer[0].size(2) for layer in layers]
+
+
+def cached_plans(plan_fn: Callable, lens: Sequence[int], *args, skip_layers=()) -> "_engine.PlanSet":
+    """``plan_fn(lens, *args, skip_layers)`` as a :class:`_engine.PlanSet`, memoised on its arguments.
+    A decode loop asks for the same plan every step (S = cap + 1 for every layer), so the planner's
+    integer arithmetic and the packing of the launch records run once, not per step.  Plans are pure
+    functions of these arguments; a planner error (``ValueError``) is never cached."""
+    try:
+        key = (plan_fn.__name__, tuple(lens), args, tuple(skip_layers))
+        hit = _PLAN_CACHE.get(key)
+    except TypeError:  # unhashable argument: plan without the cache
+        return _engine.PlanSet(plan_fn(lens, *args, skip_layers))
+    if hit is None:
+        hit = _engine.PlanSet(plan_fn(lens, *args, skip_layers))
+        if len(_PLAN_CACHE) >= _PLAN_CACHE_MAX:
+            _PLAN_CACHE.clear()
+        _PLAN_CACHE[key] = hit
+    return hit
 
 
 def execute(layers, plans, given_indices=None):

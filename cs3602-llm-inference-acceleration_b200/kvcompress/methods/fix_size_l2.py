@@ -5,7 +5,7 @@ from typing import List, Tuple
 import torch
 
 from .. import _planner
-from ._common import as_layer_list, execute, seq_lens
+from ._common import as_layer_list, cached_plans, execute, seq_lens
 
 
 def _random_indices(keys: torch.Tensor, zone_end: int, count: int) -> torch.Tensor:
@@ -28,7 +28,7 @@ def fix_size_l2_compress(past_key_values, fix_kv_size: int = 1024, keep_ratio: f
     protected, the rest of the budget is chosen from the older tokens by ``strategy``
     ("keep_low" / "keep_high" L2 norm, or "random").  Unknown strategies raise ``ValueError``."""
     layers = as_layer_list(past_key_values)
-    plans = _planner.plan_fix_size(seq_lens(layers), fix_kv_size, keep_ratio, strategy, skip_layers)
+    plans = cached_plans(_planner.plan_fix_size, seq_lens(layers), fix_kv_size, keep_ratio, strategy, skip_layers=skip_layers)
     given = None
     if strategy == "random":
         given = {li: _random_indices(layers[li][0], p.sel_hi, p.k_sel)

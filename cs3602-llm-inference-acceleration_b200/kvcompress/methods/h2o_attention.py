@@ -18,7 +18,7 @@ from typing import Dict, List, Optional, Tuple
 import torch
 
 from .. import _planner
-from ._common import as_layer_list, execute, seq_lens
+from ._common import as_layer_list, cached_plans, execute, seq_lens
 
 
 class H2OAttentionManager:
@@ -94,7 +94,7 @@ def h2o_attention_compress(past_key_values, attention_scores=None, h2o_manager: 
         return layers
     if h2o_manager is not None and attention_scores is not None:
         h2o_manager.update_attention_scores(attention_scores, skip_layers)  # :274-275
-    plans = _planner.plan_h2o(seq_lens(layers), start_size, heavy_hitter_size, recent_size, skip_layers)
+    plans = cached_plans(_planner.plan_h2o, seq_lens(layers), start_size, heavy_hitter_size, recent_size, skip_layers=skip_layers)
     if h2o_manager is None:
         return execute(layers, plans)
 

@@ -5,7 +5,7 @@ from typing import List, Tuple
 import torch
 
 from .. import _planner
-from ._common import as_layer_list, execute, seq_lens
+from ._common import as_layer_list, cached_plans, execute, seq_lens
 
 
 def l2_compress(past_key_values, keep_ratio: float = 1.0, prune_after: int = 1000,
@@ -16,7 +16,7 @@ def l2_compress(past_key_values, keep_ratio: float = 1.0, prune_after: int = 100
     in ``skip_layers`` and everything when ``keep_ratio >= 1`` are returned as the same tensor objects.
     """
     layers = as_layer_list(past_key_values)
-    plans = _planner.plan_l2(seq_lens(layers), keep_ratio, prune_after, skip_layers)
+    plans = cached_plans(_planner.plan_l2, seq_lens(layers), keep_ratio, prune_after, skip_layers=skip_layers)
     return execute(layers, plans)
 
 

@@ -5,7 +5,7 @@ from typing import List, Tuple
 import torch
 
 from .. import _planner
-from ._common import as_layer_list, execute, seq_lens
+from ._common import as_layer_list, cached_plans, execute, seq_lens
 
 
 def recent_only_compress(past_key_values, window_size: int = 512, skip_layers: List[int] = [0, 1],
@@ -13,7 +13,7 @@ def recent_only_compress(past_key_values, window_size: int = 512, skip_layers: L
     """Keep the last ``window_size`` tokens.  Like the reference this returns *views* of the input
     (``x[:, :, -window_size:, :]``), so it moves no bytes and launches nothing."""
     layers = as_layer_list(past_key_values)
-    plans = _planner.plan_recent_only(seq_lens(layers), window_size, skip_layers)
+    plans = cached_plans(_planner.plan_recent_only, seq_lens(layers), window_size, skip_layers=skip_layers)
     return execute(layers, plans)
 
 

@@ -5,7 +5,7 @@ from typing import List, Tuple
 import torch
 
 from .. import _planner
-from ._common import as_layer_list, execute, seq_lens
+from ._common import as_layer_list, cached_plans, execute, seq_lens
 
 
 def snapkv_lite_compress(past_key_values, observation_window: int = 32, keep_size: int = 512,
@@ -16,7 +16,7 @@ def snapkv_lite_compress(past_key_values, observation_window: int = 32, keep_siz
     layers = as_layer_list(past_key_values)
     if not layers:
         return layers
-    plans = _planner.plan_snapkv(seq_lens(layers), observation_window, keep_size, pooling_kernel, skip_layers)
+    plans = cached_plans(_planner.plan_snapkv, seq_lens(layers), observation_window, keep_size, pooling_kernel, skip_layers=skip_layers)
     return execute(layers, plans)
 
 

@@ -5,7 +5,7 @@ from typing import List, Tuple
 import torch
 
 from .. import _planner
-from ._common import as_layer_list, execute, seq_lens
+from ._common import as_layer_list, cached_plans, execute, seq_lens
 
 
 def streaming_llm_compress(past_key_values, start_size: int = 4, recent_size: int = 508,
@@ -15,7 +15,7 @@ def streaming_llm_compress(past_key_values, start_size: int = 4, recent_size: in
     layers = as_layer_list(past_key_values)
     if not layers:
         return layers
-    plans = _planner.plan_streaming(seq_lens(layers), start_size, recent_size, skip_layers)
+    plans = cached_plans(_planner.plan_streaming, seq_lens(layers), start_size, recent_size, skip_layers=skip_layers)
     return execute(layers, plans)
 
 
@@ -25,7 +25,7 @@ def evict_for_space(past_key_values, num_coming: int, start_size: int = 4, recen
     layers = as_layer_list(past_key_values)
     if not layers:
         return layers
-    plans = _planner.plan_evict_for_space(seq_lens(layers), num_coming, start_size, recent_size, skip_layers)
+    plans = cached_plans(_planner.plan_evict_for_space, seq_lens(layers), num_coming, start_size, recent_size, skip_layers=skip_layers)
     return execute(layers, plans)
 
 

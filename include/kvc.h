@@ -29,6 +29,9 @@
  * pointers to [B, H, S, D] arrays whose last dimension is dense (stride 1) and
  * whose rows are 16-byte aligned; B/H/S strides are given in ELEMENTS.  Outputs are
  * dense [B, H, C, D] with C = sink + k_sel + tail.  There is no CPU path.
+ * "Device pointer" includes page-locked host memory mapped into the device's address
+ * space (cudaHostAlloc / cudaHostRegister under UVA): an offloaded cache is then read
+ * and written in place over PCIe, each needed row crossing the link once per read.
  */
 #ifndef KVC_H_
 #define KVC_H_

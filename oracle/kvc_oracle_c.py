@@ -49,7 +49,13 @@ def lib():
 
 
 def max_threads() -> int:
-    return int(lib().kvc_oracle_max_threads())
+    """Host threads this process may use.  Launchers such as torchrun export OMP_NUM_THREADS=1, which
+    would silently make the CPU baseline single-threaded: go by the CPU affinity mask instead and pass
+    the count explicitly to the C port (omp_set_num_threads)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:  # not Linux
+        return max(1, os.cpu_count() or int(lib().kvc_oracle_max_threads()))
 
 
 def norms(K: np.ndarray, dtype: str, lo: int, hi: int, nthreads: int = 0) -> np.ndarray:
