@@ -1,0 +1,242 @@
+// kvc_slab.cuh — slab-cache kernels: in-place append (+ key norms) and in-place compaction.
+//
+// The container step on both sides of the compress call: replaces the
+// torch.cat of HF's cache.update (transformers cache_utils.py:119-120), the fresh-tensor gather of the
+// compress functions and the rebuild in to_dynamic_cache (reference utils.py:12-27).
+//
+//   kvc_slab_append_kernel    one thread per appended row: copy K and V rows into the slab and
+//                             record dtype(sqrt(sum k^2)) with the SAME chunk/tree summation as the
+//                             fused scan (row_sumsq tree), so stored norms are bit-identical to what
+//                             kvc_compress_layers would compute from the rows.
+//   kvc_slab_compress_kernel  per (layer, batch, head): radix keys from the stored norms (2-4 B per
+//                             token instead of D*e), select, then slide kept rows down in place.
+//                             Rows move in rounds of (staging warps x 32) output rows: every warp
+//                             bulk-loads its 32 source rows, the CTA synchronises, then every warp
+//                             bulk-stores.  Kept rows are ascending and never move up (src >= dst),
+//                             so sources of later rounds lie above every destination written so far.
+#pragma once
+#include "kvc_fused_tma.cuh"
+
+namespace kvc {
+
+struct SlabLayerDev {
+    char* k;
+    char* v;
+    char* n;
+    int32_t* idx_out;
+    const int32_t* idx_in;
+    int64_t ksb, ksh, vsb, vsh, nsb, nsh;  // BYTE strides (batch, head)
+    int32_t S, sink, lo, hi, ksel, tail, score, pool;
+    int64_t pad;
+};
+static_assert(sizeof(SlabLayerDev) == 128, "SlabLayerDev is passed by value in kernel params");
+
+struct SlabBatchDev {
+    int32_t B, H;
+    int32_t idx_cap, nsw;
+    int32_t off_hist, off_idx, off_keys, off_stage;
+    SlabLayerDev layers[KVC_MAX_LAYERS_PER_LAUNCH];
+};
+
+struct AppendLayerDev {
+    const char* k_new;
+    const char* v_new;
+    char* k;
+    char* v;
+    char* n;
+    int64_t nksb, nksh, nkss, nvsb, nvsh, nvss;  // new rows: BYTE strides
+    int64_t ksb, ksh, vsb, vsh, nsb, nsh;        // slab: BYTE strides
+    int32_t cur_len, n_new;
+};
+static_assert(sizeof(AppendLayerDev) == 144, "AppendLayerDev is passed by value in kernel params");
+
+struct AppendBatchDev {
+    int32_t B, H;
+    int32_t max_new, pad;
+    AppendLayerDev layers[KVC_MAX_LAYERS_PER_LAUNCH];
+};
+
+constexpr int kMiscFirst = 3;  // misc[] slot: first output row whose source row differs from it
+
+// Same value as row_sumsq_smem (chunk sums + balanced tree; the tree is invariant under the
+// scan's XOR read order), reading the row from global memory and optionally copying it.
+template <int DT, int CPR>
+__device__ __forceinline__ float row_sumsq_copy(const char* src, char* dst) {
+    using Tr = Traits<DT>;
+    constexpr int SB = swz_bits(CPR);
+    constexpr int G = 1 << SB;
+    float acc[CPR];
+#pragma unroll
+    for (int c = 0; c < CPR; ++c) {
+        const int4 v = *reinterpret_cast<const int4*>(src + c * 16);
+        acc[c] = Tr::sumsq(v, 0.f);
+        *reinterpret_cast<int4*>(dst + c * 16) = v;
+    }
+    float tot = 0.f;
+#pragma unroll
+    for (int g = 0; g < CPR / G; ++g) {
+#pragma unroll
+        for (int s = 1; s < G; s <<= 1) {
+#pragma unroll
+            for (int m = 0; m < G; m += 2 * s) acc[g * G + m] += acc[g * G + m + s];
+        }
+        tot = (g == 0) ? acc[0] : tot + acc[g * G];
+    }
+    return tot;
+}
+
+template <int DT, int CPR>
+__global__ void __launch_bounds__(128) kvc_slab_append_kernel(const __grid_constant__ AppendBatchDev bd) {
+    using Tr = Traits<DT>;
+    using Key = typename Tr::Key;
+    constexpr int RB = CPR * 16;
+    const AppendLayerDev& L = bd.layers[blockIdx.y];
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // flat (bh, t)
+    const int T = L.n_new;
+    if (r >= (int64_t)bd.B * bd.H * T) return;
+    const int bh = (int)(r / T), t = (int)(r - (int64_t)bh * T);
+    const int b = bh / bd.H, h = bh - b * bd.H;
+    const int row = L.cur_len + t;
+    const char* ks = L.k_new + (int64_t)b * L.nksb + (int64_t)h * L.nksh + (int64_t)t * L.nkss;
+    const char* vs = L.v_new + (int64_t)b * L.nvsb + (int64_t)h * L.nvsh + (int64_t)t * L.nvss;
+    char* kd = L.k + (int64_t)b * L.ksb + (int64_t)h * L.ksh + (int64_t)row * RB;
+    char* vd = L.v + (int64_t)b * L.vsb + (int64_t)h * L.vsh + (int64_t)row * RB;
+    const float ss = row_sumsq_copy<DT, CPR>(ks, kd);
+#pragma unroll
+    for (int c = 0; c < CPR; ++c) *reinterpret_cast<int4*>(vd + c * 16) = *reinterpret_cast<const int4*>(vs + c * 16);
+    Key* nd = reinterpret_cast<Key*>(L.n + (int64_t)b * L.nsb + (int64_t)h * L.nsh);
+    nd[row] = (Key)Tr::to_raw(sqrtf(ss));
+}
+
+template <int DT, int CPR, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) kvc_slab_compress_kernel(const __grid_constant__ SlabBatchDev bd) {
+    using Tr = Traits<DT>;
+    using Key = typename Tr::Key;
+    constexpr int RB = CPR * 16;
+    constexpr int kShift0 = Tr::kKeyBits - kHistBits;
+
+    const SlabLayerDev& L = bd.layers[blockIdx.y];
+    const int bh = blockIdx.x;
+    const int b = bh / bd.H, h = bh - b * bd.H;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    extern __shared__ __align__(128) unsigned char smem[];
+    int32_t* misc = reinterpret_cast<int32_t*>(smem);
+    uint32_t* hist = reinterpret_cast<uint32_t*>(smem + bd.off_hist);
+    int32_t* sidx = reinterpret_cast<int32_t*>(smem + bd.off_idx);
+    Key* keys = reinterpret_cast<Key*>(smem + bd.off_keys);
+    const int nsw = bd.nsw;
+    const bool stager = warp < nsw;
+    const uint32_t slot = smem_u32(smem + bd.off_stage) + (uint32_t)warp * (32 * RB);
+    const uint32_t bar = smem_u32(smem + kMiscInts * 4) + (uint32_t)warp * 8;
+    uint32_t parity = 0;
+    if (stager) {
+        if (lane == 0) {
+            mbar_init(bar, 1);
+            mbar_init_fence();
+        }
+        __syncwarp();
+    }
+
+    const int R = L.hi - L.lo;
+    const int ksel = L.ksel;
+    const int score = L.score;
+    char* kbase = L.k + (int64_t)b * L.ksb + (int64_t)h * L.ksh;
+    char* vbase = L.v + (int64_t)b * L.vsb + (int64_t)h * L.vsh;
+    Key* nbase = reinterpret_cast<Key*>(L.n + (int64_t)b * L.nsb + (int64_t)h * L.nsh);
+    const int sink = L.sink;
+    const int C = sink + ksel + L.tail;
+    const int tail0 = L.S - L.tail - sink - ksel;  // src row = j + tail0 for tail rows
+
+    if (tid == 0) {
+        misc[kMiscMaxRaw] = 0;
+        misc[kMiscFirst] = C;
+    }
+    if (ksel > 0 && score == KVC_SCORE_GIVEN_INDEX) {
+        const int32_t* src = L.idx_in + (int64_t)bh * ksel;
+        for (int i = tid; i < ksel; i += NT) sidx[i] = src[i];
+    } else if (ksel > 0) {
+        // ---------------------------------------------------------- keys from the stored norms
+        for (int i = tid; i < kHistBins; i += NT) hist[i] = 0;
+        __syncthreads();
+        const bool snap = (score == KVC_SCORE_SNAPKV_POOL);
+        const bool desc = (score == KVC_SCORE_L2_HIGH);
+        uint32_t local_max = 0;
+        for (int i = tid; i < R; i += NT) {
+            const uint32_t raw = (uint32_t)nbase[L.lo + i];
+            if (snap) {
+                keys[i] = (Key)raw;
+                local_max = max(local_max, raw);
+            } else {
+                const Key key = ordered_key<Key>(raw, desc);
+                keys[i] = key;
+                atomicAdd(&hist[(uint32_t)key >> kShift0], 1u);
+            }
+        }
+        if (snap) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
+            if (lane == 0) atomicMax(reinterpret_cast<uint32_t*>(&misc[kMiscMaxRaw]), local_max);
+        }
+        __syncthreads();
+        if (snap) snapkv_transform<DT, NT>(keys, R, L.pool, hist, misc);
+        block_radix_select<Key, NT>(keys, R, ksel, hist, misc, sidx, L.lo);
+    }
+    __syncthreads();
+
+    auto src_row = [&](int j) -> int { return j < sink ? j : (j < sink + ksel ? sidx[j - sink] : j + tail0); };
+    // ---------------------------------------------------------- first row that actually moves
+    {
+        int first = C;
+        for (int j = tid; j < C; j += NT)
+            if (src_row(j) != j) {
+                first = j;
+                break;  // rows are ascending: this thread's later rows move too
+            }
+        if (first < C) atomicMin(&misc[kMiscFirst], first);
+    }
+    if (L.idx_out != nullptr) {
+        int32_t* io = L.idx_out + (int64_t)bh * C;
+        for (int j = tid; j < C; j += NT) io[j] = src_row(j);
+    }
+    __syncthreads();
+    const int jf = misc[kMiscFirst];
+    if (jf >= C) return;  // nothing moves (CTA-uniform)
+
+    // ---------------------------------------------------------- slide rows down, K then V, in rounds
+    const int nb = (C - jf + 31) >> 5;
+    for (int t0 = 0; t0 < 2 * nb; t0 += nsw) {
+        const int t = t0 + warp;
+        const bool active = stager && t < 2 * nb;
+        const bool isv = t >= nb;
+        const int j0 = jf + ((isv ? t - nb : t) << 5);
+        const int rows = min(32, C - j0);
+        if (active) {
+            const int j = j0 + lane;
+            const int row = lane < rows ? src_row(j) : 0;
+            const char* src = (isv ? vbase : kbase) + (int64_t)row * RB;
+            warp_load_rows<RB>(slot, bar, src, rows, true, lane);
+            mbar_wait(bar, parity);
+            parity ^= 1;
+        }
+        __syncthreads();  // every source row of this round is on chip before any destination is written
+        if (active) {
+            if (lane == 0) {
+                bulk_s2g((isv ? vbase : kbase) + (int64_t)j0 * RB, slot, (uint32_t)rows * RB);
+                bulk_commit();
+                bulk_wait_read<0>();
+            }
+            __syncwarp();
+        }
+    }
+    // ---------------------------------------------------------- norms slide with their rows
+    for (int c0 = jf; c0 < C; c0 += NT) {
+        const int j = c0 + tid;
+        Key val = 0;
+        if (j < C) val = nbase[src_row(j)];
+        __syncthreads();
+        if (j < C) nbase[j] = val;
+    }
+}
+
+}  // namespace kvc

@@ -19,6 +19,7 @@
 
 #include "kvc_device.cuh"
 #include "kvc_fused_tma.cuh"
+#include "kvc_slab.cuh"
 
 #define KVC_STR2(x) #x
 #define KVC_STR(x) KVC_STR2(x)
@@ -433,6 +434,64 @@ static int ensure_tma_attrs(const void* fn, int device) {
     return KVC_OK;
 }
 
+
+// ------------------------------------------------------------------ slab kernels: variant tables
+using SlabFn = void (*)(const SlabBatchDev);
+using AppendFn = void (*)(const AppendBatchDev);
+
+template <int DT, int NT, int MINB>
+static SlabFn pick_slab_cpr(int cpr) {
+    switch (cpr) {
+        case 8: return kvc_slab_compress_kernel<DT, 8, NT, MINB>;
+        case 10: return kvc_slab_compress_kernel<DT, 10, NT, MINB>;
+        case 16: return kvc_slab_compress_kernel<DT, 16, NT, MINB>;
+        case 20: return kvc_slab_compress_kernel<DT, 20, NT, MINB>;
+        case 32: return kvc_slab_compress_kernel<DT, 32, NT, MINB>;
+        default: return nullptr;
+    }
+}
+template <int DT>
+static SlabFn pick_slab_nt(int cpr, int nt) {
+    return nt == 512 ? pick_slab_cpr<DT, 512, 1>(cpr) : pick_slab_cpr<DT, 256, 3>(cpr);
+}
+static SlabFn pick_slab(int dtype, int cpr, int nt) {
+    switch (dtype) {
+        case KVC_DTYPE_F32: return pick_slab_nt<KVC_DTYPE_F32>(cpr, nt);
+        case KVC_DTYPE_F16: return pick_slab_nt<KVC_DTYPE_F16>(cpr, nt);
+        default: return pick_slab_nt<KVC_DTYPE_BF16>(cpr, nt);
+    }
+}
+template <int DT>
+static AppendFn pick_append_cpr(int cpr) {
+    switch (cpr) {
+        case 8: return kvc_slab_append_kernel<DT, 8>;
+        case 10: return kvc_slab_append_kernel<DT, 10>;
+        case 16: return kvc_slab_append_kernel<DT, 16>;
+        case 20: return kvc_slab_append_kernel<DT, 20>;
+        case 32: return kvc_slab_append_kernel<DT, 32>;
+        default: return nullptr;
+    }
+}
+static AppendFn pick_append(int dtype, int cpr) {
+    switch (dtype) {
+        case KVC_DTYPE_F32: return pick_append_cpr<KVC_DTYPE_F32>(cpr);
+        case KVC_DTYPE_F16: return pick_append_cpr<KVC_DTYPE_F16>(cpr);
+        default: return pick_append_cpr<KVC_DTYPE_BF16>(cpr);
+    }
+}
+
+static int check_shape(const kvc_shape* shape, int* cpr_out) {
+    if (!shape) return KVC_ERR_INVALID_ARG;
+    const int B = shape->batch, H = shape->heads, D = shape->head_dim, dt = shape->dtype;
+    if (B <= 0 || H <= 0 || D <= 0) return KVC_ERR_INVALID_ARG;
+    if (dt != KVC_DTYPE_F32 && dt != KVC_DTYPE_F16 && dt != KVC_DTYPE_BF16) return KVC_ERR_UNSUPPORTED;
+    const int e = elem_bytes(dt);
+    if (((int64_t)D * e) % 16 != 0) return KVC_ERR_UNSUPPORTED;
+    if ((int64_t)B * H > 0x7fffffffLL) return KVC_ERR_INVALID_ARG;
+    *cpr_out = D * e / 16;
+    return KVC_OK;
+}
+
 }  // namespace kvc
 
 using namespace kvc;
@@ -665,6 +724,167 @@ int kvc_select(int32_t dtype, int32_t device, const void* scores, int64_t n_rows
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return cuda_fail(err, "kvc_select_kernel launch");
     g_launches.fetch_add(1);
+    return KVC_OK;
+}
+
+int kvc_slab_append(const kvc_shape* shape, int32_t n_layers, const kvc_slab_layer* slabs,
+                    const kvc_slab_new_rows* rows, void* stream) {
+    int cpr = 0;
+    int st = check_shape(shape, &cpr);
+    if (st != KVC_OK) return st;
+    if (n_layers < 0 || (n_layers > 0 && (!slabs || !rows))) return KVC_ERR_INVALID_ARG;
+    if (n_layers == 0) return KVC_OK;
+    if (!tma_supported_cpr(cpr)) return KVC_ERR_UNSUPPORTED;
+    const int B = shape->batch, H = shape->heads, dt = shape->dtype;
+    const int e = elem_bytes(dt);
+    for (int l = 0; l < n_layers; ++l) {
+        const kvc_slab_layer& sl = slabs[l];
+        const kvc_slab_new_rows& r = rows[l];
+        if (r.n_new < 0 || r.cur_len < 0) return KVC_ERR_INVALID_ARG;
+        if (r.n_new == 0) continue;
+        if (!sl.k || !sl.v || !sl.norms || !r.k_new || !r.v_new) return KVC_ERR_INVALID_ARG;
+        const uintptr_t a = (uintptr_t)sl.k | (uintptr_t)sl.v | (uintptr_t)r.k_new | (uintptr_t)r.v_new;
+        if (a & 15) return KVC_ERR_UNSUPPORTED;
+        const int64_t sb = sl.k_stride_b | sl.k_stride_h | sl.v_stride_b | sl.v_stride_h | r.k_stride_b | r.k_stride_h |
+                           r.k_stride_s | r.v_stride_b | r.v_stride_h | r.v_stride_s;
+        if ((sb * e) & 15) return KVC_ERR_UNSUPPORTED;
+        if ((int64_t)B * H * r.n_new > 0x7fffffffLL) return KVC_ERR_TOO_LARGE;
+    }
+    st = set_device(shape->device);
+    if (st != KVC_OK) return st;
+    AppendFn fn = pick_append(dt, cpr);
+    for (int l0 = 0; l0 < n_layers; l0 += KVC_MAX_LAYERS_PER_LAUNCH) {
+        const int nl = (n_layers - l0) < KVC_MAX_LAYERS_PER_LAUNCH ? (n_layers - l0) : KVC_MAX_LAYERS_PER_LAUNCH;
+        AppendBatchDev bd;
+        memset(&bd, 0, sizeof(bd));
+        bd.B = B;
+        bd.H = H;
+        int n_active = 0, max_new = 0;
+        for (int l = 0; l < nl; ++l) {
+            const kvc_slab_layer& sl = slabs[l0 + l];
+            const kvc_slab_new_rows& r = rows[l0 + l];
+            if (r.n_new == 0) continue;
+            AppendLayerDev& d = bd.layers[n_active++];
+            d.k_new = (const char*)r.k_new;
+            d.v_new = (const char*)r.v_new;
+            d.k = (char*)sl.k;
+            d.v = (char*)sl.v;
+            d.n = (char*)sl.norms;
+            d.nksb = r.k_stride_b * e;
+            d.nksh = r.k_stride_h * e;
+            d.nkss = r.k_stride_s * e;
+            d.nvsb = r.v_stride_b * e;
+            d.nvsh = r.v_stride_h * e;
+            d.nvss = r.v_stride_s * e;
+            d.ksb = sl.k_stride_b * e;
+            d.ksh = sl.k_stride_h * e;
+            d.vsb = sl.v_stride_b * e;
+            d.vsh = sl.v_stride_h * e;
+            d.nsb = sl.n_stride_b * key_bytes(dt);
+            d.nsh = sl.n_stride_h * key_bytes(dt);
+            d.cur_len = r.cur_len;
+            d.n_new = r.n_new;
+            if (r.n_new > max_new) max_new = r.n_new;
+        }
+        if (n_active == 0) continue;
+        bd.max_new = max_new;
+        const int64_t threads = (int64_t)B * H * max_new;
+        dim3 grid((unsigned)((threads + 127) / 128), (unsigned)n_active, 1);
+        fn<<<grid, 128, 0, (cudaStream_t)stream>>>(bd);
+        cudaError_t err = cudaGetLastError();
+        if (err != cudaSuccess) return cuda_fail(err, "kvc_slab_append_kernel launch");
+        g_launches.fetch_add(1);
+    }
+    return KVC_OK;
+}
+
+int kvc_slab_compress(const kvc_shape* shape, int32_t n_layers, const kvc_layer_plan* plans,
+                      const kvc_slab_layer* slabs, int32_t* const* idx_out, const int32_t* const* idx_in,
+                      void* stream) {
+    int cpr = 0;
+    int st = check_shape(shape, &cpr);
+    if (st != KVC_OK) return st;
+    if (n_layers < 0 || (n_layers > 0 && (!slabs || !plans))) return KVC_ERR_INVALID_ARG;
+    if (n_layers == 0) return KVC_OK;
+    if (!tma_supported_cpr(cpr)) return KVC_ERR_UNSUPPORTED;
+    const int B = shape->batch, H = shape->heads, dt = shape->dtype;
+    const int e = elem_bytes(dt);
+    for (int l = 0; l < n_layers; ++l) {
+        const kvc_layer_plan& p = plans[l];
+        const kvc_slab_layer& sl = slabs[l];
+        if (p.seq_len < 0 || p.sink < 0 || p.k_sel < 0 || p.tail < 0) return KVC_ERR_INVALID_ARG;
+        if (p.sink > p.seq_len || p.tail > p.seq_len) return KVC_ERR_INVALID_ARG;
+        if ((int64_t)p.sink + p.k_sel + p.tail > p.seq_len) return KVC_ERR_INVALID_ARG;
+        if (p.k_sel > 0) {
+            if (p.sel_lo < p.sink || p.sel_hi > p.seq_len - p.tail || p.sel_lo > p.sel_hi) return KVC_ERR_INVALID_ARG;
+            if (p.k_sel > p.sel_hi - p.sel_lo) return KVC_ERR_INVALID_ARG;
+            if (p.score <= KVC_SCORE_NONE || p.score > KVC_SCORE_GIVEN_INDEX) return KVC_ERR_INVALID_ARG;
+            if (p.score == KVC_SCORE_GIVEN_INDEX && (!idx_in || !idx_in[l])) return KVC_ERR_INVALID_ARG;
+            if (p.score == KVC_SCORE_SNAPKV_POOL && p.pool_kernel > 2 * kMaxPoolHalo) return KVC_ERR_UNSUPPORTED;
+        }
+        if (p.sink + p.k_sel + p.tail == 0) continue;
+        if (!sl.k || !sl.v || !sl.norms) return KVC_ERR_INVALID_ARG;
+        if (((uintptr_t)sl.k | (uintptr_t)sl.v) & 15) return KVC_ERR_UNSUPPORTED;
+        if (((sl.k_stride_b | sl.k_stride_h | sl.v_stride_b | sl.v_stride_h) * e) & 15) return KVC_ERR_UNSUPPORTED;
+    }
+    st = set_device(shape->device);
+    if (st != KVC_OK) return st;
+    for (int l0 = 0; l0 < n_layers; l0 += KVC_MAX_LAYERS_PER_LAUNCH) {
+        const int nl = (n_layers - l0) < KVC_MAX_LAYERS_PER_LAUNCH ? (n_layers - l0) : KVC_MAX_LAYERS_PER_LAUNCH;
+        SlabBatchDev bd;
+        memset(&bd, 0, sizeof(bd));
+        bd.B = B;
+        bd.H = H;
+        int n_active = 0, max_region = 0, max_ksel = 0;
+        bool any_select = false;
+        for (int l = 0; l < nl; ++l) {
+            const kvc_layer_plan& p = plans[l0 + l];
+            const kvc_slab_layer& sl = slabs[l0 + l];
+            if (p.sink + p.k_sel + p.tail == 0) continue;
+            SlabLayerDev& d = bd.layers[n_active++];
+            d.k = (char*)sl.k;
+            d.v = (char*)sl.v;
+            d.n = (char*)sl.norms;
+            d.idx_out = idx_out ? idx_out[l0 + l] : nullptr;
+            d.idx_in = idx_in ? idx_in[l0 + l] : nullptr;
+            d.ksb = sl.k_stride_b * e;
+            d.ksh = sl.k_stride_h * e;
+            d.vsb = sl.v_stride_b * e;
+            d.vsh = sl.v_stride_h * e;
+            d.nsb = sl.n_stride_b * key_bytes(dt);
+            d.nsh = sl.n_stride_h * key_bytes(dt);
+            d.S = p.seq_len;
+            d.sink = p.sink;
+            d.lo = p.sel_lo;
+            d.hi = p.sel_hi;
+            d.ksel = p.k_sel;
+            d.tail = p.tail;
+            d.score = p.k_sel > 0 ? p.score : KVC_SCORE_NONE;
+            d.pool = p.pool_kernel;
+            if (p.k_sel > 0) {
+                any_select = true;
+                if (p.k_sel > max_ksel) max_ksel = p.k_sel;
+                if (p.score != KVC_SCORE_GIVEN_INDEX && p.sel_hi - p.sel_lo > max_region) max_region = p.sel_hi - p.sel_lo;
+            }
+        }
+        if (n_active == 0) continue;
+        bd.idx_cap = (max_ksel + 3) & ~3;
+        const TmaPlan tp = plan_tma(dt, cpr, max_region, bd.idx_cap, any_select);
+        if (!tp.ok) return KVC_ERR_TOO_LARGE;
+        SlabFn fn = pick_slab(dt, cpr, tp.nt);
+        bd.nsw = tp.nsw;
+        bd.off_hist = tp.off_hist;
+        bd.off_idx = tp.off_idx;
+        bd.off_keys = tp.off_keys;
+        bd.off_stage = tp.off_stage;
+        st = ensure_tma_attrs((const void*)fn, shape->device);
+        if (st != KVC_OK) return st;
+        dim3 grid((unsigned)((int64_t)B * H), (unsigned)n_active, 1);
+        fn<<<grid, tp.nt, tp.smem, (cudaStream_t)stream>>>(bd);
+        cudaError_t err = cudaGetLastError();
+        if (err != cudaSuccess) return cuda_fail(err, "kvc_slab_compress_kernel launch");
+        g_launches.fetch_add(1);
+    }
     return KVC_OK;
 }
 

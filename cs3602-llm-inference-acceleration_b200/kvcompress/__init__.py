@@ -27,6 +27,7 @@ from .methods import (
     register_method,
     COMPRESS_METHODS,
 )
+from .slab_cache import KVSlabCache
 from .utils import (
     to_dynamic_cache,
     normalize_kv_cache,
@@ -41,6 +42,7 @@ __all__ = [
     "snapkv_lite_compress", "pyramid_kv_compress", "adaptive_l2_compress",
     "get_compress_fn", "list_methods", "register_method", "COMPRESS_METHODS",
     "to_dynamic_cache", "normalize_kv_cache", "get_cache_size_mb", "get_cache_info", "get_seq_len",
+    "KVSlabCache",
 ]
 
 __version__ = "2.0.0"

@@ -70,6 +70,11 @@ def load_library():
     lib.kvc_select.restype = ctypes.c_int
     lib.kvc_select.argtypes = [ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32,
                                ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_void_p]
+    lib.kvc_slab_append.restype = ctypes.c_int
+    lib.kvc_slab_append.argtypes = [ctypes.c_char_p, ctypes.c_int32, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_void_p]
+    lib.kvc_slab_compress.restype = ctypes.c_int
+    lib.kvc_slab_compress.argtypes = [ctypes.c_char_p, ctypes.c_int32, ctypes.c_char_p, ctypes.c_char_p,
+                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     if lib.kvc_abi_version() != 1:
         raise RuntimeError(f"{_LIB_NAME}: ABI version {lib.kvc_abi_version()} != 1 — rebuild the library")
     _lib = lib

@@ -17,7 +17,8 @@ def adaptive_l2_compress(past_key_values, target_size: int = 512, soft_limit: in
     layers = as_layer_list(past_key_values)
     if not layers:
         return layers
-    plans = cached_plans(_planner.plan_adaptive, seq_lens(layers), target_size, soft_limit, hard_limit, keep_ratio_min, keep_ratio_max, skip_layers=skip_layers)
+    plans = cached_plans(_planner.plan_adaptive, seq_lens(layers), target_size, soft_limit, hard_limit, keep_ratio_min,
+                         keep_ratio_max, skip_layers=skip_layers)
     return execute(layers, plans)
 
 

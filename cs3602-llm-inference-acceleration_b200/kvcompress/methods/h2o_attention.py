@@ -94,10 +94,12 @@ def h2o_attention_compress(past_key_values, attention_scores=None, h2o_manager: 
         return layers
     if h2o_manager is not None and attention_scores is not None:
         h2o_manager.update_attention_scores(attention_scores, skip_layers)  # :274-275
-    plans = cached_plans(_planner.plan_h2o, seq_lens(layers), start_size, heavy_hitter_size, recent_size, skip_layers=skip_layers)
+    plans = cached_plans(_planner.plan_h2o, seq_lens(layers), start_size, heavy_hitter_size, recent_size,
+                         skip_layers=skip_layers)
     if h2o_manager is None:
         return execute(layers, plans)
 
+    plans = list(plans)  # the manager rewrites per-layer plans below: never touch the cached set
     given = {}
     for li, plan in enumerate(plans):
         if plan.kind != _planner.GATHER or plan.region == 0:

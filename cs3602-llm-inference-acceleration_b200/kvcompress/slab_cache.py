@@ -1,0 +1,270 @@
+"""KVSlabCache — the cache container for the decode loop: in-place append and in-place compression.
+
+This is the step on both sides of the compress call.  The reference's loop
+(kvcompress/evaluate.py:132-166) re-allocates and copies the whole cache twice per generated token:
+
+    outputs = model(token, past_key_values=cache)          # DynamicLayer.update: torch.cat per layer
+    kv_list = list(normalize_kv_cache(outputs.past_key_values))
+    compressed = compress_fn(kv_list, skip_layers=..., **kw)   # gather into fresh tensors (+ cat)
+    cache = to_dynamic_cache(compressed)                    # reference utils.py:12-27
+
+Here every layer's K and V live in pre-allocated ``[B, H, capacity, D]`` slabs on the GPU, next to a
+``[B, H, capacity]`` array of key norms (what ``torch.norm(K, p=2, dim=-1)`` returns for those rows):
+
+    cache.update(k_new, v_new, layer_idx)     # rows written in place, their norms recorded (one kernel)
+    cache.compress_("h2o_l2", skip_layers=..., **kw)   # ONE launch for all layers, no allocation:
+                                                       # scores from the stored norms, rows slide down
+
+``compress_`` keeps exactly the rows the function of the same name keeps (same planner, same select,
+bit-identical norms) — ``tests/test_gpu_slab.py`` walks both loops side by side.  Any registered
+compress function also accepts a slab cache directly (``to_legacy_cache`` hands out views).
+"""
+
+from __future__ import annotations
+
+import ctypes
+import inspect
+import struct
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _engine
+from . import _planner as P
+
+_SLAB = struct.Struct("3P6q")    # kvc_slab_layer: k v norms | k_stride_b k_stride_h v_stride_b v_stride_h n_stride_b n_stride_h
+_ROWS = struct.Struct("2P6q2i")  # kvc_slab_new_rows: k_new v_new | 6 strides | cur_len n_new
+assert _SLAB.size == 72 and _ROWS.size == 72
+
+# method name -> (planner, planner arguments in order); defaults come from the compress function's signature
+_PLANNERS = {
+    "l2_compress": (P.plan_l2, ("keep_ratio", "prune_after")),
+    "fix_size_l2": (P.plan_fix_size, ("fix_kv_size", "keep_ratio", "strategy")),
+    "streaming_llm": (P.plan_streaming, ("start_size", "recent_size")),
+    "recent_only": (P.plan_recent_only, ("window_size",)),
+    "h2o_l2": (P.plan_h2o, ("start_size", "heavy_hitter_size", "recent_size")),
+    "snapkv_lite": (P.plan_snapkv, ("observation_window", "keep_size", "pooling_kernel")),
+    "pyramid_kv": (P.plan_pyramid, ("base_size", "layer_decay", "min_size", "profile")),
+    "adaptive_l2": (P.plan_adaptive, ("target_size", "soft_limit", "hard_limit", "keep_ratio_min", "keep_ratio_max")),
+}
+_DEFAULTS: Dict[str, dict] = {}
+
+
+def _method_defaults(method: str) -> dict:
+    if method not in _DEFAULTS:
+        from .methods import COMPRESS_METHODS
+
+        sig = inspect.signature(COMPRESS_METHODS[method])
+        _DEFAULTS[method] = {k: v.default for k, v in sig.parameters.items() if v.default is not inspect.Parameter.empty}
+    return _DEFAULTS[method]
+
+
+def _in_place(plans: Sequence[P.LayerPlan]) -> List[P.LayerPlan]:
+    """A slab's valid rows always start at row 0, so a tail-only result (a view in the reference,
+    e.g. recent_only.py:65-66) becomes a physical move of the last n rows."""
+    out = []
+    for p in plans:
+        if p.kind == P.VIEW:
+            out.append(P.LayerPlan(P.GATHER, p.seq_len, tail=P.suffix_len(p.seq_len, p.view_n)))
+        else:
+            out.append(p)
+    return out
+
+
+class KVSlabCache:
+    """Pre-allocated per-layer K/V slabs with in-place ``update`` (append) and ``compress_``."""
+
+    def __init__(self, num_layers: int, batch: int, heads: int, head_dim: int, capacity: int,
+                 dtype: torch.dtype = torch.bfloat16, device="cuda"):
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise RuntimeError("KVSlabCache lives on a CUDA device (sm_100a): there is no CPU path")
+        if dtype not in _engine.KVC_DTYPE:
+            raise ValueError(f"dtype {dtype} is not supported (float32, float16, bfloat16)")
+        row_bytes = head_dim * torch.empty((), dtype=dtype).element_size()
+        if row_bytes % 16 or row_bytes // 16 not in (8, 10, 16, 20, 32):
+            raise ValueError(f"head_dim*itemsize = {row_bytes} B: the slab kernels cover rows of 128, 160, 256, 320 "
+                             "and 512 bytes")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.num_layers, self.batch, self.heads, self.head_dim = num_layers, batch, heads, head_dim
+        self.capacity, self.dtype, self.device = capacity, dtype, device
+        self.k = torch.empty((num_layers, batch, heads, capacity, head_dim), dtype=dtype, device=device)
+        self.v = torch.empty((num_layers, batch, heads, capacity, head_dim), dtype=dtype, device=device)
+        self.n = torch.zeros((num_layers, batch, heads, capacity), dtype=dtype, device=device)
+        self.lengths: List[int] = [0] * num_layers
+        self._shape = _engine._SHAPE.pack(batch, heads, head_dim, _engine.KVC_DTYPE[dtype], device.index)
+        self._recs = [_SLAB.pack(self.k[l].data_ptr(), self.v[l].data_ptr(), self.n[l].data_ptr(),
+                                 self.k.stride(1), self.k.stride(2), self.v.stride(1), self.v.stride(2),
+                                 self.n.stride(1), self.n.stride(2)) for l in range(num_layers)]
+        self._launch_cache: Dict[int, tuple] = {}
+
+    # ------------------------------------------------------------------ construction / views
+    @classmethod
+    def from_legacy_cache(cls, past_key_values, capacity: Optional[int] = None) -> "KVSlabCache":
+        """Build a slab cache holding a list of ``(K, V)`` pairs (``capacity`` rows per layer, default: twice the
+        longest layer)."""
+        from .utils import normalize_kv_cache
+
+        layers = list(normalize_kv_cache(past_key_values))
+        if not layers:
+            raise ValueError("cannot size a slab cache from an empty cache")
+        k0 = layers[0][0]
+        B, H, _, D = k0.shape
+        longest = max(k.size(2) for k, _ in layers)
+        cache = cls(len(layers), B, H, D, capacity or max(2 * longest, 16), k0.dtype, k0.device)
+        cache.append(layers)
+        return cache
+
+    def __len__(self) -> int:
+        return self.num_layers
+
+    def __getitem__(self, layer_idx: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        n = self.lengths[layer_idx]
+        return self.k[layer_idx, :, :, :n], self.v[layer_idx, :, :, :n]
+
+    def __iter__(self):
+        return (self[l] for l in range(self.num_layers))
+
+    def to_legacy_cache(self) -> List[Tuple[torch.Tensor, torch.Tensor]]:
+        """Views of the valid rows, layer by layer — what ``normalize_kv_cache`` (reference utils.py:30-44) asks for."""
+        return [self[l] for l in range(self.num_layers)]
+
+    def get_seq_length(self, layer_idx: int = 0) -> int:
+        return self.lengths[layer_idx] if self.num_layers else 0
+
+    def key_norms(self, layer_idx: int) -> torch.Tensor:
+        """Stored ``||K||_2`` of the valid rows of one layer, ``[B, H, S]`` in the cache dtype."""
+        return self.n[layer_idx, :, :, :self.lengths[layer_idx]]
+
+    # ------------------------------------------------------------------ append
+    def _check_new(self, keys: torch.Tensor, values: torch.Tensor, layer_idx: int) -> None:
+        if not keys.is_cuda or keys.device != self.device or values.device != self.device:
+            raise RuntimeError(f"layer {layer_idx}: new rows must live on {self.device}")
+        if keys.dtype != self.dtype or values.dtype != self.dtype:
+            raise ValueError(f"layer {layer_idx}: new rows must be {self.dtype}")
+        if keys.dim() != 4 or keys.shape != values.shape or keys.size(0) != self.batch or keys.size(1) != self.heads \
+                or keys.size(3) != self.head_dim:
+            raise ValueError(f"layer {layer_idx}: new rows must be [B={self.batch}, H={self.heads}, T, D={self.head_dim}]")
+        if self.lengths[layer_idx] + keys.size(2) > self.capacity:
+            raise ValueError(f"layer {layer_idx}: {self.lengths[layer_idx]} + {keys.size(2)} rows exceed the slab "
+                             f"capacity {self.capacity}")
+
+    def _append(self, items: Sequence[Tuple[int, torch.Tensor, torch.Tensor]]) -> None:
+        lib = _engine.load_library()
+        slab_buf = bytearray(_SLAB.size * len(items))
+        rows_buf = bytearray(_ROWS.size * len(items))
+        keep = []
+        for m, (l, keys, values) in enumerate(items):
+            self._check_new(keys, values, l)
+            if not _engine._rows_ok(keys):
+                keys = keys.contiguous()
+            if not _engine._rows_ok(values):
+                values = values.contiguous()
+            keep.append((keys, values))
+            ks, vs = keys.stride(), values.stride()
+            slab_buf[m * _SLAB.size:(m + 1) * _SLAB.size] = self._recs[l]
+            _ROWS.pack_into(rows_buf, m * _ROWS.size, keys.data_ptr(), values.data_ptr(), ks[0], ks[1], ks[2],
+                            vs[0], vs[1], vs[2], self.lengths[l], keys.size(2))
+        status = lib.kvc_slab_append(self._shape, len(items), bytes(slab_buf), bytes(rows_buf),
+                                     ctypes.c_void_p(_engine._stream_ptr(self.device)))
+        _engine._check(status, "kvc_slab_append")
+        for l, keys, _ in items:
+            self.lengths[l] += keys.size(2)
+
+    def update(self, key_states: torch.Tensor, value_states: torch.Tensor, layer_idx: int, cache_kwargs=None):
+        """HF ``Cache.update`` contract: append ``[B, H, T, D]`` rows to one layer, return that layer's full
+        ``(K, V)`` (views of the slab) — replaces the ``torch.cat`` of transformers ``cache_utils.py:119-120``."""
+        self._append([(layer_idx, key_states, value_states)])
+        return self[layer_idx]
+
+    def append(self, new_rows) -> "KVSlabCache":
+        """Append one ``(k_new, v_new)`` pair per layer — every layer in ONE launch."""
+        items = [(l, kv[0], kv[1]) for l, kv in enumerate(new_rows) if kv is not None and kv[0].size(2) > 0]
+        if items:
+            self._append(items)
+        return self
+
+    # ------------------------------------------------------------------ in-place compression
+    def plans_for(self, method: str, **kwargs) -> _engine.PlanSet:
+        """The in-place plans of ``COMPRESS_METHODS[method](cache, **kwargs)`` for the current lengths."""
+        from .methods._common import cached_plans
+
+        if method not in _PLANNERS:
+            from .methods import COMPRESS_METHODS
+
+            raise ValueError(f"Unknown method: {method}. Available in place: {list(_PLANNERS)}"
+                             if method not in COMPRESS_METHODS else
+                             f"{method} has no in-place form; call the function on the slab cache instead")
+        planner, names = _PLANNERS[method]
+        args = dict(_method_defaults(method))
+        args.update(kwargs)
+        return cached_plans(planner, self.lengths, *[args[n] for n in names], skip_layers=args.get("skip_layers", ()))
+
+    def compress_(self, method: str, return_indices: bool = False, **kwargs):
+        """``cache = to_dynamic_cache(get_compress_fn(method)(normalize_kv_cache(cache), **kwargs))`` in place:
+        one launch for every layer, no allocation, scores from the stored key norms."""
+        plans = self.plans_for(method, **kwargs)
+        given = None
+        if method == "fix_size_l2" and kwargs.get("strategy") == "random":
+            from .methods.fix_size_l2 import _random_indices
+
+            given = {li: _random_indices(self[li][0], p.sel_hi, p.k_sel)
+                     for li, p in enumerate(plans) if p.kind == P.GATHER and p.score == P.SCORE_GIVEN_INDEX}
+        return self.apply_plans_(plans, given_indices=given, return_indices=return_indices)
+
+    def apply_plans_(self, plans, given_indices: Optional[dict] = None, return_indices: bool = False):
+        ps = plans if isinstance(plans, _engine.PlanSet) else _engine.PlanSet(plans)
+        if len(ps) != self.num_layers:
+            raise ValueError(f"{len(ps)} plans for {self.num_layers} layers")
+        entry = self._launch_cache.get(id(ps))
+        if entry is None or entry[0] is not ps:
+            moved = _in_place(ps.plans)
+            ids = [i for i, p in enumerate(moved) if p.kind == P.GATHER]
+            for i in ids:
+                if moved[i].seq_len != self.lengths[i]:
+                    raise ValueError(f"layer {i}: plan built for {moved[i].seq_len} rows, the slab holds {self.lengths[i]}")
+            plan_buf = b"".join(_engine._PLAN.pack(p.seq_len, p.sink, p.sel_lo, p.sel_hi, p.k_sel, p.tail, p.score,
+                                                   p.pool_kernel) for p in (moved[i] for i in ids))
+            slab_buf = b"".join(self._recs[i] for i in ids)
+            entry = (ps, ids, plan_buf, slab_buf, [moved[i].out_len for i in ids],
+                     [moved[i].seq_len for i in ids])
+            if len(self._launch_cache) > 64:
+                self._launch_cache.clear()
+            self._launch_cache[id(ps)] = entry
+        _, ids, plan_buf, slab_buf, out_lens, in_lens = entry
+        indices = {}
+        if not ids:
+            return (self, indices) if return_indices else self
+        for i, n in zip(ids, in_lens):
+            if self.lengths[i] != n:
+                raise ValueError(f"layer {i}: plan built for {n} rows, the slab holds {self.lengths[i]}")
+        idx_out = idx_in = None
+        keep = []
+        if return_indices:
+            ptrs = (ctypes.c_void_p * len(ids))()
+            for m, (i, c) in enumerate(zip(ids, out_lens)):
+                t = torch.empty((self.batch, self.heads, c), dtype=torch.int32, device=self.device)
+                indices[i] = t
+                ptrs[m] = t.data_ptr()
+            idx_out = ptrs
+        if given_indices:
+            ptrs = (ctypes.c_void_p * len(ids))()
+            for m, i in enumerate(ids):
+                gi = given_indices.get(i)
+                if gi is not None:
+                    if gi.dtype != torch.int32 or not gi.is_contiguous() or gi.device != self.device:
+                        raise ValueError(f"layer {i}: indices must be a contiguous int32 tensor on {self.device}")
+                    keep.append(gi)
+                    ptrs[m] = gi.data_ptr()
+            idx_in = ptrs
+        lib = _engine.load_library()
+        status = lib.kvc_slab_compress(self._shape, len(ids), plan_buf, slab_buf, idx_out, idx_in,
+                                       ctypes.c_void_p(_engine._stream_ptr(self.device)))
+        _engine._check(status, "kvc_slab_compress")
+        for i, c in zip(ids, out_lens):
+            self.lengths[i] = c
+        return (self, indices) if return_indices else self
+
+
+__all__ = ["KVSlabCache"]

@@ -124,6 +124,51 @@ int kvc_key_norms(const kvc_shape* shape, const void* k_in, int64_t stride_b, in
 int kvc_select(int32_t dtype, int32_t device, const void* scores, int64_t n_rows, int32_t n,
                int32_t k, int32_t largest, int32_t* idx_out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Slab cache: the container step on both sides of the compress call.
+ *
+ * The reference's decode loop re-allocates and copies the whole cache twice per step: HF
+ * DynamicLayer.update appends with torch.cat (transformers cache_utils.py:119-120), the compress
+ * function gathers into fresh tensors, and to_dynamic_cache (reference utils.py:12-27) rebuilds
+ * the container.  Here one layer's K and V live in pre-allocated [B, H, capacity, D] slabs with
+ * dense rows, next to a [B, H, capacity] array of key norms in the cache dtype (exactly what
+ * torch.norm(K, p=2, dim=-1) returns for those rows: fp32 sum of squares, one rounding).
+ *
+ *   kvc_slab_append    copies n_new rows per (b,h) to rows [cur_len, cur_len + n_new) of the slabs
+ *                      and records their key norms — replaces the torch.cat of cache.update.
+ *   kvc_slab_compress  applies a keep-plan IN PLACE: scores come from the stored norms (K is not
+ *                      re-read), kept rows slide down to rows [0, C) of the same slabs (rows whose
+ *                      position does not change are not touched), norms slide with them.  Same kept
+ *                      set and same bytes as kvc_compress_layers on the same cache.
+ */
+typedef struct kvc_slab_layer {
+    void* k;      /* [B,H,capacity,D] keys,   rows dense */
+    void* v;      /* [B,H,capacity,D] values, rows dense */
+    void* norms;  /* [B,H,capacity] key norms, cache dtype */
+    int64_t k_stride_b, k_stride_h; /* elements */
+    int64_t v_stride_b, v_stride_h; /* elements */
+    int64_t n_stride_b, n_stride_h; /* elements */
+} kvc_slab_layer;
+
+typedef struct kvc_slab_new_rows {
+    const void* k_new; /* [B,H,n_new,D] rows to append, last dim dense */
+    const void* v_new;
+    int64_t k_stride_b, k_stride_h, k_stride_s; /* elements */
+    int64_t v_stride_b, v_stride_h, v_stride_s; /* elements */
+    int32_t cur_len;   /* rows already valid in this layer's slab */
+    int32_t n_new;     /* rows to append */
+} kvc_slab_new_rows;
+
+/* Append rows to n_layers slabs in one launch.  head_dim * sizeof(dtype) / 16 must be one of 8, 10, 16, 20, 32. */
+int kvc_slab_append(const kvc_shape* shape, int32_t n_layers, const kvc_slab_layer* slabs,
+                    const kvc_slab_new_rows* rows, void* stream);
+
+/* Compact n_layers slabs in place in one launch.  plans[l].seq_len = rows currently valid.
+ * idx_out[l] (optional, may be NULL / hold NULLs): [B,H,C] kept absolute rows; idx_in[l]: GIVEN_INDEX rows. */
+int kvc_slab_compress(const kvc_shape* shape, int32_t n_layers, const kvc_layer_plan* plans,
+                      const kvc_slab_layer* slabs, int32_t* const* idx_out, const int32_t* const* idx_in,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

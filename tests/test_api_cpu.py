@@ -132,3 +132,26 @@ def test_h2o_manager_bookkeeping():
     idx = m.get_heavy_hitter_indices(0, 9)   # middle = rows [1, 7): relative positions of rows 3 and 5
     assert idx.tolist() == [2, 4]
     assert m.get_heavy_hitter_indices(7, 30).tolist() == list(range(0, 27, 13))[:2]
+
+
+def test_slab_cache_planner_table_matches_function_signatures():
+    """Every in-place method resolves its planner arguments from the drop-in function's own defaults."""
+    import inspect
+
+    from kvcompress import _planner as P
+    from kvcompress import slab_cache
+
+    for name, (planner, names) in slab_cache._PLANNERS.items():
+        defaults = slab_cache._method_defaults(name)
+        assert set(names) <= set(defaults), (name, names, defaults)
+        assert "skip_layers" in defaults
+        params = list(inspect.signature(planner).parameters)
+        want = params[1:params.index("skip_layers")]
+        assert len(want) == len(names), (name, want, names)
+    plans = [P.LayerPlan(P.KEEP, 10), P.LayerPlan(P.VIEW, 10, view_n=4), P.LayerPlan(P.VIEW, 10, view_n=0)]
+    moved = slab_cache._in_place(plans)
+    assert moved[0].kind == P.KEEP
+    assert (moved[1].kind, moved[1].tail, moved[1].out_len) == (P.GATHER, 4, 4)
+    assert (moved[2].kind, moved[2].tail) == (P.GATHER, 10)  # x[:, :, -0:] is the whole tensor
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        slab_cache.KVSlabCache(1, 1, 1, 80, 16, device="cpu")

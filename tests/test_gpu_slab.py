@@ -1,0 +1,146 @@
+"""-m gpu: KVSlabCache (in-place append + in-place compression) against the
+out-of-place functions walked through the same decode loop — the reference's loop shape
+(evaluate.py:132-166): append one token per layer, compress, repeat."""
+
+import pytest
+import torch
+
+import kvcompress
+from kvcompress import KVSlabCache, _engine
+from kvcompress import _planner as P
+from test_planner import plan_for
+
+pytestmark = pytest.mark.gpu
+
+DT = {"bf16": torch.bfloat16, "f16": torch.float16, "f32": torch.float32}
+
+
+def rand_rows(B, H, T, D, dtype, gen, spread=True):
+    k = torch.randn(B, H, T, D, generator=gen, device="cuda")
+    if spread:
+        k = k * torch.exp(0.35 * torch.randn(B, H, T, 1, generator=gen, device="cuda"))
+    v = torch.randn(B, H, T, D, generator=gen, device="cuda")
+    return k.to(dtype), v.to(dtype)
+
+
+LOOPS = [
+    ("streaming_llm", dict(start_size=4, recent_size=60), "bf16", 80),
+    ("streaming_llm", dict(start_size=0, recent_size=33, skip_layers=[1]), "f32", 128),
+    ("h2o_l2", dict(start_size=4, heavy_hitter_size=16, recent_size=44), "bf16", 80),
+    ("h2o_l2", dict(start_size=4, heavy_hitter_size=16, recent_size=44), "f32", 80),
+    ("fix_size_l2", dict(fix_kv_size=64, keep_ratio=0.2, skip_layers=[0]), "bf16", 128),
+    ("fix_size_l2", dict(fix_kv_size=64, keep_ratio=0.5, strategy="keep_high", skip_layers=[]), "f16", 64),
+    ("fix_size_l2", dict(fix_kv_size=64, keep_ratio=0.25, strategy="random", skip_layers=[]), "bf16", 80),
+    ("fix_size_l2", dict(fix_kv_size=64, keep_ratio=1.0, skip_layers=[]), "bf16", 80),   # tail-only (a view in the reference)
+    ("snapkv_lite", dict(observation_window=8, keep_size=64, pooling_kernel=5), "bf16", 128),
+    ("snapkv_lite", dict(observation_window=8, keep_size=64, pooling_kernel=4), "f32", 80),
+    ("pyramid_kv", dict(base_size=64, layer_decay=0.8, min_size=16), "bf16", 80),
+    ("adaptive_l2", dict(target_size=64, soft_limit=32, hard_limit=100), "bf16", 128),
+    ("l2_compress", dict(keep_ratio=0.9, prune_after=60, skip_layers=[0]), "f32", 80),
+    ("recent_only", dict(window_size=50, skip_layers=[0]), "bf16", 80),
+]
+
+
+@pytest.mark.parametrize("method,kwargs,dtype,D", LOOPS, ids=[f"{m}-{i}" for i, (m, *_r) in enumerate(LOOPS)])
+def test_decode_loop_matches_out_of_place(method, kwargs, dtype, D):
+    """Same lengths and bit-identical K/V after every step of prefill -> (append 1 token, compress) x N."""
+    L, B, H, S0, steps = 3, 2, 3, 150, 24
+    dt = DT[dtype]
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    fn = kvcompress.get_compress_fn(method)
+    prefill = [rand_rows(B, H, S0, D, dt, gen) for _ in range(L)]
+    slab = KVSlabCache.from_legacy_cache(prefill, capacity=256)
+    kv = [(k.clone(), v.clone()) for k, v in prefill]
+    for (k, v), (ks, vs) in zip(kv, slab):
+        assert torch.equal(k, ks) and torch.equal(v, vs)
+    for step in range(steps):
+        torch.manual_seed(1000 + step)
+        kv = fn(kv, **kwargs)
+        torch.manual_seed(1000 + step)
+        n0 = _engine.launch_count()
+        slab.compress_(method, **kwargs)
+        assert _engine.launch_count() - n0 <= 1, "in-place compression of all layers is ONE launch"
+        assert [k.size(2) for k, _ in kv] == slab.lengths, (step, slab.lengths)
+        for li, ((k, v), (ks, vs)) in enumerate(zip(kv, slab)):
+            assert torch.equal(k, ks), (method, step, li)
+            assert torch.equal(v, vs), (method, step, li)
+        new = [rand_rows(B, H, 1, D, dt, gen) for _ in range(L)]
+        kv = [(torch.cat([k, nk], 2), torch.cat([v, nv], 2)) for (k, v), (nk, nv) in zip(kv, new)]
+        if step % 2:
+            slab.append(new)                       # all layers, one launch
+        else:
+            for li, (nk, nv) in enumerate(new):    # HF-style per-layer update
+                full_k, full_v = slab.update(nk, nv, li)
+                assert full_k.size(2) == kv[li][0].size(2)
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "f16", "f32"])
+@pytest.mark.parametrize("D", [64, 80, 128])
+def test_append_copies_rows_and_records_torch_norms(dtype, D):
+    dt = DT[dtype]
+    if D * torch.empty((), dtype=dt).element_size() // 16 not in (8, 10, 16, 20, 32):
+        pytest.skip("row width not covered by the slab kernels")
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    L, B, H = 2, 2, 4
+    slab = KVSlabCache(L, B, H, D, 300, dt)
+    ref = [[], []]
+    for T in (130, 1, 7, 1):
+        new = [rand_rows(B, H, T, D, dt, gen) for _ in range(L)]
+        # strided new rows ([B,T,H,D] storage, as attention layers produce them)
+        new = [(k.permute(0, 2, 1, 3).contiguous().permute(0, 2, 1, 3), v) for k, v in new]
+        slab.append(new)
+        for li in range(L):
+            ref[li].append(new[li])
+    for li in range(L):
+        k = torch.cat([x[0] for x in ref[li]], 2)
+        v = torch.cat([x[1] for x in ref[li]], 2)
+        assert slab.lengths[li] == 139
+        assert torch.equal(slab[li][0], k) and torch.equal(slab[li][1], v)
+        want = torch.linalg.vector_norm(k.float(), dim=-1)
+        got = slab.key_norms(li).float()
+        tol = 1e-6 if dtype == "f32" else (2 ** -8 if dtype == "bf16" else 2 ** -11)
+        assert torch.all((got - want).abs() <= tol * want + 1e-30)
+        if dtype != "f32":  # == torch.norm's rounding except where the fp32 sum order flips the last rounding
+            assert (got == want.to(dt).float()).float().mean() > 0.995
+
+
+def test_in_place_indices_match_out_of_place_and_functions_accept_slabs():
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    L, B, H, S, D = 4, 2, 8, 2000, 128
+    kv = [rand_rows(B, H, S, D, torch.bfloat16, gen) for _ in range(L)]
+    for method, kwargs in (("h2o_l2", dict(start_size=4, heavy_hitter_size=64, recent_size=444)),
+                           ("snapkv_lite", dict(observation_window=32, keep_size=512)),
+                           ("pyramid_kv", dict(base_size=512)),
+                           ("adaptive_l2", dict(target_size=512))):
+        slab = KVSlabCache.from_legacy_cache(kv, capacity=2048)
+        # a registered function applied to the slab (through to_legacy_cache views)
+        out = kvcompress.get_compress_fn(method)(slab, **kwargs)
+        plans = plan_for(method, [S] * L, kwargs)
+        out2, idx = _engine.run_plans(kv, plans, return_indices=True)
+        _, idx_ip = slab.compress_(method, return_indices=True, **kwargs)
+        for li in range(L):
+            assert torch.equal(out[li][0], out2[li][0]) and torch.equal(out[li][1], out2[li][1])
+            assert torch.equal(slab[li][0], out2[li][0]) and torch.equal(slab[li][1], out2[li][1])
+            if plans[li].kind == P.GATHER:
+                assert torch.equal(idx_ip[li], idx[li])
+                # norms slid with their rows
+                want = torch.gather(torch.linalg.vector_norm(kv[li][0].float(), dim=-1).to(torch.bfloat16), 2,
+                                    idx[li].long())
+                assert (slab.key_norms(li) == want).float().mean() > 0.995
+
+
+def test_slab_errors():
+    slab = KVSlabCache(1, 1, 2, 80, 32, torch.bfloat16)
+    k = torch.zeros(1, 2, 40, 80, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(ValueError, match="exceed the slab capacity"):
+        slab.update(k, k, 0)
+    with pytest.raises(ValueError, match="must be torch.bfloat16"):
+        slab.update(k[:, :, :4].float(), k[:, :, :4].float(), 0)
+    with pytest.raises(RuntimeError, match="must live on"):
+        slab.update(k[:, :, :4].cpu(), k[:, :, :4].cpu(), 0)
+    with pytest.raises(ValueError, match="Unknown method"):
+        slab.compress_("nope")
+    with pytest.raises(ValueError, match="cover rows of"):
+        KVSlabCache(1, 1, 2, 24, 32, torch.bfloat16)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        KVSlabCache(1, 1, 2, 80, 32, torch.bfloat16, device="cpu")
