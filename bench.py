@@ -71,6 +71,9 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="override the per-rank batch")
     ap.add_argument("--seq-len", type=int, default=0, help="override the context length (diagnostics)")
+    ap.add_argument("--mode", default="functions", choices=["functions", "slab"],
+                    help="functions: the drop-in compress functions (default, the BASELINE metric); slab: the same calls "
+                         "in place on a KVSlabCache (append + compress_), SURVEY 8f rank 1")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-slab", type=int, default=8, help="streams per host<->device slab in the e2e leg")
@@ -562,10 +565,102 @@ def run_e2e(cfg, B, kv, fns, step_bytes, args, device, world, barrier):
     return best
 
 
+def run_slab(args):
+    """The same calls IN PLACE on a KVSlabCache: per decode step `compress_` (one launch, scores from the stored
+    key norms, rows slide down inside the slab) and, at steady state (S = cap + 1), `append` of the next token
+    (one launch for all layers).  Reported against the SAME algorithmic bytes as the out-of-place functions
+    ("In-place mode is reported against the same figure"), so GB/s above the HBM peak means bytes
+    that no longer move."""
+    import torch
+
+    import kvcompress
+    from kvcompress import KVSlabCache, _engine
+
+    if int(os.environ.get("WORLD_SIZE", "1")) != 1:
+        raise SystemExit("--mode slab is a single-GPU measurement")
+    torch.cuda.set_device(0)
+    device = torch.device("cuda", 0)
+    cfg = dict(CONFIGS[args.config])
+    if args.seq_len:
+        cfg["S"] = args.seq_len
+    B = args.batch or cfg["B"]
+    S = cfg["S"]
+    per_call_bytes = call_bytes(cfg, B)
+    kv = make_cache(cfg, B, device, seed=1234)
+    dt = kv[0][0].dtype
+    slabs, news, steady = [], [], []
+    for method, kw in cfg["calls"]:
+        slab = KVSlabCache.from_legacy_cache(kv, capacity=S + 8)
+        plans = slab.plans_for(method, **kw)
+        steady.append(all(p.kind == "keep" or p.out_len == S - 1 for p in plans))
+        slabs.append(slab)
+        # the next decode token, for the layers the call compresses (skipped layers are left at S rows)
+        news.append([(torch.randn(B, cfg["H"], 1, cfg["D"], device=device).to(dt),
+                      torch.randn(B, cfg["H"], 1, cfg["D"], device=device).to(dt)) if p.kind != "keep" else None
+                     for p in plans])
+    del kv
+    torch.cuda.synchronize()
+
+    def one_step(events=None):
+        for i, ((method, kw), slab) in enumerate(zip(cfg["calls"], slabs)):
+            if events is not None:
+                events[i][0].record()
+            slab.compress_(method, **kw)
+            if events is not None:
+                events[i][1].record()
+            if steady[i]:
+                slab.append(news[i])        # the next decode token: back to S rows
+            else:
+                slab.lengths = [S] * cfg["L"]  # prefill-sized compress: rewind (rows stay valid data)
+            if events is not None:
+                events[i][2].record()
+
+    for _ in range(max(args.warmup, 3)):
+        one_step()
+    torch.cuda.synchronize()
+    K = args.steps
+    ev = [[tuple(torch.cuda.Event(enable_timing=True) for _ in range(3)) for _ in cfg["calls"]] for _ in range(K)]
+    sampler = ClockSampler(0)
+    sampler.start()
+    launches0 = _engine.launch_count()
+    t0 = time.perf_counter()
+    for s in range(K):
+        one_step(ev[s])
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3 / K
+    launches = _engine.launch_count() - launches0
+    clocks = sampler.stop()
+    peak, peak_src = measured_peak()
+    per_call = {}
+    total_ms = 0.0
+    for i, (method, _) in enumerate(cfg["calls"]):
+        comp = [x[i][0].elapsed_time(x[i][1]) for x in ev]
+        app = [x[i][1].elapsed_time(x[i][2]) for x in ev]
+        c_ms, a_ms = statistics.mean(comp), statistics.mean(app)
+        total_ms += c_ms + (a_ms if steady[i] else 0.0)
+        per_call[method] = {"compress_us_mean": round(c_ms * 1e3, 1), "compress_us_min": round(min(comp) * 1e3, 1),
+                            "append_us_mean": round(a_ms * 1e3, 1) if steady[i] else None,
+                            "algorithmic_bytes": per_call_bytes[i],
+                            "effective_gbs": round(per_call_bytes[i] / (c_ms * 1e-3) / 1e9, 1),
+                            "steady_state": steady[i]}
+    line = {
+        "metric": "kv_compress_step_throughput", "mode": "slab_in_place", "value": round(sum(per_call_bytes) / (total_ms * 1e-3) / 1e9, 1),
+        "unit": "GB/s (same algorithmic bytes as the out-of-place functions)", "n_gpus": 1, "steps": K,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(total_ms, 4), "wall_ms_per_step": round(wall_ms, 4),
+        "higher_is_better": True, "dtype": cfg["dtype"], "data": "synthetic",
+        "config": workload_config(cfg, args.config, B, 1), "tok_per_s": round(B / (total_ms * 1e-3), 1),
+        "per_call": per_call, "gpu_launches": launches, "clocks": clocks,
+        "peak": peak, "peak_source": peak_src,
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.mode == "slab":
+        run_slab(args)
     else:
         run_ours(args)
 

@@ -346,7 +346,7 @@ static int env_int(const char* name, int dflt) {
 // Choose threads per CTA, resident CTAs per SM and staging warps so that (a) the on-chip key
 // buffer fits, (b) as close to 128 KB of rows as possible are in flight per SM, (c) as many CTAs as possible are
 // resident so one unit's select phase hides under its neighbours' HBM phases.
-static TmaPlan plan_tma(int dtype, int cpr, int max_region, int idx_cap, bool any_select) {
+static TmaPlan plan_tma(int dtype, int cpr, int max_region, int idx_cap, bool any_select, bool light_traffic = false) {
     TmaPlan best;
     const int stage = 32 * cpr * 16;
     int end = kTmaHead;
@@ -376,7 +376,9 @@ static TmaPlan plan_tma(int dtype, int cpr, int max_region, int idx_cap, bool an
         if (force_nsw && force_nsw < nsw) nsw = force_nsw;
         const long inflight = (long)ctas * nsw * stage;
         // saturating score: bytes in flight up to 128 KB matter most (measured: c5 +8% from 64 -> 128 KB), then residency
-        const long score = (inflight < 131072 ? inflight : 131072) * 8 + ctas * 4096 + (inflight >> 6);
+        long score = (inflight < 131072 ? inflight : 131072) * 8 + ctas * 4096 + (inflight >> 6);
+        // in-place compaction moves few bytes (scores come from stored norms): residency first, 2+ slots are enough
+        if (light_traffic) score = (nsw >= 2 ? 1 : 0) * (1L << 30) + ctas * (1L << 20) + nsw;
         if (score > best_score) {
             best_score = score;
             best = base;
@@ -869,7 +871,7 @@ int kvc_slab_compress(const kvc_shape* shape, int32_t n_layers, const kvc_layer_
         }
         if (n_active == 0) continue;
         bd.idx_cap = (max_ksel + 3) & ~3;
-        const TmaPlan tp = plan_tma(dt, cpr, max_region, bd.idx_cap, any_select);
+        const TmaPlan tp = plan_tma(dt, cpr, max_region, bd.idx_cap, any_select, /*light_traffic=*/true);
         if (!tp.ok) return KVC_ERR_TOO_LARGE;
         SlabFn fn = pick_slab(dt, cpr, tp.nt);
         bd.nsw = tp.nsw;

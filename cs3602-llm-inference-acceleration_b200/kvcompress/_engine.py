@@ -23,7 +23,7 @@ from . import _planner as P
 
 _LIB_NAME = "libkvc_sm100a.so"
 _CSRC_DIR = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "csrc"))
-_LIB_PATH = os.path.join(_CSRC_DIR, _LIB_NAME)
+_LIB_PATH = os.environ.get("KVC_LIBRARY") or os.path.join(_CSRC_DIR, _LIB_NAME)  # KVC_LIBRARY: A/B builds of the kernels
 
 # struct layouts of include/kvc.h
 _PLAN = struct.Struct("8i")        # kvc_layer_plan: seq_len sink sel_lo sel_hi k_sel tail score pool_kernel

@@ -97,6 +97,7 @@ class KVSlabCache:
         self._recs = [_SLAB.pack(self.k[l].data_ptr(), self.v[l].data_ptr(), self.n[l].data_ptr(),
                                  self.k.stride(1), self.k.stride(2), self.v.stride(1), self.v.stride(2),
                                  self.n.stride(1), self.n.stride(2)) for l in range(num_layers)]
+        self._all_recs = b"".join(self._recs)
         self._launch_cache: Dict[int, tuple] = {}
 
     # ------------------------------------------------------------------ construction / views
@@ -136,6 +137,48 @@ class KVSlabCache:
     def key_norms(self, layer_idx: int) -> torch.Tensor:
         """Stored ``||K||_2`` of the valid rows of one layer, ``[B, H, S]`` in the cache dtype."""
         return self.n[layer_idx, :, :, :self.lengths[layer_idx]]
+
+    def as_hf_cache(self):
+        """This slab as a ``transformers.Cache``: the model's attention layers call ``update`` (in-place append)
+        and read lengths / mask sizes from the slab, so it can be passed as ``past_key_values``."""
+        from transformers.cache_utils import Cache, CacheLayerMixin
+
+        slab = self
+
+        class _SlabLayer(CacheLayerMixin):
+            is_sliding = False
+            is_compileable = False
+
+            def __init__(self, layer_idx: int):
+                self.layer_idx = layer_idx
+                self.is_initialized = True
+                self.dtype, self.device = slab.dtype, slab.device
+
+            keys = property(lambda self: slab[self.layer_idx][0], lambda self, value: None)
+            values = property(lambda self: slab[self.layer_idx][1], lambda self, value: None)
+
+            def lazy_initialization(self, key_states, value_states) -> None:
+                return None
+
+            def update(self, key_states, value_states, *args, **kwargs):
+                return slab.update(key_states, value_states, self.layer_idx)
+
+            def get_mask_sizes(self, query_length) -> Tuple[int, int]:
+                q = query_length if isinstance(query_length, int) else int(query_length.shape[0])
+                return slab.lengths[self.layer_idx] + q, 0
+
+            def get_seq_length(self) -> int:
+                return slab.lengths[self.layer_idx]
+
+            def get_max_cache_shape(self) -> int:
+                return -1
+
+            def reset(self) -> None:
+                slab.lengths[self.layer_idx] = 0
+
+        cache = Cache(layers=[_SlabLayer(l) for l in range(self.num_layers)])
+        cache.slab = self
+        return cache
 
     # ------------------------------------------------------------------ append
     def _check_new(self, keys: torch.Tensor, values: torch.Tensor, layer_idx: int) -> None:
@@ -183,6 +226,29 @@ class KVSlabCache:
         items = [(l, kv[0], kv[1]) for l, kv in enumerate(new_rows) if kv is not None and kv[0].size(2) > 0]
         if items:
             self._append(items)
+        return self
+
+    def append_stacked(self, k_new: torch.Tensor, v_new: torch.Tensor) -> "KVSlabCache":
+        """Append ``[L, B, H, T, D]`` rows (one tensor for all layers, e.g. a model's fused KV projection output)
+        in ONE launch; the per-layer host work is pointer arithmetic only."""
+        if k_new.dim() != 5 or k_new.shape != v_new.shape or k_new.size(0) != self.num_layers:
+            raise ValueError(f"stacked rows must be [L={self.num_layers}, B, H, T, D]")
+        self._check_new(k_new[0], v_new[0], 0)
+        T = k_new.size(3)
+        if max(self.lengths) + T > self.capacity:
+            raise ValueError(f"{max(self.lengths)} + {T} rows exceed the slab capacity {self.capacity}")
+        if not (_engine._rows_ok(k_new[0]) and _engine._rows_ok(v_new[0])):
+            k_new, v_new = k_new.contiguous(), v_new.contiguous()
+        ks, vs, esz = k_new.stride(), v_new.stride(), k_new.element_size()
+        kp, vp = k_new.data_ptr(), v_new.data_ptr()
+        rows_buf = bytearray(_ROWS.size * self.num_layers)
+        for l in range(self.num_layers):
+            _ROWS.pack_into(rows_buf, l * _ROWS.size, kp + l * ks[0] * esz, vp + l * vs[0] * esz, ks[1], ks[2], ks[3],
+                            vs[1], vs[2], vs[3], self.lengths[l], T)
+        status = _engine.load_library().kvc_slab_append(self._shape, self.num_layers, self._all_recs, bytes(rows_buf),
+                                                        ctypes.c_void_p(_engine._stream_ptr(self.device)))
+        _engine._check(status, "kvc_slab_append")
+        self.lengths = [n + T for n in self.lengths]
         return self
 
     # ------------------------------------------------------------------ in-place compression

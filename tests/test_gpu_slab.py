@@ -66,8 +66,10 @@ def test_decode_loop_matches_out_of_place(method, kwargs, dtype, D):
             assert torch.equal(v, vs), (method, step, li)
         new = [rand_rows(B, H, 1, D, dt, gen) for _ in range(L)]
         kv = [(torch.cat([k, nk], 2), torch.cat([v, nv], 2)) for (k, v), (nk, nv) in zip(kv, new)]
-        if step % 2:
+        if step % 3 == 1:
             slab.append(new)                       # all layers, one launch
+        elif step % 3 == 2 and len(set(slab.lengths)) == 1:
+            slab.append_stacked(torch.stack([k for k, _ in new]), torch.stack([v for _, v in new]))
         else:
             for li, (nk, nv) in enumerate(new):    # HF-style per-layer update
                 full_k, full_v = slab.update(nk, nv, li)
