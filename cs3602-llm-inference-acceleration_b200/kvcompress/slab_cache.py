@@ -98,6 +98,9 @@ class KVSlabCache:
                                  self.k.stride(1), self.k.stride(2), self.v.stride(1), self.v.stride(2),
                                  self.n.stride(1), self.n.stride(2)) for l in range(num_layers)]
         self._all_recs = b"".join(self._recs)
+        self._k_layers = list(self.k.unbind(0))
+        self._v_layers = list(self.v.unbind(0))
+        self._lib = None
         self._launch_cache: Dict[int, tuple] = {}
 
     # ------------------------------------------------------------------ construction / views
@@ -122,7 +125,7 @@ class KVSlabCache:
 
     def __getitem__(self, layer_idx: int) -> Tuple[torch.Tensor, torch.Tensor]:
         n = self.lengths[layer_idx]
-        return self.k[layer_idx, :, :, :n], self.v[layer_idx, :, :, :n]
+        return self._k_layers[layer_idx].narrow(2, 0, n), self._v_layers[layer_idx].narrow(2, 0, n)
 
     def __iter__(self):
         return (self[l] for l in range(self.num_layers))
@@ -218,8 +221,31 @@ class KVSlabCache:
     def update(self, key_states: torch.Tensor, value_states: torch.Tensor, layer_idx: int, cache_kwargs=None):
         """HF ``Cache.update`` contract: append ``[B, H, T, D]`` rows to one layer, return that layer's full
         ``(K, V)`` (views of the slab) — replaces the ``torch.cat`` of transformers ``cache_utils.py:119-120``."""
-        self._append([(layer_idx, key_states, value_states)])
-        return self[layer_idx]
+        # hot path of the decode loop (called once per layer per token): checks and packing inlined
+        if not (key_states.is_cuda and key_states.dtype is self.dtype and value_states.dtype is self.dtype
+                and key_states.device == self.device and value_states.device == self.device):
+            self._check_new(key_states, value_states, layer_idx)
+        shape = key_states.shape
+        n, T = self.lengths[layer_idx], shape[2]
+        if len(shape) != 4 or value_states.shape != shape or shape[0] != self.batch or shape[1] != self.heads \
+                or shape[3] != self.head_dim or n + T > self.capacity:
+            self._check_new(key_states, value_states, layer_idx)
+        if T == 0:
+            return self[layer_idx]
+        if not _engine._rows_ok(key_states):
+            key_states = key_states.contiguous()
+        if not _engine._rows_ok(value_states):
+            value_states = value_states.contiguous()
+        ks, vs = key_states.stride(), value_states.stride()
+        rows = _ROWS.pack(key_states.data_ptr(), value_states.data_ptr(), ks[0], ks[1], ks[2], vs[0], vs[1], vs[2], n, T)
+        if self._lib is None:
+            self._lib = _engine.load_library()
+        status = self._lib.kvc_slab_append(self._shape, 1, self._recs[layer_idx], rows,
+                                           ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+        if status:
+            _engine._check(status, "kvc_slab_append")
+        self.lengths[layer_idx] = n + T
+        return self._k_layers[layer_idx].narrow(2, 0, n + T), self._v_layers[layer_idx].narrow(2, 0, n + T)
 
     def append(self, new_rows) -> "KVSlabCache":
         """Append one ``(k_new, v_new)`` pair per layer — every layer in ONE launch."""
