@@ -333,7 +333,7 @@ __device__ __forceinline__ void block_radix_select(const Key* __restrict__ keys,
 // windows are read before a single __syncthreads().  All NT threads must call; ends synchronised.
 template <int DT, int NT>
 __device__ __forceinline__ void snapkv_transform(typename Traits<DT>::Key* keys, int R, int pk, uint32_t* hist,
-                                                 int32_t* misc) {
+                                                 int32_t* misc, bool invert = true) {
     using Tr = Traits<DT>;
     using Key = typename Tr::Key;
     constexpr int kShift0 = Tr::kKeyBits - kHistBits;
@@ -366,7 +366,8 @@ __device__ __forceinline__ void snapkv_transform(typename Traits<DT>::Key* keys,
             const uint32_t vn = __shfl_sync(0xffffffffu, next, sl & 31);
             const uint32_t rj = sl < 0 ? vp : (sl >= 32 ? vn : vc);
             const int j = i + d;
-            if (j >= 0 && j < R) acc += round_dt<DT>(mxe - Tr::from_raw(rj));
+            // invert: snapkv-lite's (max + 1e-6 - norm); otherwise the rows carry caller-supplied scores
+            if (j >= 0 && j < R) acc += invert ? round_dt<DT>(mxe - Tr::from_raw(rj)) : Tr::from_raw(rj);
         }
         if (i < R) {
             const float outv = pooling ? round_dt<DT>(acc / den) : acc;

@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(NT, MINB) kvc_fused_tma_kernel(const __grid_co
     const int ksel = L.ksel;
     const int score = L.score;
     const bool kdense = L.kss == RB, vdense = L.vss == RB;
-    const bool scan = ksel > 0 && score != KVC_SCORE_GIVEN_INDEX;
+    const bool scan = ksel > 0 && score != KVC_SCORE_GIVEN_INDEX && score != KVC_SCORE_GIVEN_SCORE;
 
     if (stager) {
         if (lane == 0) {
@@ -124,6 +124,14 @@ __global__ void __launch_bounds__(NT, MINB) kvc_fused_tma_kernel(const __grid_co
     if (ksel > 0 && score == KVC_SCORE_GIVEN_INDEX) {
         const int32_t* src = L.idx_in + (int64_t)bh * ksel;
         for (int i = tid; i < ksel; i += NT) sidx[i] = src[i];
+    } else if (ksel > 0 && score == KVC_SCORE_GIVEN_SCORE) {
+        // ---------------------------------------------------------- caller-supplied scores: pool -> keep the highest
+        for (int i = tid; i < kHistBins; i += NT) hist[i] = 0;
+        const Key* src = reinterpret_cast<const Key*>(L.idx_in) + (int64_t)bh * R;
+        for (int i = tid; i < R; i += NT) keys[i] = src[i];
+        __syncthreads();
+        snapkv_transform<DT, NT>(keys, R, L.pool, hist, misc, /*invert=*/false);
+        block_radix_select<Key, NT>(keys, R, ksel, hist, misc, sidx, L.lo);
     } else if (ksel > 0) {
         // ---------------------------------------------------------- K1: scan
         for (int i = tid; i < kHistBins; i += NT) hist[i] = 0;

@@ -11,6 +11,7 @@
 // Algorithmic HBM bytes per unit: e*D*(R + 4*C)  (SURVEY.md §8d).
 #include <atomic>
 #include <cstdio>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
@@ -20,6 +21,7 @@
 #include "kvc_device.cuh"
 #include "kvc_fused_tma.cuh"
 #include "kvc_slab.cuh"
+#include "kvc_vote.cuh"
 
 #define KVC_STR2(x) #x
 #define KVC_STR(x) KVC_STR2(x)
@@ -553,8 +555,10 @@ int kvc_compress_layers(const kvc_shape* shape, int32_t n_layers, const kvc_laye
             if (p.sel_lo < 0 || p.sel_hi > p.seq_len || p.sel_lo > p.sel_hi) return KVC_ERR_INVALID_ARG;
             if (p.k_sel > p.sel_hi - p.sel_lo) return KVC_ERR_INVALID_ARG;
             if (p.score == KVC_SCORE_NONE) return KVC_ERR_INVALID_ARG;
-            if (p.score < KVC_SCORE_NONE || p.score > KVC_SCORE_GIVEN_INDEX) return KVC_ERR_INVALID_ARG;
+            if (p.score < KVC_SCORE_NONE || p.score > KVC_SCORE_GIVEN_SCORE) return KVC_ERR_INVALID_ARG;
             if (p.score == KVC_SCORE_GIVEN_INDEX && !x.idx_in) return KVC_ERR_INVALID_ARG;
+            if (p.score == KVC_SCORE_GIVEN_SCORE && (!x.score_in || !tma_supported_cpr(cpr))) return KVC_ERR_INVALID_ARG;
+            if (p.score == KVC_SCORE_GIVEN_SCORE && p.pool_kernel > 2 * kMaxPoolHalo) return KVC_ERR_UNSUPPORTED;
             if (p.score == KVC_SCORE_SNAPKV_POOL && p.pool_kernel > 2 * kMaxPoolHalo) return KVC_ERR_UNSUPPORTED;
         }
         if (C == 0) continue;
@@ -590,7 +594,7 @@ int kvc_compress_layers(const kvc_shape* shape, int32_t n_layers, const kvc_laye
             d.k_out = (char*)x.k_out;
             d.v_out = (char*)x.v_out;
             d.idx_out = x.idx_out;
-            d.idx_in = x.idx_in;
+            d.idx_in = p.score == KVC_SCORE_GIVEN_SCORE ? (const int32_t*)x.score_in : x.idx_in;
             d.ksb = x.k_stride_b * e;
             d.ksh = x.k_stride_h * e;
             d.kss = x.k_stride_s * e;
@@ -616,7 +620,11 @@ int kvc_compress_layers(const kvc_shape* shape, int32_t n_layers, const kvc_laye
         bd.idx_cap = (max_ksel + 3) & ~3;
         dim3 grid((unsigned)((int64_t)B * H), (unsigned)n_active, 1);
         TmaPlan tp;
-        if (tma_supported_cpr(cpr) && !env_int("KVC_FORCE_LDG", 0)) tp = plan_tma(dt, cpr, max_region, bd.idx_cap, any_select);
+        bool given_score = false;
+        for (int l = 0; l < nl; ++l) given_score |= plans[l0 + l].k_sel > 0 && plans[l0 + l].score == KVC_SCORE_GIVEN_SCORE;
+        if (tma_supported_cpr(cpr) && (given_score || !env_int("KVC_FORCE_LDG", 0)))
+            tp = plan_tma(dt, cpr, max_region, bd.idx_cap, any_select);
+        if (given_score && !tp.ok) return KVC_ERR_TOO_LARGE;
         if (tp.ok) {
             // bulk-copy form: rows are staged through shared memory by the TMA unit
             FusedFn fn = pick_tma(dt, cpr, tp.nt);
@@ -885,6 +893,69 @@ int kvc_slab_compress(const kvc_shape* shape, int32_t n_layers, const kvc_layer_
         fn<<<grid, tp.nt, tp.smem, (cudaStream_t)stream>>>(bd);
         cudaError_t err = cudaGetLastError();
         if (err != cudaSuccess) return cuda_fail(err, "kvc_slab_compress_kernel launch");
+        g_launches.fetch_add(1);
+    }
+    return KVC_OK;
+}
+
+int kvc_snapkv_vote(const kvc_shape* shape, int32_t n_layers, const kvc_vote_layer* layers, int32_t group,
+                    int32_t window, void* stream) {
+    int cpr = 0;
+    int st = check_shape(shape, &cpr);
+    if (st != KVC_OK) return st;
+    if (n_layers < 0 || (n_layers > 0 && !layers) || group <= 0 || window <= 0) return KVC_ERR_INVALID_ARG;
+    if (n_layers == 0) return KVC_OK;
+    const int B = shape->batch, H = shape->heads, dt = shape->dtype;
+    if (dt == KVC_DTYPE_F32) return KVC_ERR_UNSUPPORTED;
+    if (cpr != 8 && cpr != 10 && cpr != 16) return KVC_ERR_UNSUPPORTED;
+    if ((int64_t)group * window > kVoteM) return KVC_ERR_UNSUPPORTED;
+    for (int l = 0; l < n_layers; ++l) {
+        const kvc_vote_layer& v = layers[l];
+        if (!v.k_in || !v.q_obs || !v.votes_out || v.seq_len <= window) return KVC_ERR_INVALID_ARG;
+        if (((uintptr_t)v.k_in | (uintptr_t)v.q_obs) & 15) return KVC_ERR_UNSUPPORTED;
+        const int64_t sb = v.k_stride_b | v.k_stride_h | v.k_stride_s | v.q_stride_b | v.q_stride_h | v.q_stride_s;
+        if ((sb * 2) & 15) return KVC_ERR_UNSUPPORTED;
+    }
+    st = set_device(shape->device);
+    if (st != KVC_OK) return st;
+    using VoteFn = void (*)(const VoteBatchDev);
+    VoteFn fn = nullptr;
+    if (dt == KVC_DTYPE_BF16)
+        fn = cpr == 8 ? kvc_snapkv_vote_kernel<KVC_DTYPE_BF16, 8> : cpr == 10 ? kvc_snapkv_vote_kernel<KVC_DTYPE_BF16, 10>
+                                                                             : kvc_snapkv_vote_kernel<KVC_DTYPE_BF16, 16>;
+    else
+        fn = cpr == 8 ? kvc_snapkv_vote_kernel<KVC_DTYPE_F16, 8> : cpr == 10 ? kvc_snapkv_vote_kernel<KVC_DTYPE_F16, 10>
+                                                                            : kvc_snapkv_vote_kernel<KVC_DTYPE_F16, 16>;
+    const size_t smem = 1280 + 3 * (size_t)(kVoteTile / 8) * cpr * kVoteLBO;
+    st = ensure_tma_attrs((const void*)fn, shape->device);
+    if (st != KVC_OK) return st;
+    for (int l0 = 0; l0 < n_layers; l0 += KVC_MAX_LAYERS_PER_LAUNCH) {
+        const int nl = (n_layers - l0) < KVC_MAX_LAYERS_PER_LAUNCH ? (n_layers - l0) : KVC_MAX_LAYERS_PER_LAUNCH;
+        VoteBatchDev bd;
+        memset(&bd, 0, sizeof(bd));
+        bd.B = B;
+        bd.H = H;
+        bd.G = group;
+        bd.W = window;
+        bd.scale_log2e = 1.4426950408889634f / sqrtf((float)shape->head_dim);
+        for (int l = 0; l < nl; ++l) {
+            const kvc_vote_layer& v = layers[l0 + l];
+            VoteLayerDev& d = bd.layers[l];
+            d.k = (const char*)v.k_in;
+            d.q = (const char*)v.q_obs;
+            d.votes = (char*)v.votes_out;
+            d.ksb = v.k_stride_b * 2;
+            d.ksh = v.k_stride_h * 2;
+            d.kss = v.k_stride_s * 2;
+            d.qsb = v.q_stride_b * 2;
+            d.qsh = v.q_stride_h * 2;
+            d.qss = v.q_stride_s * 2;
+            d.S = v.seq_len;
+        }
+        dim3 grid((unsigned)((int64_t)B * H), (unsigned)nl, 1);
+        fn<<<grid, 128, smem, (cudaStream_t)stream>>>(bd);
+        cudaError_t err = cudaGetLastError();
+        if (err != cudaSuccess) return cuda_fail(err, "kvc_snapkv_vote_kernel launch");
         g_launches.fetch_add(1);
     }
     return KVC_OK;

@@ -1,0 +1,301 @@
+// kvc_vote.cuh — SnapKV observation-window vote on the 5th-generation tensor cores (tcgen05 + TMEM).
+//
+// OPT-IN EXTENSION.  The reference's snapkv_lite has no queries and no q.K^T (snapkv_lite.py:93-100 ranks
+// keys by inverted L2 norm); this kernel implements the vote the method is named after (reference
+// docs/logsAndBugs/SnapKV_Feasibility_Analysis.md:29-62): the last W queries of every query head attend
+// over the whole cache, and each prefix key's score is the attention mass it receives,
+//
+//     vote[b, hkv, j] = sum over the G query heads of the group and the W window queries i of
+//                       softmax_j( q_i . k_j / sqrt(D)  [causal inside the window] )         for j < P = S - W
+//
+// One CTA (128 threads) owns one (layer, batch, kv head).  Queries of the group are stacked into a
+// 128-row operand (G*W <= 128, zero rows beyond).  Keys stream in tiles of 128 rows, twice:
+//
+//   pass 1  S   = Q . Ktile^T  (M = query rows, N = keys): TMEM lane = query row, so each thread keeps the
+//           online softmax statistics (running max m_i, sum l_i) of ITS row — no cross-thread traffic;
+//   pass 2  S^T = Ktile . Q^T  (M = keys, N = query rows): TMEM lane = key, so each thread sums
+//           exp2(s*c - m_i) / l_i over the 128 columns of ITS key — the vote — and stores it.
+//
+// Operands are staged in shared memory in the canonical K-major no-swizzle UMMA layout (8x16-byte core
+// matrices) by the CTA's own threads (LDG.128 -> registers -> STS.128, prefetched one tile ahead), the
+// accumulator lives in TMEM (2 x 128 columns, double-buffered), `tcgen05.mma` is issued by one thread,
+// completion arrives on an mbarrier through `tcgen05.commit`, and `tcgen05.ld` brings scores to registers.
+// Intensity is ~2*128 flop per key byte at most: the kernel stays HBM/MUFU-bound, not tensor-bound
+// (SURVEY.md §7 "SnapKV vote spec gap") — the tensor pipe is reported, not chased.
+#pragma once
+#include "kvc_device.cuh"
+#include "kvc_tma.cuh"
+
+namespace kvc {
+
+struct VoteLayerDev {
+    const char* k;    // [B,H,S,D] keys
+    const char* q;    // [B,Hq,W,D] observation-window queries, Hq = G*H
+    char* votes;      // [B,H,P] in the cache dtype
+    int64_t ksb, ksh, kss;  // BYTE strides of K
+    int64_t qsb, qsh, qss;  // BYTE strides of Q (batch, query head, row)
+    int32_t S, pad;
+};
+static_assert(sizeof(VoteLayerDev) == 80, "VoteLayerDev is passed by value in kernel params");
+
+struct VoteBatchDev {
+    int32_t B, H, G, W;
+    float scale_log2e;  // log2(e) / sqrt(D)
+    int32_t pad[3];
+    VoteLayerDev layers[KVC_MAX_LAYERS_PER_LAUNCH];
+};
+
+constexpr int kVoteM = 128;     // rows of both MMA shapes
+constexpr int kVoteTile = 128;  // keys per tile
+
+// ---------------------------------------------------------------- tcgen05 wrappers
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// D[tmem] (+)= A[smem] . B[smem]^T, bf16/fp16 inputs, fp32 accumulate; issued by ONE thread.
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// mbarrier arrive once every previously issued tcgen05.mma of this thread has completed.
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (lane = TMEM lane base + laneid).
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, no swizzle: 8x16-byte core matrices; LBO = step between the two 16-byte K chunks of one
+// K=16 instruction, SBO = step between 8-row groups (cute/arch/mma_sm100_desc.hpp, SmemDescriptor).
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+    d |= (uint64_t)1 << 46;  // descriptor version (Blackwell)
+    return d;                // base_offset 0, lbo_mode 0, layout_type 0 = SWIZZLE_NONE
+}
+// Instruction descriptor (cute/arch/mma_sm100_desc.hpp, InstrDescriptor): fp32 accumulate, K-major A and B.
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int fmt /*0 f16, 1 bf16*/, int m, int n) {
+    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// Chunk (row r, 16-byte chunk c) of a [rows][CPR chunks] operand tile in the canonical layout.  Core
+// matrices (8 rows x 16 B = 128 B) are spaced kVoteLBO = 144 B apart: the odd 16-byte pitch makes the
+// 8 consecutive chunks a quarter-warp stores (one row, coalesced global read) land in 8 different bank groups.
+constexpr int kVoteLBO = 144;
+template <int CPR>
+__device__ __forceinline__ uint32_t umma_off(int r, int c) {
+    return (uint32_t)((r >> 3) * (CPR * kVoteLBO) + c * kVoteLBO + (r & 7) * 16);
+}
+
+template <int DT, int CPR>
+__global__ void __launch_bounds__(128, 2) kvc_snapkv_vote_kernel(const __grid_constant__ VoteBatchDev bd) {
+    using Tr = Traits<DT>;
+    using Key = typename Tr::Key;
+    static_assert(DT != KVC_DTYPE_F32, "the vote runs on 16-bit caches (kind::f16)");
+    constexpr int TILE_BYTES = (kVoteTile / 8) * CPR * kVoteLBO;  // padded canonical layout
+    constexpr int CH = kVoteTile * CPR / 128;  // 16-byte chunks per thread per tile
+    constexpr uint32_t IDESC = umma_idesc_f16(DT == KVC_DTYPE_BF16 ? 1 : 0, kVoteM, kVoteTile);
+
+    const VoteLayerDev& L = bd.layers[blockIdx.y];
+    const int bh = blockIdx.x;
+    const int b = bh / bd.H, h = bh - b * bd.H;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int S = L.S, W = bd.W, G = bd.G;
+    const int P = S - W;
+    const int rows_q = G * W;
+
+    extern __shared__ __align__(128) unsigned char smem[];
+    // [0,256): scalars + 2 mbarriers; then row statistics; then Q and two K-tile buffers
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem);
+    const uint32_t bar0 = smem_u32(smem + 16);
+    float* s_m = reinterpret_cast<float*>(smem + 256);        // [128] row max (log2 domain)
+    float* s_invl = reinterpret_cast<float*>(smem + 256 + 512);  // [128] 1 / row sum (0 for padding rows)
+    unsigned char* s_q = smem + 1280;
+    unsigned char* s_k = s_q + TILE_BYTES;  // two buffers of TILE_BYTES
+
+    if (warp == 0) tmem_alloc(smem_u32(s_tmem), 256);
+    if (tid == 0) {
+        mbar_init(bar0, 1);
+        mbar_init(bar0 + 8, 1);
+        mbar_init_fence();
+    }
+    // ---------------------------------------------------------------- Q operand (once per unit)
+    const char* kbase = L.k + (int64_t)b * L.ksb + (int64_t)h * L.ksh;
+    for (int q = tid; q < kVoteM * CPR; q += 128) {
+        const int r = q / CPR, c = q - r * CPR;
+        int4 v = make_int4(0, 0, 0, 0);
+        if (r < rows_q) {
+            const int g = r / W, w = r - g * W;
+            v = ldg128_stream(L.q + (int64_t)b * L.qsb + (int64_t)(h * G + g) * L.qsh + (int64_t)w * L.qss + c * 16);
+        }
+        *reinterpret_cast<int4*>(s_q + umma_off<CPR>(r, c)) = v;
+    }
+    // tile loader: thread owns CH chunks; chunk index q -> (row, chunk), diagonal order keeps STS conflict-free
+    auto load_tile = [&](int t, int4 (&reg)[CH]) {
+        const int r0 = t * kVoteTile;
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+            const int q = i * 128 + tid;
+            const int r = q / CPR, c = q - r * CPR;
+            reg[i] = (r0 + r < S) ? ldg128_stream(kbase + (int64_t)(r0 + r) * L.kss + c * 16) : make_int4(0, 0, 0, 0);
+        }
+    };
+    auto store_tile = [&](int buf, const int4 (&reg)[CH]) {
+        unsigned char* dst = s_k + buf * TILE_BYTES;
+#pragma unroll
+        for (int i = 0; i < CH; ++i) {
+            const int q = i * 128 + tid;
+            const int r = q / CPR, c = q - r * CPR;
+            *reinterpret_cast<int4*>(dst + umma_off<CPR>(r, c)) = reg[i];
+        }
+    };
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *s_tmem;
+    const uint32_t q_addr = smem_u32(s_q), k_addr = smem_u32(s_k);
+
+    // issue the CPR/2 K-steps of one 128x128xD product: pass 1 (A = Q, B = K tile) or pass 2 (A = K tile, B = Q)
+    auto issue = [&](int buf, bool keys_are_rows) {
+        const uint32_t a0 = keys_are_rows ? k_addr + buf * TILE_BYTES : q_addr;
+        const uint32_t b0 = keys_are_rows ? q_addr : k_addr + buf * TILE_BYTES;
+#pragma unroll
+        for (int ks = 0; ks < CPR / 2; ++ks) {
+            const uint64_t ad = umma_smem_desc(a0 + ks * 2 * kVoteLBO, kVoteLBO, CPR * kVoteLBO);
+            const uint64_t bdsc = umma_smem_desc(b0 + ks * 2 * kVoteLBO, kVoteLBO, CPR * kVoteLBO);
+            umma_f16(tmem + buf * kVoteTile, ad, bdsc, IDESC, ks > 0 ? 1u : 0u);
+        }
+        umma_commit(bar0 + buf * 8);
+    };
+
+    const float c2 = bd.scale_log2e;
+    const int lane_row = tid;  // TMEM lane owned by this thread (warp w reads lanes 32w..32w+31)
+    const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
+    uint32_t phase[2] = {0, 0};
+
+    for (int pass = 0; pass < 2; ++pass) {
+        const bool keys_are_rows = pass == 1;
+        const int n_tiles = keys_are_rows ? (P + kVoteTile - 1) / kVoteTile : (S + kVoteTile - 1) / kVoteTile;
+        float m_run = -INFINITY, l_run = 0.f;  // pass 1 state of query row `lane_row`
+        int4 reg[CH];
+        // prologue: tiles 0 and 1 staged, MMA(0) and MMA(1) in flight
+        for (int t = 0; t < 2 && t < n_tiles; ++t) {
+            load_tile(t, reg);
+            store_tile(t, reg);
+        }
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            for (int t = 0; t < 2 && t < n_tiles; ++t) issue(t, keys_are_rows);
+        }
+        for (int t = 0; t < n_tiles; ++t) {
+            const int buf = t & 1;
+            const bool more = t + 2 < n_tiles;
+            if (more) load_tile(t + 2, reg);  // global loads in flight across the math below
+            mbar_wait(bar0 + buf * 8, phase[buf]);
+            phase[buf] ^= 1;
+            tc_fence_after();
+            const int key0 = t * kVoteTile;
+            if (!keys_are_rows) {
+                // ---------------- pass 1: row = query, columns = keys of this tile
+                const int w_pos = (lane_row < rows_q) ? (lane_row % W) : 0;
+                const int limit = P + w_pos;  // last key this query may attend (causal inside the window)
+                uint32_t v[32];
+                // online softmax statistics, 32 columns at a time
+#pragma unroll 1
+                for (int cb = 0; cb < kVoteTile; cb += 32) {
+                    tmem_ld32(t_lane + buf * kVoteTile + cb, v);
+                    float cmax = -INFINITY;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const int key = key0 + cb + j;
+                        const float s = (key <= limit && key < S) ? __uint_as_float(v[j]) * c2 : -INFINITY;
+                        v[j] = __float_as_uint(s);
+                        cmax = fmaxf(cmax, s);
+                    }
+                    const float m_new = fmaxf(m_run, cmax);
+                    if (m_new > -INFINITY) {
+                        float acc = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) acc += ex2(__uint_as_float(v[j]) - m_new);
+                        l_run = l_run * ex2(m_run - m_new) + acc;
+                        m_run = m_new;
+                    }
+                }
+            } else {
+                // ---------------- pass 2: row = key, columns = query rows
+                float vote = 0.f;
+                uint32_t v[32];
+#pragma unroll 1
+                for (int cb = 0; cb < kVoteM; cb += 32) {
+                    tmem_ld32(t_lane + buf * kVoteTile + cb, v);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 mm = *reinterpret_cast<const float4*>(s_m + cb + j);
+                        const float4 il = *reinterpret_cast<const float4*>(s_invl + cb + j);
+                        vote = fmaf(ex2(fmaf(__uint_as_float(v[j + 0]), c2, -mm.x)), il.x, vote);
+                        vote = fmaf(ex2(fmaf(__uint_as_float(v[j + 1]), c2, -mm.y)), il.y, vote);
+                        vote = fmaf(ex2(fmaf(__uint_as_float(v[j + 2]), c2, -mm.z)), il.z, vote);
+                        vote = fmaf(ex2(fmaf(__uint_as_float(v[j + 3]), c2, -mm.w)), il.w, vote);
+                    }
+                }
+                const int key = key0 + lane_row;
+                if (key < P) {
+                    Key* out = reinterpret_cast<Key*>(L.votes) + (int64_t)bh * P;
+                    out[key] = (Key)Tr::to_raw(vote);
+                }
+            }
+            // the accumulator and the operand buffer of tile t are free again: stage tile t+2 and issue it
+            tc_fence_before();
+            if (more) {
+                store_tile(buf, reg);
+                fence_proxy_async_smem();
+            }
+            __syncthreads();
+            if (more && tid == 0) {
+                tc_fence_after();
+                issue(buf, keys_are_rows);
+            }
+        }
+        if (!keys_are_rows) {
+            // publish the row statistics; padding rows (>= G*W) never vote
+            s_m[lane_row] = (lane_row < rows_q && l_run > 0.f) ? m_run : 0.f;
+            s_invl[lane_row] = (lane_row < rows_q && l_run > 0.f) ? 1.f / l_run : 0.f;
+            __syncthreads();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+}  // namespace kvc

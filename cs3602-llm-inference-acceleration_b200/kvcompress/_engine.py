@@ -27,9 +27,10 @@ _LIB_PATH = os.environ.get("KVC_LIBRARY") or os.path.join(_CSRC_DIR, _LIB_NAME) 
 
 # struct layouts of include/kvc.h
 _PLAN = struct.Struct("8i")        # kvc_layer_plan: seq_len sink sel_lo sel_hi k_sel tail score pool_kernel
-_IO = struct.Struct("4P6q2P")      # kvc_layer_io: k_in v_in k_out v_out | 6 strides | idx_out idx_in
+_IO = struct.Struct("4P6q3P")      # kvc_layer_io: k_in v_in k_out v_out | 6 strides | idx_out idx_in score_in
 _SHAPE = struct.Struct("5i")       # kvc_shape: batch heads head_dim dtype device
-assert _PLAN.size == 32 and _IO.size == 96 and _SHAPE.size == 20
+assert _PLAN.size == 32 and _IO.size == 104 and _SHAPE.size == 20
+KVC_ABI_VERSION = 2
 
 KVC_DTYPE = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
 KVC_OK = 0
@@ -75,8 +76,11 @@ def load_library():
     lib.kvc_slab_compress.restype = ctypes.c_int
     lib.kvc_slab_compress.argtypes = [ctypes.c_char_p, ctypes.c_int32, ctypes.c_char_p, ctypes.c_char_p,
                                       ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
-    if lib.kvc_abi_version() != 1:
-        raise RuntimeError(f"{_LIB_NAME}: ABI version {lib.kvc_abi_version()} != 1 — rebuild the library")
+    lib.kvc_snapkv_vote.restype = ctypes.c_int
+    lib.kvc_snapkv_vote.argtypes = [ctypes.c_char_p, ctypes.c_int32, ctypes.c_char_p, ctypes.c_int32, ctypes.c_int32,
+                                    ctypes.c_void_p]
+    if lib.kvc_abi_version() != KVC_ABI_VERSION:
+        raise RuntimeError(f"{_LIB_NAME}: ABI version {lib.kvc_abi_version()} != {KVC_ABI_VERSION} — rebuild the library")
     _lib = lib
     return lib
 
@@ -154,7 +158,7 @@ class PlanSet:
 
 
 def run_plans(kv: Sequence[Tuple[torch.Tensor, torch.Tensor]], plans, given_indices: Optional[dict] = None,
-              return_indices: bool = False):
+              return_indices: bool = False, given_scores: Optional[dict] = None):
     """Apply per-layer plans (a list of ``LayerPlan`` or a cached :class:`PlanSet`) to a list of (K, V) pairs.
 
     KEEP layers keep their tensor objects, VIEW layers become ``x[:, :, -n:, :]`` views (both
@@ -163,6 +167,7 @@ def run_plans(kv: Sequence[Tuple[torch.Tensor, torch.Tensor]], plans, given_indi
     The outputs of a group with one common length are carved out of ONE allocation.
 
     given_indices: {layer_idx: int32 tensor [B, H, k_sel]} for SCORE_GIVEN_INDEX plans.
+    given_scores: {layer_idx: cache-dtype tensor [B, H, sel_hi - sel_lo]} for SCORE_GIVEN_SCORE plans.
     return_indices: also return {layer_idx: int32 tensor [B, H, C]} of kept absolute rows.
     """
     ps = plans if isinstance(plans, PlanSet) else PlanSet(plans)
@@ -250,10 +255,20 @@ def run_plans(kv: Sequence[Tuple[torch.Tensor, torch.Tensor]], plans, given_indi
                     gi = gi.pin_memory()
                 idx_in_ptr = gi.data_ptr()
                 keepalive.append(gi)
+            score_in_ptr = 0
+            if plan.score == P.SCORE_GIVEN_SCORE and plan.k_sel > 0:
+                gs = None if given_scores is None else given_scores.get(li)
+                if gs is None:
+                    raise ValueError(f"layer {li}: plan needs caller-supplied scores")
+                if gs.dtype != dtype or not gs.is_contiguous() or tuple(gs.shape) != (B, H, plan.sel_hi - plan.sel_lo) \
+                        or gs.device != device:
+                    raise ValueError(f"layer {li}: scores must be a contiguous {dtype} [B, H, region] tensor on {device}")
+                score_in_ptr = gs.data_ptr()
+                keepalive.append(gs)
             plan_buf[m * _PLAN.size:(m + 1) * _PLAN.size] = ps.packed[li]
             ks, vs = keys.stride(), values.stride()
             _IO.pack_into(io_buf, m * _IO.size, keys.data_ptr(), values.data_ptr(), k_out_ptr, v_out_ptr,
-                          ks[0], ks[1], ks[2], vs[0], vs[1], vs[2], idx_out_ptr, idx_in_ptr)
+                          ks[0], ks[1], ks[2], vs[0], vs[1], vs[2], idx_out_ptr, idx_in_ptr, score_in_ptr)
         dev_index = run_device.index if run_device.index is not None else torch.cuda.current_device()
         shape_rec = _SHAPE.pack(B, H, D, KVC_DTYPE[dtype], dev_index)
         status = lib.kvc_compress_layers(shape_rec, n, bytes(plan_buf), bytes(io_buf),
@@ -296,4 +311,55 @@ def select(scores: torch.Tensor, k: int, largest: bool = False) -> torch.Tensor:
                                        1 if largest else 0, out.data_ptr(),
                                        ctypes.c_void_p(_stream_ptr(scores.device)))
     _check(status, "kvc_select")
+    return out
+
+
+_VOTE = struct.Struct("3P6q2i")  # kvc_vote_layer: k_in q_obs votes_out | 6 strides | seq_len reserved
+assert _VOTE.size == 80
+
+
+def snapkv_votes(layers: Sequence[Tuple[torch.Tensor, torch.Tensor]], window: int) -> List[torch.Tensor]:
+    """Observation-window votes on the tensor cores (tcgen05), one launch for every (keys, obs_queries) pair.
+
+    layers: [(keys [B,H,S,D], obs_queries [B,H*G,W,D]), ...] 16-bit CUDA tensors of one shape.
+    Returns votes [B,H,S-W] per layer (cache dtype):
+    ``softmax(Q K^T / sqrt(D), causal inside the window)[..., :S-W].sum over the window queries and the group``."""
+    if not layers:
+        return []
+    k0, q0 = layers[0]
+    _require_cuda(k0, "keys")
+    B, H, _, D = k0.shape
+    if q0.dim() != 4 or q0.size(0) != B or q0.size(1) % H or q0.size(2) != window or q0.size(3) != D:
+        raise ValueError(f"obs_queries must be [B={B}, H*G, W={window}, D={D}], got {tuple(q0.shape)}")
+    G = q0.size(1) // H
+    if k0.dtype not in (torch.bfloat16, torch.float16):
+        raise ValueError("the q.K^T vote runs on bfloat16/float16 caches")
+    if D * 2 // 16 not in (8, 10, 16) or (D * 2) % 16:
+        raise ValueError(f"head_dim {D}: the vote kernel covers head_dim 64, 80 and 128")
+    if G * window > 128:
+        raise ValueError(f"group size x observation_window = {G * window} exceeds the 128 query rows of one MMA")
+    out, keep = [], []
+    buf = bytearray(_VOTE.size * len(layers))
+    for m, (keys, q) in enumerate(layers):
+        _require_cuda(keys, f"layer {m} keys")
+        _require_cuda(q, f"layer {m} obs_queries")
+        if keys.shape[:2] != (B, H) or keys.size(3) != D or keys.dtype != k0.dtype or q.dtype != k0.dtype \
+                or tuple(q.shape) != tuple(q0.shape) or keys.device != k0.device or q.device != k0.device:
+            raise ValueError(f"layer {m}: keys / obs_queries do not match layer 0's shape, dtype or device")
+        if keys.size(2) <= window:
+            raise ValueError(f"layer {m}: {keys.size(2)} rows do not exceed the observation window {window}")
+        if not _rows_ok(keys):
+            keys = keys.contiguous()
+        if not _rows_ok(q):
+            q = q.contiguous()
+        keep.append((keys, q))
+        votes = torch.empty((B, H, keys.size(2) - window), dtype=keys.dtype, device=keys.device)
+        out.append(votes)
+        ks, qs = keys.stride(), q.stride()
+        _VOTE.pack_into(buf, m * _VOTE.size, keys.data_ptr(), q.data_ptr(), votes.data_ptr(), ks[0], ks[1], ks[2],
+                        qs[0], qs[1], qs[2], keys.size(2), 0)
+    shape = _SHAPE.pack(B, H, D, KVC_DTYPE[k0.dtype], k0.device.index)
+    status = load_library().kvc_snapkv_vote(shape, len(layers), bytes(buf), G, window,
+                                            ctypes.c_void_p(_stream_ptr(k0.device)))
+    _check(status, "kvc_snapkv_vote")
     return out

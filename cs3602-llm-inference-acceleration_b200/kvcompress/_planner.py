@@ -26,6 +26,7 @@ SCORE_L2_LOW = 1
 SCORE_L2_HIGH = 2
 SCORE_SNAPKV_POOL = 3
 SCORE_GIVEN_INDEX = 4
+SCORE_GIVEN_SCORE = 5
 
 KEEP = "keep"      # layer is returned untouched (the same tensor objects)
 VIEW = "view"      # layer is replaced by the view  x[:, :, -view_n:, :]  (no bytes move)

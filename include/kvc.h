@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define KVC_ABI_VERSION 1
+#define KVC_ABI_VERSION 2
 
 typedef enum kvc_status {
     KVC_OK = 0,
@@ -64,7 +64,9 @@ typedef enum kvc_score_kind {
     KVC_SCORE_L2_LOW = 1,      /* keep the k_sel lowest  ||K||_2  (norm().argsort()[:k])            */
     KVC_SCORE_L2_HIGH = 2,     /* keep the k_sel highest ||K||_2  (argsort(descending=True)[:k])    */
     KVC_SCORE_SNAPKV_POOL = 3, /* (max norm + 1e-6 - norm) -> avg_pool1d -> topk (snapkv_lite.py:96-134) */
-    KVC_SCORE_GIVEN_INDEX = 4  /* caller supplies ascending absolute row indices (fix_size_l2 "random") */
+    KVC_SCORE_GIVEN_INDEX = 4, /* caller supplies ascending absolute row indices (fix_size_l2 "random") */
+    KVC_SCORE_GIVEN_SCORE = 5  /* caller supplies per-row scores (score_in): avg_pool1d(pool_kernel) -> keep the
+                                  k_sel HIGHEST (snapkv vote mode: kvc_snapkv_vote output; h2o_attention.py:194-213) */
 } kvc_score_kind;
 
 /* One layer's keep-plan: integers computed by the host planner (reference arithmetic). */
@@ -89,6 +91,7 @@ typedef struct kvc_layer_io {
     int64_t v_stride_b, v_stride_h, v_stride_s; /* elements      */
     int32_t* idx_out;      /* optional [B,H,C] kept absolute row indices, ascending; may be NULL */
     const int32_t* idx_in; /* GIVEN_INDEX only: [B,H,k_sel] ascending absolute rows inside the region */
+    const void* score_in;  /* GIVEN_SCORE only: [B,H,sel_hi-sel_lo] scores of the region's rows, cache dtype, dense */
 } kvc_layer_io;
 
 typedef struct kvc_shape {
@@ -123,6 +126,26 @@ int kvc_key_norms(const kvc_shape* shape, const void* k_in, int64_t stride_b, in
  * `largest`) entries, ties to the lowest index, written as ascending int32 indices [n_rows, k]. */
 int kvc_select(int32_t dtype, int32_t device, const void* scores, int64_t n_rows, int32_t n,
                int32_t k, int32_t largest, int32_t* idx_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * SnapKV observation-window vote on the tensor cores (tcgen05 + TMEM) — OPT-IN EXTENSION.
+ * The reference's snapkv_lite ranks keys by inverted L2 norm (snapkv_lite.py:93-100: no queries, no
+ * q.K^T); this entry computes the vote the method is named after (reference
+ * docs/logsAndBugs/SnapKV_Feasibility_Analysis.md:29-62):
+ *   votes[b,h,j] = sum_{g<G} sum_{i<W} softmax_j( Q[b,h*G+g,i,:] . K[b,h,j,:] / sqrt(D) ),  j < S - W,
+ * the softmax running over all S keys with the causal mask inside the window.  16-bit caches only;
+ * head_dim*2/16 in {8,10,16}; G*W <= 128.  Feed votes to kvc_compress_layers as KVC_SCORE_GIVEN_SCORE. */
+typedef struct kvc_vote_layer {
+    const void* k_in;   /* [B,H,S,D] keys */
+    const void* q_obs;  /* [B,H*G,W,D] queries of the last W positions, last dim dense */
+    void* votes_out;    /* [B,H,S-W] votes, cache dtype, dense */
+    int64_t k_stride_b, k_stride_h, k_stride_s; /* elements */
+    int64_t q_stride_b, q_stride_h, q_stride_s; /* elements */
+    int32_t seq_len;    /* S */
+    int32_t reserved;
+} kvc_vote_layer;
+int kvc_snapkv_vote(const kvc_shape* shape, int32_t n_layers, const kvc_vote_layer* layers, int32_t group,
+                    int32_t window, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Slab cache: the container step on both sides of the compress call.

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_library_metadata_and_argument_checks():
     lib = _engine.load_library()
-    assert lib.kvc_abi_version() == 1
+    assert lib.kvc_abi_version() == 2
     assert b"sm_100a" in lib.kvc_build_info()
     assert lib.kvc_status_string(0) == b"ok"
     assert lib.kvc_launch_count() >= 0
@@ -38,7 +38,7 @@ def test_library_metadata_and_argument_checks():
     assert lib.kvc_compress_layers(None, 1, None, None, None) == 1
     shape = _engine._SHAPE.pack(1, 1, 12, 2, 0)  # D=12 bf16 -> 24-byte rows: not 16-byte aligned
     plan = _engine._PLAN.pack(10, 1, 0, 0, 0, 1, 0, 1)
-    io = _engine._IO.pack(16, 16, 16, 16, 120, 120, 12, 120, 120, 12, 0, 0)
+    io = _engine._IO.pack(16, 16, 16, 16, 120, 120, 12, 120, 120, 12, 0, 0, 0)
     assert lib.kvc_compress_layers(shape, 1, plan, io, None) == 2
     shape = _engine._SHAPE.pack(1, 1, 16, 2, 0)
     bad_plan = _engine._PLAN.pack(10, 1, 0, 20, 3, 1, 1, 1)  # sel_hi > seq_len
@@ -46,4 +46,4 @@ def test_library_metadata_and_argument_checks():
 
 
 def test_structs_match_header_sizes():
-    assert _engine._PLAN.size == 32 and _engine._IO.size == 96 and _engine._SHAPE.size == 20
+    assert _engine._PLAN.size == 32 and _engine._IO.size == 104 and _engine._SHAPE.size == 20

@@ -1,0 +1,108 @@
+"""-m gpu: the opt-in tcgen05 q.K^T observation-window vote (an extension: the reference's snapkv_lite has no
+queries) against a plain torch fp32 reference of the same op, and its select against the reference scores."""
+
+import math
+
+import pytest
+import torch
+
+import kvcompress
+from kvcompress import _engine
+
+pytestmark = pytest.mark.gpu
+
+
+def vote_reference(keys, queries, window):
+    """fp32: softmax over all S keys (causal inside the window), summed over window queries and group heads."""
+    B, H, S, D = keys.shape
+    G = queries.size(1) // H
+    P = S - window
+    k = keys.float().repeat_interleave(G, dim=1)                       # [B, H*G, S, D]
+    s = torch.matmul(queries.float(), k.transpose(-1, -2)) / math.sqrt(D)   # [B, H*G, W, S]
+    pos_q = P + torch.arange(window, device=keys.device).view(1, 1, window, 1)
+    pos_k = torch.arange(S, device=keys.device).view(1, 1, 1, S)
+    s = s.masked_fill(pos_k > pos_q, float("-inf"))
+    attn = torch.softmax(s, dim=-1)
+    return attn[..., :P].sum(dim=2).view(B, H, G, P).sum(dim=2)        # [B, H, P]
+
+
+CASES = [
+    # B, H, G, W, S, D, dtype
+    (1, 2, 4, 32, 1000, 128, torch.bfloat16),   # Llama-3-8B GQA shape: 4 query heads x 32 window rows = 128
+    (2, 3, 1, 32, 700, 80, torch.bfloat16),     # Pythia MHA: 32 query rows, 96 padding rows
+    (1, 2, 2, 16, 300, 64, torch.float16),
+    (1, 1, 4, 32, 129, 128, torch.bfloat16),    # P = 97: a single partial tile, window straddles it
+    (2, 8, 4, 32, 4096, 128, torch.bfloat16),
+]
+
+
+@pytest.mark.parametrize("B,H,G,W,S,D,dtype", CASES, ids=[f"B{c[0]}H{c[1]}G{c[2]}W{c[3]}S{c[4]}D{c[5]}" for c in CASES])
+def test_votes_match_torch_reference(B, H, G, W, S, D, dtype):
+    gen = torch.Generator(device="cuda").manual_seed(S + D)
+    keys = [torch.randn(B, H, S, D, generator=gen, device="cuda").to(dtype) for _ in range(2)]
+    qs = [(1.5 * torch.randn(B, H * G, W, D, generator=gen, device="cuda")).to(dtype) for _ in range(2)]
+    n0 = _engine.launch_count()
+    votes = _engine.snapkv_votes(list(zip(keys, qs)), W)
+    assert _engine.launch_count() - n0 == 1
+    for k, q, v in zip(keys, qs, votes):
+        want = vote_reference(k, q, W)
+        assert v.shape == want.shape and v.dtype == dtype
+        got = v.float()
+        ulp = 2.0 ** -8 if dtype == torch.bfloat16 else 2.0 ** -11
+        # fp32 accumulate + ex2.approx, then ONE rounding to the cache dtype
+        assert torch.all((got - want).abs() <= 2.5 * ulp * want + 1e-7), float(((got - want).abs() / (want + 1e-12)).max())
+        # every window query distributes mass 1 over the keys it sees: votes sum to <= G*W per head
+        assert torch.all(want.sum(-1) <= G * W + 1e-3)
+
+
+def test_strided_keys_and_queries():
+    B, H, G, W, S, D = 1, 2, 4, 32, 600, 128
+    k = torch.randn(B, S, H, D, device="cuda").bfloat16().permute(0, 2, 1, 3)      # [B,S,H,D] storage
+    q = torch.randn(B, W, H * G, D, device="cuda").bfloat16().permute(0, 2, 1, 3)
+    a = _engine.snapkv_votes([(k, q)], W)[0]
+    b = _engine.snapkv_votes([(k.contiguous(), q.contiguous())], W)[0]
+    assert torch.equal(a, b)
+
+
+def test_snapkv_vote_mode_selects_the_highest_pooled_votes():
+    torch.manual_seed(0)
+    L, B, H, G, W, S, D, keep, pk = 3, 2, 2, 4, 32, 1500, 128, 256, 5
+    kv = [(torch.randn(B, H, S, D, device="cuda").bfloat16(), torch.randn(B, H, S, D, device="cuda").bfloat16())
+          for _ in range(L)]
+    qs = [(2.0 * torch.randn(B, H * G, W, D, device="cuda")).bfloat16() for _ in range(L)]
+    n0 = _engine.launch_count()
+    out = kvcompress.snapkv_lite_compress(kv, observation_window=W, keep_size=keep, pooling_kernel=pk,
+                                          skip_layers=[0], obs_queries=qs)
+    assert _engine.launch_count() - n0 == 2  # one vote launch + one pool/select/gather launch for all layers
+    assert out[0][0] is kv[0][0]
+    for li in (1, 2):
+        k_in, v_in = kv[li]
+        k_out, v_out = out[li]
+        assert k_out.shape == (B, H, keep, D)
+        # window rows are the last W rows
+        assert torch.equal(k_out[:, :, -W:], k_in[:, :, -W:]) and torch.equal(v_out[:, :, -W:], v_in[:, :, -W:])
+        # recover the kept prefix rows by matching V rows (random data: rows are unique)
+        votes = _engine.snapkv_votes([(k_in, qs[li])], W)[0]
+        pooled = torch.nn.functional.avg_pool1d(votes.float().reshape(B * H, 1, -1), pk, 1, pk // 2).reshape(B, H, -1)
+        pooled = pooled.to(torch.bfloat16).float()
+        want_idx = torch.topk(pooled, keep - W, dim=-1)[1].sort(dim=-1)[0]
+        rows_ref = torch.gather(v_in, 2, want_idx.unsqueeze(-1).expand(-1, -1, -1, D))
+        # identical up to ties at the threshold: compare the multiset of pooled scores of the kept rows
+        got_rows = v_out[:, :, :keep - W]
+        match = (got_rows.unsqueeze(3) == v_in[:, :, :S - W].unsqueeze(2)[..., :1, :]).all(-1) if False else None
+        same = (got_rows == rows_ref).all(-1).float().mean()
+        assert same > 0.97, float(same)
+        # out-of-place K rows correspond to the same positions as V rows
+        k_ref = torch.gather(k_in, 2, want_idx.unsqueeze(-1).expand(-1, -1, -1, D))
+        assert ((k_out[:, :, :keep - W] == k_ref).all(-1) == (got_rows == rows_ref).all(-1)).all()
+
+
+def test_vote_errors():
+    k = torch.randn(1, 2, 300, 128, device="cuda")
+    q = torch.randn(1, 8, 32, 128, device="cuda")
+    with pytest.raises(ValueError, match="bfloat16/float16"):
+        _engine.snapkv_votes([(k, q)], 32)
+    with pytest.raises(ValueError, match="exceeds the 128 query rows"):
+        _engine.snapkv_votes([(k.bfloat16(), torch.randn(1, 16, 32, 128, device="cuda").bfloat16())], 32)
+    with pytest.raises(ValueError, match="obs_queries"):
+        kvcompress.snapkv_lite_compress([(k.bfloat16(), k.bfloat16())], obs_queries=[])
