@@ -49,6 +49,10 @@ CONFIGS = {
     "c4": dict(LLAMA, B=16, S=32768, dtype="bf16", calls=[
         ("snapkv_lite", dict(observation_window=32, keep_size=512)),
     ]),
+    # configs[3] with the opt-in tcgen05 q.K^T vote (4 query heads per KV head, W=32 -> 128 query rows)
+    "c4_vote": dict(LLAMA, B=16, S=32768, dtype="bf16", calls=[
+        ("snapkv_lite", dict(observation_window=32, keep_size=512, _vote_group=4)),
+    ]),
     # configs[4]: B=64 total = 8 ranks x 8 streams (34 GB per rank)
     "c5": dict(LLAMA, B=8, S=32768, dtype="bf16", calls=[
         ("pyramid_kv", dict(base_size=512)),
@@ -135,7 +139,10 @@ def call_bytes(cfg, batch):
     out = []
     for method, kw in cfg["calls"]:
         plans = plans_for(method, [cfg["S"]] * cfg["L"], kw)
-        out.append(P.algorithmic_bytes(plans, batch, cfg["H"], cfg["D"], e))
+        nbytes = P.algorithmic_bytes(plans, batch, cfg["H"], cfg["D"], e)
+        if "_vote_group" in kw:  # vote mode reads the region's K rows twice (e*B*H*D*(2R + 4C))
+            nbytes += sum(p.region for p in plans if p.kind == P.GATHER) * batch * cfg["H"] * cfg["D"] * e
+        out.append(nbytes)
     return out
 
 
@@ -350,11 +357,19 @@ def run_ours(args):
         cfg["S"] = args.seq_len
     B = args.batch or cfg["B"]
     e = 4 if cfg["dtype"] == "f32" else 2
-    fns = [(kvcompress.get_compress_fn(m), kw) for m, kw in cfg["calls"]]
+    fns = [(kvcompress.get_compress_fn(m), {k: v for k, v in kw.items() if not k.startswith("_")}) for m, kw in cfg["calls"]]
     per_call_bytes = call_bytes(cfg, B)
     step_bytes = sum(per_call_bytes)
 
     kv = make_cache(cfg, B, device, seed=1234 + 1000 * rank)
+    vote_flops = 0
+    for (m, kw), (_, run_kw) in zip(cfg["calls"], fns):
+        if "_vote_group" in kw:  # synthetic observation-window queries: [B, H*G, W, D] per layer
+            G, Wn = kw["_vote_group"], kw["observation_window"]
+            run_kw["obs_queries"] = [(1.5 * torch.randn(B, cfg["H"] * G, Wn, cfg["D"], device=device)).to(kv[0][0].dtype)
+                                     for _ in range(cfg["L"])]
+            # two 128 x S x D products per (layer, b, kv head); 128 = padded query rows of the MMA
+            vote_flops += 2 * 2 * 128 * cfg["S"] * cfg["D"] * B * cfg["H"] * cfg["L"]
     torch.cuda.synchronize()
 
     def barrier():
@@ -447,6 +462,7 @@ def run_ours(args):
             "us_per_step": round(ms_per_step * 1e3, 1), "tok_per_s": round(B * world / (ms_per_step * 1e-3), 1),
             "algorithmic_bytes_per_step": step_bytes * world, "per_call": per_call, "roofline": roofline,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "tensor_tflops": round(vote_flops / (ms_per_step * 1e-3) / 1e12, 1) if vote_flops else None,
             "library": os.path.relpath(_engine.library_path(), ROOT),
         }
         print(json.dumps(line), flush=True)

@@ -926,7 +926,7 @@ int kvc_snapkv_vote(const kvc_shape* shape, int32_t n_layers, const kvc_vote_lay
     else
         fn = cpr == 8 ? kvc_snapkv_vote_kernel<KVC_DTYPE_F16, 8> : cpr == 10 ? kvc_snapkv_vote_kernel<KVC_DTYPE_F16, 10>
                                                                             : kvc_snapkv_vote_kernel<KVC_DTYPE_F16, 16>;
-    const size_t smem = 1280 + 3 * (size_t)(kVoteTile / 8) * cpr * kVoteLBO;
+    const size_t smem = 2304 + 3 * (size_t)(kVoteTile / 8) * cpr * kVoteLBO;
     st = ensure_tma_attrs((const void*)fn, shape->device);
     if (st != KVC_OK) return st;
     for (int l0 = 0; l0 < n_layers; l0 += KVC_MAX_LAYERS_PER_LAUNCH) {
@@ -953,7 +953,7 @@ int kvc_snapkv_vote(const kvc_shape* shape, int32_t n_layers, const kvc_vote_lay
             d.S = v.seq_len;
         }
         dim3 grid((unsigned)((int64_t)B * H), (unsigned)nl, 1);
-        fn<<<grid, 128, smem, (cudaStream_t)stream>>>(bd);
+        fn<<<grid, 256, smem, (cudaStream_t)stream>>>(bd);
         cudaError_t err = cudaGetLastError();
         if (err != cudaSuccess) return cuda_fail(err, "kvc_snapkv_vote_kernel launch");
         g_launches.fetch_add(1);

@@ -8,7 +8,7 @@
 //     vote[b, hkv, j] = sum over the G query heads of the group and the W window queries i of
 //                       softmax_j( q_i . k_j / sqrt(D)  [causal inside the window] )         for j < P = S - W
 //
-// One CTA (128 threads) owns one (layer, batch, kv head).  Queries of the group are stacked into a
+// One CTA (256 threads) owns one (layer, batch, kv head).  Queries of the group are stacked into a
 // 128-row operand (G*W <= 128, zero rows beyond).  Keys stream in tiles of 128 rows, twice:
 //
 //   pass 1  S   = Q . Ktile^T  (M = query rows, N = keys): TMEM lane = query row, so each thread keeps the
@@ -17,8 +17,9 @@
 //           exp2(s*c - m_i) / l_i over the 128 columns of ITS key — the vote — and stores it.
 //
 // Operands are staged in shared memory in the canonical K-major no-swizzle UMMA layout (8x16-byte core
-// matrices) by the CTA's own threads (LDG.128 -> registers -> STS.128, prefetched one tile ahead), the
-// accumulator lives in TMEM (2 x 128 columns, double-buffered), `tcgen05.mma` is issued by one thread,
+// matrices) by the CTA's own threads (`cp.async` 16-byte copies straight into the layout, in flight under
+// the math of the previous tile), the accumulator lives in TMEM (2 x 128 columns, one per 128-thread
+// pipeline), `tcgen05.mma` is issued by one thread per pipeline,
 // completion arrives on an mbarrier through `tcgen05.commit`, and `tcgen05.ld` brings scores to registers.
 // Intensity is ~2*128 flop per key byte at most: the kernel stays HBM/MUFU-bound, not tensor-bound
 // (SURVEY.md §7 "SnapKV vote spec gap") — the tensor pipe is reported, not chased.
@@ -106,51 +107,80 @@ __device__ __forceinline__ float ex2(float x) {
     return y;
 }
 
-// Chunk (row r, 16-byte chunk c) of a [rows][CPR chunks] operand tile in the canonical layout.  Core
-// matrices (8 rows x 16 B = 128 B) are spaced kVoteLBO = 144 B apart: the odd 16-byte pitch makes the
-// 8 consecutive chunks a quarter-warp stores (one row, coalesced global read) land in 8 different bank groups.
-constexpr int kVoteLBO = 144;
+// Chunk (row r, 16-byte chunk c) of a [rows][CPR chunks] operand tile in the canonical layout: dense
+// 128-byte core matrices (8 rows x 16 B), K chunks kVoteLBO = 128 B apart, 8-row groups CPR*128 B apart.
+constexpr int kVoteLBO = 128;
 template <int CPR>
 __device__ __forceinline__ uint32_t umma_off(int r, int c) {
     return (uint32_t)((r >> 3) * (CPR * kVoteLBO) + c * kVoteLBO + (r & 7) * 16);
 }
+// Work item q of a tile -> (row, chunk) such that 8 consecutive threads write the 8 rows of ONE core matrix
+// (one 128-byte line of shared memory: conflict-free) while the 4 octets of a warp read 4 consecutive
+// chunks of those rows (64 contiguous bytes per row: every 32-byte sector it touches is fully used).
+template <int CPR>
+__device__ __forceinline__ void tile_item(int q, int& r, int& c) {
+    const int rg = q / (8 * CPR), rem = q - rg * (8 * CPR);
+    c = rem >> 3;
+    r = rg * 8 + (rem & 7);
+}
 
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, bool valid) {
+    const uint32_t n = valid ? 16u : 0u;  // src-size 0: the 16 destination bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(n) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ void group_barrier(int grp) {  // immediate ids: ptxas reserves only the barriers named
+    if (grp == 0)
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+    else
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+}
+
+// 256 threads = two independent 128-thread pipelines ("groups").  Group g owns key tiles t = g, g+2, ...,
+// one operand buffer, one 128-column accumulator in TMEM, one mbarrier and one named barrier; both share the
+// Q operand and the row statistics.  Per tile a group: waits for its MMA, starts the cp.async of its next
+// tile straight into the canonical layout (no registers), does the softmax math on the accumulator while
+// those copies fly, then hands the staged tile to the tensor core.  The other group (and the second resident
+// CTA) keep the SM busy meanwhile.
 template <int DT, int CPR>
-__global__ void __launch_bounds__(128, 2) kvc_snapkv_vote_kernel(const __grid_constant__ VoteBatchDev bd) {
+__global__ void __launch_bounds__(256, 2) kvc_snapkv_vote_kernel(const __grid_constant__ VoteBatchDev bd) {
     using Tr = Traits<DT>;
     using Key = typename Tr::Key;
     static_assert(DT != KVC_DTYPE_F32, "the vote runs on 16-bit caches (kind::f16)");
-    constexpr int TILE_BYTES = (kVoteTile / 8) * CPR * kVoteLBO;  // padded canonical layout
-    constexpr int CH = kVoteTile * CPR / 128;  // 16-byte chunks per thread per tile
+    constexpr int TILE_BYTES = (kVoteTile / 8) * CPR * kVoteLBO;
+    constexpr int CH = kVoteTile * CPR / 128;                     // 16-byte chunks per thread per tile
     constexpr uint32_t IDESC = umma_idesc_f16(DT == KVC_DTYPE_BF16 ? 1 : 0, kVoteM, kVoteTile);
 
     const VoteLayerDev& L = bd.layers[blockIdx.y];
     const int bh = blockIdx.x;
     const int b = bh / bd.H, h = bh - b * bd.H;
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int grp = tid >> 7, gt = tid & 127;  // group and thread-in-group (= TMEM lane)
     const int S = L.S, W = bd.W, G = bd.G;
     const int P = S - W;
     const int rows_q = G * W;
 
     extern __shared__ __align__(128) unsigned char smem[];
-    // [0,256): scalars + 2 mbarriers; then row statistics; then Q and two K-tile buffers
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem);
-    const uint32_t bar0 = smem_u32(smem + 16);
-    float* s_m = reinterpret_cast<float*>(smem + 256);        // [128] row max (log2 domain)
-    float* s_invl = reinterpret_cast<float*>(smem + 256 + 512);  // [128] 1 / row sum (0 for padding rows)
-    unsigned char* s_q = smem + 1280;
-    unsigned char* s_k = s_q + TILE_BYTES;  // two buffers of TILE_BYTES
+    const uint32_t bar = smem_u32(smem + 16) + grp * 8;
+    float* s_m = reinterpret_cast<float*>(smem + 256);            // [128] row max (log2 domain)
+    float* s_invl = reinterpret_cast<float*>(smem + 256 + 512);   // [128] 1 / row sum (0 for padding rows)
+    float* s_part = reinterpret_cast<float*>(smem + 256 + 1024);  // [2][128] group 1's partial (m, l)
+    unsigned char* s_q = smem + 2304;
+    unsigned char* s_k = s_q + TILE_BYTES + grp * TILE_BYTES;     // this group's operand buffer
 
     if (warp == 0) tmem_alloc(smem_u32(s_tmem), 256);
-    if (tid == 0) {
-        mbar_init(bar0, 1);
-        mbar_init(bar0 + 8, 1);
+    if (gt == 0) {
+        mbar_init(bar, 1);
         mbar_init_fence();
     }
     // ---------------------------------------------------------------- Q operand (once per unit)
     const char* kbase = L.k + (int64_t)b * L.ksb + (int64_t)h * L.ksh;
-    for (int q = tid; q < kVoteM * CPR; q += 128) {
-        const int r = q / CPR, c = q - r * CPR;
+    for (int q = tid; q < kVoteM * CPR; q += 256) {
+        int r, c;
+        tile_item<CPR>(q, r, c);
         int4 v = make_int4(0, 0, 0, 0);
         if (r < rows_q) {
             const int g = r / W, w = r - g * W;
@@ -158,144 +188,156 @@ __global__ void __launch_bounds__(128, 2) kvc_snapkv_vote_kernel(const __grid_co
         }
         *reinterpret_cast<int4*>(s_q + umma_off<CPR>(r, c)) = v;
     }
-    // tile loader: thread owns CH chunks; chunk index q -> (row, chunk), diagonal order keeps STS conflict-free
-    auto load_tile = [&](int t, int4 (&reg)[CH]) {
+    const uint32_t k_addr = smem_u32(s_k), q_addr = smem_u32(s_q);
+    // stage key tile t into this group's buffer (cp.async, 16 bytes per copy, CPR copies per thread).
+    // The row stride is pinned in a register: re-reading it from the parameter bank inside the loop put a
+    // long-scoreboard stall on every address (profiles/r01_vote_*).
+    int64_t kss = L.kss;
+    asm volatile("" : "+l"(kss));
+    auto stage_tile = [&](int t) {
         const int r0 = t * kVoteTile;
+        const char* tile = kbase + (int64_t)r0 * kss;
 #pragma unroll
         for (int i = 0; i < CH; ++i) {
-            const int q = i * 128 + tid;
-            const int r = q / CPR, c = q - r * CPR;
-            reg[i] = (r0 + r < S) ? ldg128_stream(kbase + (int64_t)(r0 + r) * L.kss + c * 16) : make_int4(0, 0, 0, 0);
+            int r, c;
+            tile_item<CPR>(i * 128 + gt, r, c);
+            const bool ok = r0 + r < S;
+            cp_async16(k_addr + umma_off<CPR>(r, c), ok ? tile + r * kss + c * 16 : kbase, ok);
         }
     };
-    auto store_tile = [&](int buf, const int4 (&reg)[CH]) {
-        unsigned char* dst = s_k + buf * TILE_BYTES;
-#pragma unroll
-        for (int i = 0; i < CH; ++i) {
-            const int q = i * 128 + tid;
-            const int r = q / CPR, c = q - r * CPR;
-            *reinterpret_cast<int4*>(dst + umma_off<CPR>(r, c)) = reg[i];
-        }
-    };
+    fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *s_tmem;
-    const uint32_t q_addr = smem_u32(s_q), k_addr = smem_u32(s_k);
+    const uint32_t tmem = *s_tmem + grp * kVoteTile;                 // this group's accumulator columns
+    const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);  // this warp's 32 TMEM lanes
 
-    // issue the CPR/2 K-steps of one 128x128xD product: pass 1 (A = Q, B = K tile) or pass 2 (A = K tile, B = Q)
-    auto issue = [&](int buf, bool keys_are_rows) {
-        const uint32_t a0 = keys_are_rows ? k_addr + buf * TILE_BYTES : q_addr;
-        const uint32_t b0 = keys_are_rows ? q_addr : k_addr + buf * TILE_BYTES;
+    // the CPR/2 K-steps of one 128x128xD product: pass 1 (A = Q, B = K tile) or pass 2 (A = K tile, B = Q)
+    auto issue = [&](bool keys_are_rows) {
+        const uint32_t a0 = keys_are_rows ? k_addr : q_addr;
+        const uint32_t b0 = keys_are_rows ? q_addr : k_addr;
 #pragma unroll
         for (int ks = 0; ks < CPR / 2; ++ks) {
             const uint64_t ad = umma_smem_desc(a0 + ks * 2 * kVoteLBO, kVoteLBO, CPR * kVoteLBO);
             const uint64_t bdsc = umma_smem_desc(b0 + ks * 2 * kVoteLBO, kVoteLBO, CPR * kVoteLBO);
-            umma_f16(tmem + buf * kVoteTile, ad, bdsc, IDESC, ks > 0 ? 1u : 0u);
+            umma_f16(tmem, ad, bdsc, IDESC, ks > 0 ? 1u : 0u);
         }
-        umma_commit(bar0 + buf * 8);
+        umma_commit(bar);
     };
 
     const float c2 = bd.scale_log2e;
-    const int lane_row = tid;  // TMEM lane owned by this thread (warp w reads lanes 32w..32w+31)
-    const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
-    uint32_t phase[2] = {0, 0};
-
+    uint32_t phase = 0;
     for (int pass = 0; pass < 2; ++pass) {
         const bool keys_are_rows = pass == 1;
         const int n_tiles = keys_are_rows ? (P + kVoteTile - 1) / kVoteTile : (S + kVoteTile - 1) / kVoteTile;
-        float m_run = -INFINITY, l_run = 0.f;  // pass 1 state of query row `lane_row`
-        int4 reg[CH];
-        // prologue: tiles 0 and 1 staged, MMA(0) and MMA(1) in flight
-        for (int t = 0; t < 2 && t < n_tiles; ++t) {
-            load_tile(t, reg);
-            store_tile(t, reg);
+        float m_run = -INFINITY, l_run = 0.f;  // pass 1: this group's share of query row `gt`
+        if (grp < n_tiles) {
+            stage_tile(grp);
+            cp_async_wait_all();
+            fence_proxy_async_smem();
         }
-        fence_proxy_async_smem();
-        __syncthreads();
-        if (tid == 0) {
+        group_barrier(grp);
+        if (gt == 0 && grp < n_tiles) {
             tc_fence_after();
-            for (int t = 0; t < 2 && t < n_tiles; ++t) issue(t, keys_are_rows);
+            issue(keys_are_rows);
         }
-        for (int t = 0; t < n_tiles; ++t) {
-            const int buf = t & 1;
+        for (int t = grp; t < n_tiles; t += 2) {
             const bool more = t + 2 < n_tiles;
-            if (more) load_tile(t + 2, reg);  // global loads in flight across the math below
-            mbar_wait(bar0 + buf * 8, phase[buf]);
-            phase[buf] ^= 1;
+            mbar_wait(bar, phase);
+            phase ^= 1;
             tc_fence_after();
+            if (more) stage_tile(t + 2);  // the operand buffer is free: copies fly under the math below
             const int key0 = t * kVoteTile;
+            uint32_t v[32];
             if (!keys_are_rows) {
-                // ---------------- pass 1: row = query, columns = keys of this tile
-                const int w_pos = (lane_row < rows_q) ? (lane_row % W) : 0;
-                const int limit = P + w_pos;  // last key this query may attend (causal inside the window)
-                uint32_t v[32];
-                // online softmax statistics, 32 columns at a time
+                // ---------------- pass 1: lane = query row, columns = keys of this tile (online softmax statistics)
+                const int limit = P + ((gt < rows_q) ? (gt % W) : 0);  // causal inside the window
+                const bool masked = key0 + kVoteTile > P;               // only the last tiles meet the mask / S
 #pragma unroll 1
                 for (int cb = 0; cb < kVoteTile; cb += 32) {
-                    tmem_ld32(t_lane + buf * kVoteTile + cb, v);
+                    tmem_ld32(t_lane + cb, v);
                     float cmax = -INFINITY;
+                    if (masked) {
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const int key = key0 + cb + j;
-                        const float s = (key <= limit && key < S) ? __uint_as_float(v[j]) * c2 : -INFINITY;
-                        v[j] = __float_as_uint(s);
-                        cmax = fmaxf(cmax, s);
+                        for (int j = 0; j < 32; ++j) {
+                            const int key = key0 + cb + j;
+                            if (key > limit || key >= S) v[j] = 0xff800000u;  // -inf
+                            cmax = fmaxf(cmax, __uint_as_float(v[j]));
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) cmax = fmaxf(cmax, __uint_as_float(v[j]));
                     }
-                    const float m_new = fmaxf(m_run, cmax);
+                    const float m_new = fmaxf(m_run, cmax * c2);
                     if (m_new > -INFINITY) {
-                        float acc = 0.f;
+                        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) acc += ex2(__uint_as_float(v[j]) - m_new);
-                        l_run = l_run * ex2(m_run - m_new) + acc;
+                        for (int j = 0; j < 32; j += 4) {
+                            acc0 += ex2(fmaf(__uint_as_float(v[j]), c2, -m_new));
+                            acc1 += ex2(fmaf(__uint_as_float(v[j + 1]), c2, -m_new));
+                            acc2 += ex2(fmaf(__uint_as_float(v[j + 2]), c2, -m_new));
+                            acc3 += ex2(fmaf(__uint_as_float(v[j + 3]), c2, -m_new));
+                        }
+                        l_run = fmaf(l_run, ex2(m_run - m_new), (acc0 + acc1) + (acc2 + acc3));
                         m_run = m_new;
                     }
                 }
             } else {
-                // ---------------- pass 2: row = key, columns = query rows
-                float vote = 0.f;
-                uint32_t v[32];
+                // ---------------- pass 2: lane = key, columns = query rows
+                float vote0 = 0.f, vote1 = 0.f, vote2 = 0.f, vote3 = 0.f;
 #pragma unroll 1
                 for (int cb = 0; cb < kVoteM; cb += 32) {
-                    tmem_ld32(t_lane + buf * kVoteTile + cb, v);
+                    tmem_ld32(t_lane + cb, v);
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         const float4 mm = *reinterpret_cast<const float4*>(s_m + cb + j);
                         const float4 il = *reinterpret_cast<const float4*>(s_invl + cb + j);
-                        vote = fmaf(ex2(fmaf(__uint_as_float(v[j + 0]), c2, -mm.x)), il.x, vote);
-                        vote = fmaf(ex2(fmaf(__uint_as_float(v[j + 1]), c2, -mm.y)), il.y, vote);
-                        vote = fmaf(ex2(fmaf(__uint_as_float(v[j + 2]), c2, -mm.z)), il.z, vote);
-                        vote = fmaf(ex2(fmaf(__uint_as_float(v[j + 3]), c2, -mm.w)), il.w, vote);
+                        vote0 = fmaf(ex2(fmaf(__uint_as_float(v[j + 0]), c2, -mm.x)), il.x, vote0);
+                        vote1 = fmaf(ex2(fmaf(__uint_as_float(v[j + 1]), c2, -mm.y)), il.y, vote1);
+                        vote2 = fmaf(ex2(fmaf(__uint_as_float(v[j + 2]), c2, -mm.z)), il.z, vote2);
+                        vote3 = fmaf(ex2(fmaf(__uint_as_float(v[j + 3]), c2, -mm.w)), il.w, vote3);
                     }
                 }
-                const int key = key0 + lane_row;
+                const int key = key0 + gt;
                 if (key < P) {
                     Key* out = reinterpret_cast<Key*>(L.votes) + (int64_t)bh * P;
-                    out[key] = (Key)Tr::to_raw(vote);
+                    out[key] = (Key)Tr::to_raw((vote0 + vote1) + (vote2 + vote3));
                 }
             }
-            // the accumulator and the operand buffer of tile t are free again: stage tile t+2 and issue it
+            // accumulator read out, next tile staged: hand it to the tensor core
             tc_fence_before();
             if (more) {
-                store_tile(buf, reg);
+                cp_async_wait_all();
                 fence_proxy_async_smem();
             }
-            __syncthreads();
-            if (more && tid == 0) {
+            group_barrier(grp);
+            if (more && gt == 0) {
                 tc_fence_after();
-                issue(buf, keys_are_rows);
+                issue(keys_are_rows);
             }
         }
         if (!keys_are_rows) {
-            // publish the row statistics; padding rows (>= G*W) never vote
-            s_m[lane_row] = (lane_row < rows_q && l_run > 0.f) ? m_run : 0.f;
-            s_invl[lane_row] = (lane_row < rows_q && l_run > 0.f) ? 1.f / l_run : 0.f;
+            // merge the two groups' partial statistics of each query row; padding rows (>= G*W) never vote
+            if (grp == 1) {
+                s_part[gt] = m_run;
+                s_part[128 + gt] = l_run;
+            }
+            __syncthreads();
+            if (grp == 0) {
+                const float m1 = s_part[gt], l1 = s_part[128 + gt];
+                const float m = fmaxf(m_run, m1);
+                float l = 0.f;
+                if (m > -INFINITY) l = l_run * ex2(m_run - m) + l1 * ex2(m1 - m);
+                const bool live = gt < rows_q && l > 0.f;
+                s_m[gt] = live ? m : 0.f;
+                s_invl[gt] = live ? 1.f / l : 0.f;
+            }
             __syncthreads();
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 256);
+    if (warp == 0) tmem_dealloc(*s_tmem, 256);
 }
 
 }  // namespace kvc
