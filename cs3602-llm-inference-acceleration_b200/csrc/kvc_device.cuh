@@ -59,6 +59,10 @@ struct BatchDev {
     int32_t nsw;       // TMA form: warps that own a staging slot (<= warps per CTA)
     int32_t off_hist, off_idx, off_keys, off_stage;  // TMA form: shared-memory layout (bytes)
     int32_t upc;       // TMA form: consecutive (batch, head) units walked by one CTA
+    // optional device workspace for selections that do not fit on chip: per unit, radix keys then kept indices
+    char* ws;
+    int64_t ws_unit;   // bytes per (layer, batch, head) unit
+    int64_t ws_keys;   // bytes of the key part of a unit
     LayerDev layers[KVC_MAX_LAYERS_PER_LAUNCH];
 };
 

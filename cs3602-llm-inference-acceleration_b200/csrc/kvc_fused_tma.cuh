@@ -114,6 +114,11 @@ __global__ void __launch_bounds__(NT, MINB) kvc_fused_tma_kernel(const __grid_co
     const int bh_end = min(n_units, ((int)blockIdx.x + 1) * bd.upc);
     for (int bh = (int)blockIdx.x * bd.upc; bh < bh_end; ++bh) {
     const int b = bh / bd.H, h = bh - b * bd.H;
+    if (bd.ws != nullptr) {  // selection too large for shared memory: keys / kept indices live in the workspace
+        char* unit = bd.ws + ((int64_t)blockIdx.y * n_units + bh) * bd.ws_unit;
+        keys = reinterpret_cast<Key*>(unit);
+        sidx = reinterpret_cast<int32_t*>(unit + bd.ws_keys);
+    }
     const char* kbase = L.k_in + (int64_t)b * L.ksb + (int64_t)h * L.ksh;
     const char* vbase = L.v_in + (int64_t)b * L.vsb + (int64_t)h * L.vsh;
     const char* kreg = kbase + (int64_t)L.lo * L.kss;

@@ -35,6 +35,8 @@ struct SlabBatchDev {
     int32_t B, H;
     int32_t idx_cap, nsw;
     int32_t off_hist, off_idx, off_keys, off_stage;
+    char* ws;  // optional workspace (see BatchDev)
+    int64_t ws_unit, ws_keys;
     SlabLayerDev layers[KVC_MAX_LAYERS_PER_LAUNCH];
 };
 
@@ -125,6 +127,11 @@ __global__ void __launch_bounds__(NT, MINB) kvc_slab_compress_kernel(const __gri
     uint32_t* hist = reinterpret_cast<uint32_t*>(smem + bd.off_hist);
     int32_t* sidx = reinterpret_cast<int32_t*>(smem + bd.off_idx);
     Key* keys = reinterpret_cast<Key*>(smem + bd.off_keys);
+    if (bd.ws != nullptr) {
+        char* unit = bd.ws + ((int64_t)blockIdx.y * gridDim.x + bh) * bd.ws_unit;
+        keys = reinterpret_cast<Key*>(unit);
+        sidx = reinterpret_cast<int32_t*>(unit + bd.ws_keys);
+    }
     const int nsw = bd.nsw;
     const bool stager = warp < nsw;
     const uint32_t slot = smem_u32(smem + bd.off_stage) + (uint32_t)warp * (32 * RB);

@@ -396,6 +396,24 @@ static TmaPlan plan_tma(int dtype, int cpr, int max_region, int idx_cap, bool an
     return best;
 }
 
+// Keys + kept indices of one (layer, batch, head) unit when they live in the device workspace.
+struct WsLayout {
+    int64_t keys = 0, unit = 0;
+};
+static WsLayout ws_layout(int dtype, int max_region, int idx_cap) {
+    WsLayout w;
+    w.keys = ((int64_t)max_region * key_bytes(dtype) + 15) & ~(int64_t)15;
+    w.unit = w.keys + (((int64_t)idx_cap * 4 + 15) & ~(int64_t)15);
+    return w;
+}
+// The on-chip plan is good enough when it exists and keeps >= 48 KB of rows in flight per SM (scan kernels)
+// or has at least two slots (in-place compaction, whose traffic is light).
+static bool onchip_plan_ok(const TmaPlan& tp, int cpr, bool light_traffic) {
+    if (!tp.ok) return false;
+    if (light_traffic) return tp.nsw >= 2;
+    return (long)tp.ctas * tp.nsw * 32 * cpr * 16 >= 48 * 1024;
+}
+
 template <int DT, int NT, int MINB>
 static FusedFn pick_tma_cpr(int cpr) {
     switch (cpr) {
@@ -534,6 +552,47 @@ int32_t kvc_max_region_rows(int32_t dtype, int32_t k_sel) {
 
 int kvc_compress_layers(const kvc_shape* shape, int32_t n_layers, const kvc_layer_plan* plans,
                         const kvc_layer_io* io, void* stream) {
+    return kvc_compress_layers_ws(shape, n_layers, plans, io, nullptr, 0, stream);
+}
+
+// Launch-chunk statistics shared by kvc_workspace_bytes and the launchers.
+static void chunk_stats(const kvc_layer_plan* plans, int nl, int* n_active, int* max_region, int* max_ksel,
+                        bool* any_select) {
+    *n_active = *max_region = *max_ksel = 0;
+    *any_select = false;
+    for (int l = 0; l < nl; ++l) {
+        const kvc_layer_plan& p = plans[l];
+        if (p.sink + p.k_sel + p.tail == 0) continue;
+        ++*n_active;
+        if (p.k_sel > 0) {
+            *any_select = true;
+            if (p.k_sel > *max_ksel) *max_ksel = p.k_sel;
+            if (p.score != KVC_SCORE_GIVEN_INDEX && p.sel_hi - p.sel_lo > *max_region) *max_region = p.sel_hi - p.sel_lo;
+        }
+    }
+}
+
+int64_t kvc_workspace_bytes(const kvc_shape* shape, int32_t n_layers, const kvc_layer_plan* plans) {
+    int cpr = 0;
+    if (check_shape(shape, &cpr) != KVC_OK || n_layers <= 0 || !plans || !tma_supported_cpr(cpr)) return 0;
+    int64_t need = 0;
+    for (int l0 = 0; l0 < n_layers; l0 += KVC_MAX_LAYERS_PER_LAUNCH) {
+        const int nl = (n_layers - l0) < KVC_MAX_LAYERS_PER_LAUNCH ? (n_layers - l0) : KVC_MAX_LAYERS_PER_LAUNCH;
+        int n_active, max_region, max_ksel;
+        bool any_select;
+        chunk_stats(plans + l0, nl, &n_active, &max_region, &max_ksel, &any_select);
+        if (!any_select) continue;
+        const int idx_cap = (max_ksel + 3) & ~3;
+        const TmaPlan tp = plan_tma(shape->dtype, cpr, max_region, idx_cap, true);
+        if (onchip_plan_ok(tp, cpr, false)) continue;
+        const int64_t bytes = ws_layout(shape->dtype, max_region, idx_cap).unit * shape->batch * shape->heads * n_active;
+        if (bytes > need) need = bytes;
+    }
+    return need;
+}
+
+int kvc_compress_layers_ws(const kvc_shape* shape, int32_t n_layers, const kvc_layer_plan* plans,
+                           const kvc_layer_io* io, void* workspace, int64_t workspace_bytes, void* stream) {
     if (!shape || n_layers < 0 || (n_layers > 0 && (!plans || !io))) return KVC_ERR_INVALID_ARG;
     if (n_layers == 0) return KVC_OK;
     const int B = shape->batch, H = shape->heads, D = shape->head_dim, dt = shape->dtype;
@@ -622,8 +681,18 @@ int kvc_compress_layers(const kvc_shape* shape, int32_t n_layers, const kvc_laye
         TmaPlan tp;
         bool given_score = false;
         for (int l = 0; l < nl; ++l) given_score |= plans[l0 + l].k_sel > 0 && plans[l0 + l].score == KVC_SCORE_GIVEN_SCORE;
-        if (tma_supported_cpr(cpr) && (given_score || !env_int("KVC_FORCE_LDG", 0)))
+        if (tma_supported_cpr(cpr) && (given_score || !env_int("KVC_FORCE_LDG", 0))) {
             tp = plan_tma(dt, cpr, max_region, bd.idx_cap, any_select);
+            if (any_select && workspace != nullptr && !onchip_plan_ok(tp, cpr, false)) {
+                // keys and kept indices go to the workspace; shared memory keeps the histogram and the slots
+                const WsLayout w = ws_layout(dt, max_region, bd.idx_cap);
+                if (w.unit * B * H * n_active > workspace_bytes) return KVC_ERR_INVALID_ARG;
+                bd.ws = (char*)workspace;
+                bd.ws_unit = w.unit;
+                bd.ws_keys = w.keys;
+                tp = plan_tma(dt, cpr, 0, 0, true);
+            }
+        }
         if (given_score && !tp.ok) return KVC_ERR_TOO_LARGE;
         if (tp.ok) {
             // bulk-copy form: rows are staged through shared memory by the TMA unit
@@ -810,7 +879,7 @@ int kvc_slab_append(const kvc_shape* shape, int32_t n_layers, const kvc_slab_lay
 
 int kvc_slab_compress(const kvc_shape* shape, int32_t n_layers, const kvc_layer_plan* plans,
                       const kvc_slab_layer* slabs, int32_t* const* idx_out, const int32_t* const* idx_in,
-                      void* stream) {
+                      void* workspace, int64_t workspace_bytes, void* stream) {
     int cpr = 0;
     int st = check_shape(shape, &cpr);
     if (st != KVC_OK) return st;
@@ -879,7 +948,15 @@ int kvc_slab_compress(const kvc_shape* shape, int32_t n_layers, const kvc_layer_
         }
         if (n_active == 0) continue;
         bd.idx_cap = (max_ksel + 3) & ~3;
-        const TmaPlan tp = plan_tma(dt, cpr, max_region, bd.idx_cap, any_select, /*light_traffic=*/true);
+        TmaPlan tp = plan_tma(dt, cpr, max_region, bd.idx_cap, any_select, /*light_traffic=*/true);
+        if (any_select && workspace != nullptr && !onchip_plan_ok(tp, cpr, true)) {
+            const WsLayout w = ws_layout(dt, max_region, bd.idx_cap);
+            if (w.unit * B * H * n_active > workspace_bytes) return KVC_ERR_INVALID_ARG;
+            bd.ws = (char*)workspace;
+            bd.ws_unit = w.unit;
+            bd.ws_keys = w.keys;
+            tp = plan_tma(dt, cpr, 0, 0, true, /*light_traffic=*/true);
+        }
         if (!tp.ok) return KVC_ERR_TOO_LARGE;
         SlabFn fn = pick_slab(dt, cpr, tp.nt);
         bd.nsw = tp.nsw;

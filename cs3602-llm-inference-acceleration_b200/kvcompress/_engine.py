@@ -30,13 +30,14 @@ _PLAN = struct.Struct("8i")        # kvc_layer_plan: seq_len sink sel_lo sel_hi 
 _IO = struct.Struct("4P6q3P")      # kvc_layer_io: k_in v_in k_out v_out | 6 strides | idx_out idx_in score_in
 _SHAPE = struct.Struct("5i")       # kvc_shape: batch heads head_dim dtype device
 assert _PLAN.size == 32 and _IO.size == 104 and _SHAPE.size == 20
-KVC_ABI_VERSION = 2
+KVC_ABI_VERSION = 3
 
 KVC_DTYPE = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
 KVC_OK = 0
 _STATUS_EXC = {1: ValueError, 2: ValueError, 3: ValueError, 4: RuntimeError}
 
 _lib = None
+_WS_NEED = {}  # (plan set, group) -> workspace bytes the launch needs (0: everything fits on chip)
 
 
 def library_path() -> str:
@@ -75,7 +76,13 @@ def load_library():
     lib.kvc_slab_append.argtypes = [ctypes.c_char_p, ctypes.c_int32, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_void_p]
     lib.kvc_slab_compress.restype = ctypes.c_int
     lib.kvc_slab_compress.argtypes = [ctypes.c_char_p, ctypes.c_int32, ctypes.c_char_p, ctypes.c_char_p,
-                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                      ctypes.c_void_p]
+    lib.kvc_workspace_bytes.restype = ctypes.c_int64
+    lib.kvc_workspace_bytes.argtypes = [ctypes.c_char_p, ctypes.c_int32, ctypes.c_char_p]
+    lib.kvc_compress_layers_ws.restype = ctypes.c_int
+    lib.kvc_compress_layers_ws.argtypes = [ctypes.c_char_p, ctypes.c_int32, ctypes.c_char_p, ctypes.c_char_p,
+                                           ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
     lib.kvc_snapkv_vote.restype = ctypes.c_int
     lib.kvc_snapkv_vote.argtypes = [ctypes.c_char_p, ctypes.c_int32, ctypes.c_char_p, ctypes.c_int32, ctypes.c_int32,
                                     ctypes.c_void_p]
@@ -271,8 +278,21 @@ def run_plans(kv: Sequence[Tuple[torch.Tensor, torch.Tensor]], plans, given_indi
                           ks[0], ks[1], ks[2], vs[0], vs[1], vs[2], idx_out_ptr, idx_in_ptr, score_in_ptr)
         dev_index = run_device.index if run_device.index is not None else torch.cuda.current_device()
         shape_rec = _SHAPE.pack(B, H, D, KVC_DTYPE[dtype], dev_index)
-        status = lib.kvc_compress_layers(shape_rec, n, bytes(plan_buf), bytes(io_buf),
-                                         ctypes.c_void_p(_stream_ptr(run_device)))
+        plan_bytes = bytes(plan_buf)
+        ws_key = (id(ps), B, H, D, dtype, tuple(li for li, _, _ in members))
+        need = _WS_NEED.get(ws_key)
+        if need is None or need[0] is not ps:
+            need = (ps, int(lib.kvc_workspace_bytes(shape_rec, n, plan_bytes)))
+            if len(_WS_NEED) > 256:
+                _WS_NEED.clear()
+            _WS_NEED[ws_key] = need
+        ws_ptr, ws_bytes = None, 0
+        if need[1] > 0:  # selection larger than shared memory: radix keys / kept indices in a device workspace
+            ws = torch.empty((need[1],), dtype=torch.uint8, device=run_device)
+            keepalive.append(ws)
+            ws_ptr, ws_bytes = ctypes.c_void_p(ws.data_ptr()), need[1]
+        status = lib.kvc_compress_layers_ws(shape_rec, n, plan_bytes, bytes(io_buf), ws_ptr, ws_bytes,
+                                            ctypes.c_void_p(_stream_ptr(run_device)))
         _check(status, "kvc_compress_layers")
         if on_host:
             # host tensors are read by the caller with plain loads: finish before returning,

@@ -101,6 +101,7 @@ class KVSlabCache:
         self._k_layers = list(self.k.unbind(0))
         self._v_layers = list(self.v.unbind(0))
         self._lib = None
+        self._ws = None
         self._launch_cache: Dict[int, tuple] = {}
 
     # ------------------------------------------------------------------ construction / views
@@ -319,12 +320,13 @@ class KVSlabCache:
             plan_buf = b"".join(_engine._PLAN.pack(p.seq_len, p.sink, p.sel_lo, p.sel_hi, p.k_sel, p.tail, p.score,
                                                    p.pool_kernel) for p in (moved[i] for i in ids))
             slab_buf = b"".join(self._recs[i] for i in ids)
+            ws_need = int(_engine.load_library().kvc_workspace_bytes(self._shape, len(ids), plan_buf)) if ids else 0
             entry = (ps, ids, plan_buf, slab_buf, [moved[i].out_len for i in ids],
-                     [moved[i].seq_len for i in ids])
+                     [moved[i].seq_len for i in ids], ws_need)
             if len(self._launch_cache) > 64:
                 self._launch_cache.clear()
             self._launch_cache[id(ps)] = entry
-        _, ids, plan_buf, slab_buf, out_lens, in_lens = entry
+        _, ids, plan_buf, slab_buf, out_lens, in_lens, ws_need = entry
         indices = {}
         if not ids:
             return (self, indices) if return_indices else self
@@ -351,7 +353,12 @@ class KVSlabCache:
                     ptrs[m] = gi.data_ptr()
             idx_in = ptrs
         lib = _engine.load_library()
-        status = lib.kvc_slab_compress(self._shape, len(ids), plan_buf, slab_buf, idx_out, idx_in,
+        ws_ptr = None
+        if ws_need > 0:  # selection larger than shared memory (see kvc_workspace_bytes)
+            if self._ws is None or self._ws.numel() < ws_need:
+                self._ws = torch.empty((ws_need,), dtype=torch.uint8, device=self.device)
+            ws_ptr = ctypes.c_void_p(self._ws.data_ptr())
+        status = lib.kvc_slab_compress(self._shape, len(ids), plan_buf, slab_buf, idx_out, idx_in, ws_ptr, ws_need,
                                        ctypes.c_void_p(_engine._stream_ptr(self.device)))
         _engine._check(status, "kvc_slab_compress")
         for i, c in zip(ids, out_lens):

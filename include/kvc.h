@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define KVC_ABI_VERSION 2
+#define KVC_ABI_VERSION 3
 
 typedef enum kvc_status {
     KVC_OK = 0,
@@ -117,6 +117,16 @@ int32_t kvc_max_region_rows(int32_t dtype, int32_t k_sel);
 int kvc_compress_layers(const kvc_shape* shape, int32_t n_layers, const kvc_layer_plan* plans,
                         const kvc_layer_io* io, void* stream);
 
+/* Selections too large for shared memory (radix keys of the region + kept indices: e.g. l2_compress with
+ * keep_ratio 0.8 at 32K fp32 rows, or any region beyond kvc_max_region_rows) keep those two arrays in a
+ * caller-provided device workspace instead (they stay L2-resident: 2-4 B per row against D*e for the scan).
+ * kvc_workspace_bytes: bytes kvc_compress_layers_ws / kvc_slab_compress need for these plans, 0 if everything
+ * fits on chip.  kvc_compress_layers(...) == kvc_compress_layers_ws(..., NULL, 0, ...), which reports
+ * KVC_ERR_TOO_LARGE when a workspace would have been needed. */
+int64_t kvc_workspace_bytes(const kvc_shape* shape, int32_t n_layers, const kvc_layer_plan* plans);
+int kvc_compress_layers_ws(const kvc_shape* shape, int32_t n_layers, const kvc_layer_plan* plans,
+                           const kvc_layer_io* io, void* workspace, int64_t workspace_bytes, void* stream);
+
 /* norms[b,h,r] = dtype( sqrt( sum_d fp32(K[b,h,row_lo+r,d])^2 ) ), r in [0,row_hi-row_lo);
  * fp32 accumulation, result rounded once to the input dtype (torch.norm semantics). */
 int kvc_key_norms(const kvc_shape* shape, const void* k_in, int64_t stride_b, int64_t stride_h,
@@ -190,7 +200,7 @@ int kvc_slab_append(const kvc_shape* shape, int32_t n_layers, const kvc_slab_lay
  * idx_out[l] (optional, may be NULL / hold NULLs): [B,H,C] kept absolute rows; idx_in[l]: GIVEN_INDEX rows. */
 int kvc_slab_compress(const kvc_shape* shape, int32_t n_layers, const kvc_layer_plan* plans,
                       const kvc_slab_layer* slabs, int32_t* const* idx_out, const int32_t* const* idx_in,
-                      void* stream);
+                      void* workspace, int64_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -402,3 +402,40 @@ def test_oracle_parity_at_product_row_widths(name, method, kwargs, dtype, D, sty
             assert info["identical_heads"] == info["heads"], (case["name"], li, info)
         else:
             assert info["identical_heads"] >= 0.5 * info["heads"], (case["name"], li, info)  # validity is the rule; rounding-boundary flips are rare
+
+
+# ----------------------------------------------------------------------------------------------
+# Selections larger than shared memory: radix keys / kept indices fall back to a device workspace
+BIG = [
+    ("l2_08_32k_f32", "l2_compress", dict(keep_ratio=0.8, prune_after=100, skip_layers=[]), 2, 1, 2, 32768, 64, torch.float32),
+    ("l2_05_64k_bf16", "l2_compress", dict(keep_ratio=0.5, prune_after=100, skip_layers=[]), 1, 1, 2, 65536, 128, torch.bfloat16),
+    ("h2o_120k_bf16", "h2o_l2", dict(start_size=4, heavy_hitter_size=64, recent_size=444), 1, 1, 2, 122880, 128, torch.bfloat16),
+    ("h2o_70k_f32", "h2o_l2", dict(start_size=4, heavy_hitter_size=64, recent_size=444), 1, 1, 2, 70000, 32, torch.float32),
+    ("snapkv_120k_bf16", "snapkv_lite", dict(observation_window=32, keep_size=512), 1, 1, 1, 122880, 80, torch.bfloat16),
+]
+
+
+@pytest.mark.parametrize("name,method,kwargs,L,B,H,S,D,dtype", BIG, ids=[b[0] for b in BIG])
+def test_selections_beyond_shared_memory_use_the_workspace(name, method, kwargs, L, B, H, S, D, dtype):
+    kv = spread_cache(L, B, H, S, D, dtype)
+    plans = plan_for(method, [S] * L, kwargs)
+    lib = _engine.load_library()
+    shape = _engine._SHAPE.pack(B, H, D, _engine.KVC_DTYPE[dtype], 0)
+    packed = b"".join(_engine.PlanSet(plans).packed[i] for i in range(L))
+    assert lib.kvc_workspace_bytes(shape, L, packed) > 0, "this case is meant to exceed the on-chip buffers"
+    out, idx = _engine.run_plans(kv, plans, return_indices=True)
+    api = kvcompress.get_compress_fn(method)(kv, **kwargs)
+    for li, p in enumerate(plans):
+        rows = idx[li]
+        k_in, v_in = kv[li]
+        assert torch.equal(out[li][0], gather_rows(k_in, rows)) and torch.equal(out[li][1], gather_rows(v_in, rows))
+        assert torch.equal(api[li][0], out[li][0])
+        sel = rows[..., p.sink:p.sink + p.k_sel] - p.sel_lo
+        assert sel.min() >= 0 and sel.max() < p.sel_hi - p.sel_lo
+        if method != "snapkv_lite":
+            assert_valid_lowest(k_in[:, :, p.sel_lo:p.sel_hi], sel)
+    # the in-place path takes the same fallback and keeps the same rows
+    slab = kvcompress.KVSlabCache.from_legacy_cache(kv, capacity=S)
+    slab.compress_(method, **kwargs)
+    for li in range(L):
+        assert torch.equal(slab[li][0], out[li][0]) and torch.equal(slab[li][1], out[li][1])
