@@ -202,8 +202,17 @@ class KVSlabCache:
         slab_buf = bytearray(_SLAB.size * len(items))
         rows_buf = bytearray(_ROWS.size * len(items))
         keep = []
+        dt, dev, want = self.dtype, self.device, None
         for m, (l, keys, values) in enumerate(items):
-            self._check_new(keys, values, l)
+            shape = keys.shape
+            if want is None:
+                want = (self.batch, self.heads, shape[2], self.head_dim) if len(shape) == 4 else None
+            # one cheap comparison per tensor on the decode path; the detailed diagnosis only when it fails
+            if not (keys.is_cuda and keys.dtype is dt and values.dtype is dt and keys.device == dev
+                    and values.device == dev and tuple(shape) == want and values.shape == shape
+                    and self.lengths[l] + shape[2] <= self.capacity):
+                self._check_new(keys, values, l)
+                want = None
             if not _engine._rows_ok(keys):
                 keys = keys.contiguous()
             if not _engine._rows_ok(values):

@@ -439,3 +439,61 @@ def test_selections_beyond_shared_memory_use_the_workspace(name, method, kwargs,
     slab.compress_(method, **kwargs)
     for li in range(L):
         assert torch.equal(slab[li][0], out[li][0]) and torch.equal(slab[li][1], out[li][1])
+
+
+# ----------------------------------------------------------------------------------------------
+# BASELINE.json FULL per-GPU sizes (not reduced batch): size-independent properties only
+def _checksum(x: torch.Tensor) -> torch.Tensor:
+    """Order-independent 64-bit checksum of the raw bytes of every row: [B,H,rows]."""
+    raw = x.contiguous().view(torch.int16 if x.element_size() == 2 else torch.int32).to(torch.int64)
+    weights = torch.arange(1, raw.size(-1) + 1, device=x.device, dtype=torch.int64) * 0x9E3779B1
+    return (raw * weights).sum(-1)
+
+
+FULL_SIZE = [
+    # c2 at its full single-GPU size: 32 layers x (32,32,4096,80) bf16 = 42.9 GB
+    ("c2_full", [("streaming_llm", dict(start_size=4, recent_size=508)),
+                 ("fix_size_l2", dict(fix_kv_size=512, keep_ratio=0.2, strategy="keep_low"))], 32, 32, 32, 4096, 80),
+    # c5's per-GPU shard on 8 GPUs: 32 layers x (8,8,32768,128) bf16 = 34.4 GB
+    ("c5_shard", [("pyramid_kv", dict(base_size=512)), ("adaptive_l2", dict(target_size=512))], 32, 8, 8, 32768, 128),
+]
+
+
+@pytest.mark.parametrize("name,calls,L,B,H,S,D", FULL_SIZE, ids=[f[0] for f in FULL_SIZE])
+def test_full_baseline_size_checksums(name, calls, L, B, H, S, D):
+    """Whole-job properties at the sizes bench.py runs: every output row is an input row (checksum of rows
+    against the gather by the reported indices), sinks / tails are where the plan says, indices ascend,
+    the kept rows are the lowest-norm rows, and a second call on the result is the identity."""
+    free, _ = torch.cuda.mem_get_info()
+    need = 2 * L * B * H * S * D * 2 * 1.25
+    if free < need:
+        pytest.skip(f"needs {need / 2**30:.0f} GiB of free HBM")
+    kv = spread_cache(L, B, H, S, D, torch.bfloat16)
+    for method, kwargs in calls:
+        plans = plan_for(method, [S] * L, kwargs)
+        n0 = _engine.launch_count()
+        out, idx = _engine.run_plans(kv, plans, return_indices=True)
+        assert _engine.launch_count() - n0 == 1
+        total_in = torch.zeros((), dtype=torch.int64, device="cuda")
+        total_out = torch.zeros((), dtype=torch.int64, device="cuda")
+        for li, p in enumerate(plans):
+            if p.kind != P.GATHER:
+                assert out[li][0] is kv[li][0]
+                continue
+            rows = idx[li].long()
+            assert torch.all(rows[..., 1:] > rows[..., :-1])
+            assert torch.equal(rows[..., :p.sink], torch.arange(p.sink, device="cuda").expand(B, H, -1))
+            assert torch.equal(rows[..., p.sink + p.k_sel:], torch.arange(S - p.tail, S, device="cuda").expand(B, H, -1))
+            for x_in, x_out in zip(kv[li], out[li]):
+                want = torch.gather(_checksum(x_in), 2, rows)
+                got = _checksum(x_out)
+                assert torch.equal(got, want)
+                total_in += want.sum()
+                total_out += got.sum()
+            if p.k_sel and li % 8 == 0:  # tie-aware selection rule on a sample of layers (fp64 norms are heavy)
+                assert_valid_lowest(kv[li][0][:, :, p.sel_lo:p.sel_hi], idx[li][..., p.sink:p.sink + p.k_sel] - p.sel_lo)
+        assert int(total_in) == int(total_out)  # checksum of checksums over the whole job
+        again = kvcompress.get_compress_fn(method)(out, **kwargs)
+        if method != "adaptive_l2":
+            assert all(a[0] is b[0] for a, b in zip(again, out))
+        del out, idx, again
