@@ -251,11 +251,12 @@ def cpu_sample_batch(cfg, requested, cap):
 
     if requested > 0:
         return min(requested, cap)
-    return max(1, min(cap, 8, -(-OC.max_threads() // cfg["H"])))
+    return max(1, min(cap, 8, max(2, -(-OC.max_threads() // cfg["H"]))))
 
 
-def cpu_port_run(cfg, sample_batch, steps, warmup, host_layers=None, threads=0):
-    """Time oracle/kvc_oracle.c (the reference's algorithm, OpenMP over (b,h)) on a bounded sample."""
+def cpu_port_run(cfg, sample_batch, steps, warmup, host_layers=None, threads=0, min_seconds=0.0):
+    """Time oracle/kvc_oracle.c (the reference's algorithm, OpenMP over (b,h)) on a bounded sample: `steps` timed
+    passes, extended until `min_seconds` of CPU work have been timed (at most 400 passes)."""
     import numpy as np
     import torch
 
@@ -282,19 +283,25 @@ def cpu_port_run(cfg, sample_batch, steps, warmup, host_layers=None, threads=0):
     e = 4 if dtype == "f32" else 2
     step_bytes = 0
     for method, kw in cfg["calls"]:
-        step_bytes += O.algorithmic_bytes(O.METHODS[method](layers, dtype, select=None, **kw), e)
+        step_bytes += O.algorithmic_bytes(O.METHODS[method](layers, dtype, select=None,
+                                                            **{k: v for k, v in kw.items() if not k.startswith("_")}), e)
     times = []
-    for it in range(warmup + steps):
+    it = 0
+    while True:
         t = 0.0
         for method, kw in cfg["calls"]:
-            _, _, dt_s = OC.run_method(method, layers, dtype, nthreads=threads, **kw)
+            _, _, dt_s = OC.run_method(method, layers, dtype, nthreads=threads,
+                                       **{k: v for k, v in kw.items() if not k.startswith("_")})
             t += dt_s
         if it >= warmup:
             times.append(t)
+        it += 1
+        if len(times) >= steps and (sum(times) >= min_seconds or len(times) >= 400):
+            break
     mean_s = sum(times) / len(times)
     return dict(gbs=step_bytes / mean_s / 1e9, seconds_per_step=mean_s, threads=threads, step_bytes=step_bytes,
                 sample=f"{cfg['L']} layers x (B={sample_batch}, H={cfg['H']}, S={cfg['S']}, D={cfg['D']}) {dtype}, "
-                       f"{len(times)} timed passes of the same calls")
+                       f"{len(times)} timed passes of the same calls ({sum(times):.1f} s of CPU work)")
 
 
 # --------------------------------------------------------------------------- reference arm
@@ -303,9 +310,9 @@ def run_reference(args):
     if rank != 0:
         return
     cfg = dict(CONFIGS[args.config])
-    steps = max(1, min(args.steps, 5))
-    sb = cpu_sample_batch(cfg, args.cpu_sample_batch, cfg["B"])
-    res = cpu_port_run(cfg, sb, steps, min(args.warmup, 1))
+    steps = max(1, args.steps)
+    sb = cpu_sample_batch(cfg, args.cpu_sample_batch or 8, cfg["B"])  # 8 streams: ~0.5 s per pass on 16 cores
+    res = cpu_port_run(cfg, sb, steps, min(args.warmup, 1))  # exactly `steps` timed passes of the bounded sample
     line = {
         "impl": "reference", "metric": "kv_compress_step_throughput", "value": round(res["gbs"], 3), "unit": "GB/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
@@ -449,7 +456,7 @@ def run_ours(args):
         host_layers = [(k[:sb].cpu(), v[:sb].cpu()) for k, v in kv]
         del kv
         torch.cuda.empty_cache()
-        res = cpu_port_run(cfg, sb, steps=2, warmup=1, host_layers=host_layers)
+        res = cpu_port_run(cfg, sb, steps=2, warmup=1, host_layers=host_layers, min_seconds=12.0)
         cpu = {"value": round(res["gbs"], 3), "unit": "GB/s", "cores": res["threads"], "kind": "port",
                "sample": res["sample"], "seconds_per_sample_step": round(res["seconds_per_step"], 4)}
 
@@ -659,13 +666,33 @@ def run_slab(args):
                             "algorithmic_bytes": per_call_bytes[i],
                             "effective_gbs": round(per_call_bytes[i] / (c_ms * 1e-3) / 1e9, 1),
                             "steady_state": steady[i]}
+    # the same steady-state step (append + compress_) replayed from a CUDA graph: no per-step host work
+    graph_us = {}
+    for i, ((method, kw), slab) in enumerate(zip(cfg["calls"], slabs)):
+        if not steady[i] or any(n is None for n in news[i]) or len(set(slab.lengths)) != 1:
+            continue
+        slab.compress_(method, **kw)  # the timed loop leaves the slab one token past its cap
+        step = slab.capture_step(method, **kw)
+        for _ in range(5):
+            step()
+        torch.cuda.synchronize()
+        n_rep = max(K, 20)
+        a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        a.record()
+        for _ in range(n_rep):
+            step()
+        b2.record()
+        torch.cuda.synchronize()
+        graph_us[method] = {"device_us_per_step": round(a.elapsed_time(b2) * 1e3 / n_rep, 1),
+                            "wall_us_per_step": round((time.perf_counter() - t0) * 1e6 / n_rep, 1)}
     line = {
         "metric": "kv_compress_step_throughput", "mode": "slab_in_place", "value": round(sum(per_call_bytes) / (total_ms * 1e-3) / 1e9, 1),
         "unit": "GB/s (same algorithmic bytes as the out-of-place functions)", "n_gpus": 1, "steps": K,
         "warmup": max(args.warmup, 3), "ms_per_step": round(total_ms, 4), "wall_ms_per_step": round(wall_ms, 4),
         "higher_is_better": True, "dtype": cfg["dtype"], "data": "synthetic",
         "config": workload_config(cfg, args.config, B, 1), "tok_per_s": round(B / (total_ms * 1e-3), 1),
-        "per_call": per_call, "gpu_launches": launches, "clocks": clocks,
+        "per_call": per_call, "graph_replay": graph_us or None, "gpu_launches": launches, "clocks": clocks,
         "peak": peak, "peak_source": peak_src,
     }
     print(json.dumps(line), flush=True)

@@ -375,4 +375,51 @@ class KVSlabCache:
         return (self, indices) if return_indices else self
 
 
-__all__ = ["KVSlabCache"]
+class SlabDecodeStep:
+    """One steady-state decode step — append one token per layer, compress in place — captured in a CUDA graph.
+
+    At steady state every step has the same shape (``S = cap`` rows, one new row, ``cap`` rows kept), the slab's
+    pointers never change and nothing is allocated, so the two launches replay from a graph with no per-step host
+    work.  Write the new token's rows into ``k_new`` / ``v_new`` (``[L, B, H, 1, D]``, static buffers) and call the
+    object; the slab is updated in place.  Built by :meth:`KVSlabCache.capture_step`."""
+
+    def __init__(self, slab: "KVSlabCache", method: str, kwargs: dict):
+        self.slab, self.method, self.kwargs = slab, method, dict(kwargs)
+        L, B, H, D = slab.num_layers, slab.batch, slab.heads, slab.head_dim
+        self.k_new = torch.zeros((L, B, H, 1, D), dtype=slab.dtype, device=slab.device)
+        self.v_new = torch.zeros((L, B, H, 1, D), dtype=slab.dtype, device=slab.device)
+        before = list(slab.lengths)
+        if len(set(before)) != 1:
+            raise ValueError("capture_step needs every layer at the same length (no skipped, growing layers)")
+        saved = (slab.k.clone(), slab.v.clone(), slab.n.clone())
+        stream = torch.cuda.Stream(device=slab.device)
+        stream.wait_stream(torch.cuda.current_stream(slab.device))
+        with torch.cuda.stream(stream):  # warm-up outside capture: library attributes, plan caches
+            slab.append_stacked(self.k_new, self.v_new)
+            slab.compress_(method, **self.kwargs)
+        torch.cuda.current_stream(slab.device).wait_stream(stream)
+        if slab.lengths != before:
+            raise ValueError(f"{method}: a step changes the cache lengths {before} -> {slab.lengths}; capture at steady "
+                             "state (the cache already at its cap)")
+        slab.k.copy_(saved[0]), slab.v.copy_(saved[1]), slab.n.copy_(saved[2])
+        del saved
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            slab.append_stacked(self.k_new, self.v_new)
+            slab.compress_(method, **self.kwargs)
+        # capture records, it does not run: lengths were advanced on the host only — they are the steady state
+        assert slab.lengths == before
+
+    def __call__(self) -> "KVSlabCache":
+        self.graph.replay()
+        return self.slab
+
+
+def _capture_step(self, method: str, **kwargs) -> SlabDecodeStep:
+    """Capture ``append_stacked(k_new, v_new); compress_(method, **kwargs)`` at steady state in a CUDA graph."""
+    return SlabDecodeStep(self, method, kwargs)
+
+
+KVSlabCache.capture_step = _capture_step
+
+__all__ = ["KVSlabCache", "SlabDecodeStep"]

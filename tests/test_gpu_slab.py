@@ -146,3 +146,29 @@ def test_slab_errors():
         KVSlabCache(1, 1, 2, 24, 32, torch.bfloat16)
     with pytest.raises(RuntimeError, match="no CPU path"):
         KVSlabCache(1, 1, 2, 80, 32, torch.bfloat16, device="cpu")
+
+
+def test_captured_decode_step_replays_append_and_compress():
+    """CUDA-graph replay of (append one token, compress in place) == the same two calls made eagerly."""
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    L, B, H, D, cap = 4, 2, 4, 80, 64
+    kw = dict(start_size=4, heavy_hitter_size=16, recent_size=44)
+    prefill = [rand_rows(B, H, cap, D, torch.bfloat16, gen) for _ in range(L)]
+    a = KVSlabCache.from_legacy_cache(prefill, capacity=cap + 8)
+    b = KVSlabCache.from_legacy_cache(prefill, capacity=cap + 8)
+    step = a.capture_step("h2o_l2", skip_layers=[], **kw)
+    n0 = _engine.launch_count()
+    for _ in range(12):
+        k_new = torch.randn(L, B, H, 1, D, generator=gen, device="cuda").bfloat16()
+        v_new = torch.randn(L, B, H, 1, D, generator=gen, device="cuda").bfloat16()
+        step.k_new.copy_(k_new)
+        step.v_new.copy_(v_new)
+        step()
+        b.append_stacked(k_new, v_new).compress_("h2o_l2", skip_layers=[], **kw)
+        assert a.lengths == b.lengths == [cap] * L
+        for li in range(L):
+            assert torch.equal(a[li][0], b[li][0]) and torch.equal(a[li][1], b[li][1])
+    assert _engine.launch_count() - n0 == 24  # only the eager slab launched through the library during the loop
+    with pytest.raises(ValueError, match="steady"):
+        KVSlabCache.from_legacy_cache([(k[:, :, :40], v[:, :, :40]) for k, v in prefill], capacity=cap + 8) \
+            .capture_step("h2o_l2", skip_layers=[], **kw)
