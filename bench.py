@@ -340,6 +340,23 @@ def workload_config(cfg, name, batch, n_gpus):
     }
 
 
+def bind_to_gpu_cpus(cuda_index: int):
+    """Multi-rank runs: bind this rank to the CPU cores nearest its GPU (NVML's ideal affinity) before any pinned
+    host buffer is allocated, so the e2e leg's host cache is first-touched on the GPU's NUMA node and the ranks
+    do not all pull from one socket.  Returns the number of cores bound, or None if NVML cannot do it."""
+    try:
+        import pynvml as nv
+        import torch
+
+        nv.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(cuda_index).uuid)
+        h = nv.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+        nv.nvmlDeviceSetCpuAffinity(h)
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
 # --------------------------------------------------------------------------- our arm
 def run_ours(args):
     import torch
@@ -355,6 +372,7 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: the compress path has no CPU fallback")
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    numa = bind_to_gpu_cpus(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
     _engine.load_library()
@@ -470,6 +488,7 @@ def run_ours(args):
             "algorithmic_bytes_per_step": step_bytes * world, "per_call": per_call, "roofline": roofline,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "tensor_tflops": round(vote_flops / (ms_per_step * 1e-3) / 1e12, 1) if vote_flops else None,
+            "rank_cpu_binding": f"NVML ideal affinity, {numa} cores per rank" if numa else None,
             "library": os.path.relpath(_engine.library_path(), ROOT),
         }
         print(json.dumps(line), flush=True)
