@@ -28,7 +28,8 @@ def fix_size_l2_compress(past_key_values, fix_kv_size: int = 1024, keep_ratio: f
     protected, the rest of the budget is chosen from the older tokens by ``strategy``
     ("keep_low" / "keep_high" L2 norm, or "random").  Unknown strategies raise ``ValueError``."""
     layers = as_layer_list(past_key_values)
-    plans = cached_plans(_planner.plan_fix_size, seq_lens(layers), fix_kv_size, keep_ratio, strategy, skip_layers=skip_layers)
+    plans = cached_plans(_planner.plan_fix_size, seq_lens(layers), fix_kv_size, keep_ratio, strategy,
+                         skip_layers=skip_layers)
     given = None
     if strategy == "random":
         given = {li: _random_indices(layers[li][0], p.sel_hi, p.k_sel)

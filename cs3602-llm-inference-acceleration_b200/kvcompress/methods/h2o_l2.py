@@ -15,7 +15,8 @@ def h2o_l2_compress(past_key_values, start_size: int = 4, heavy_hitter_size: int
     layers = as_layer_list(past_key_values)
     if not layers:
         return layers
-    plans = cached_plans(_planner.plan_h2o, seq_lens(layers), start_size, heavy_hitter_size, recent_size, skip_layers=skip_layers)
+    plans = cached_plans(_planner.plan_h2o, seq_lens(layers), start_size, heavy_hitter_size, recent_size,
+                         skip_layers=skip_layers)
     return execute(layers, plans)
 
 

@@ -16,7 +16,8 @@ def pyramid_kv_compress(past_key_values, base_size: int = 512, layer_decay: floa
     layers = as_layer_list(past_key_values)
     if not layers:
         return layers
-    plans = cached_plans(_planner.plan_pyramid, seq_lens(layers), base_size, layer_decay, min_size, profile, skip_layers=skip_layers)
+    plans = cached_plans(_planner.plan_pyramid, seq_lens(layers), base_size, layer_decay, min_size, profile,
+                         skip_layers=skip_layers)
     return execute(layers, plans)
 
 

@@ -25,7 +25,8 @@ def evict_for_space(past_key_values, num_coming: int, start_size: int = 4, recen
     layers = as_layer_list(past_key_values)
     if not layers:
         return layers
-    plans = cached_plans(_planner.plan_evict_for_space, seq_lens(layers), num_coming, start_size, recent_size, skip_layers=skip_layers)
+    plans = cached_plans(_planner.plan_evict_for_space, seq_lens(layers), num_coming, start_size, recent_size,
+                         skip_layers=skip_layers)
     return execute(layers, plans)
 
 
