@@ -494,6 +494,24 @@ static AppendFn pick_append_cpr(int cpr) {
         default: return nullptr;
     }
 }
+template <int DT>
+static AppendFn pick_append_tma_cpr(int cpr) {
+    switch (cpr) {
+        case 8: return kvc_slab_append_tma_kernel<DT, 8>;
+        case 10: return kvc_slab_append_tma_kernel<DT, 10>;
+        case 16: return kvc_slab_append_tma_kernel<DT, 16>;
+        case 20: return kvc_slab_append_tma_kernel<DT, 20>;
+        case 32: return kvc_slab_append_tma_kernel<DT, 32>;
+        default: return nullptr;
+    }
+}
+static AppendFn pick_append_tma(int dtype, int cpr) {
+    switch (dtype) {
+        case KVC_DTYPE_F32: return pick_append_tma_cpr<KVC_DTYPE_F32>(cpr);
+        case KVC_DTYPE_F16: return pick_append_tma_cpr<KVC_DTYPE_F16>(cpr);
+        default: return pick_append_tma_cpr<KVC_DTYPE_BF16>(cpr);
+    }
+}
 static AppendFn pick_append(int dtype, int cpr) {
     switch (dtype) {
         case KVC_DTYPE_F32: return pick_append_cpr<KVC_DTYPE_F32>(cpr);
@@ -867,10 +885,26 @@ int kvc_slab_append(const kvc_shape* shape, int32_t n_layers, const kvc_slab_lay
         }
         if (n_active == 0) continue;
         bd.max_new = max_new;
-        const int64_t threads = (int64_t)B * H * max_new;
-        dim3 grid((unsigned)((threads + 127) / 128), (unsigned)n_active, 1);
-        fn<<<grid, 128, 0, (cudaStream_t)stream>>>(bd);
-        cudaError_t err = cudaGetLastError();
+        cudaError_t err;
+        if (max_new >= 32) {
+            // prefill / chunked prefill: rows move 32 at a time through shared memory with bulk copies
+            AppendFn tfn = pick_append_tma(dt, cpr);
+            st = ensure_tma_attrs((const void*)tfn, shape->device);
+            if (st != KVC_OK) return st;
+            const size_t smem = 128 + (size_t)8 * 32 * cpr * 16;
+            const int64_t items = (int64_t)B * H * ((max_new + 31) / 32);
+            int64_t blocks = (items + 7) / 8;
+            const int64_t cap = 148LL * 3 * 8;  // a few waves; warps stride over the remaining blocks
+            if (blocks > cap) blocks = cap;
+            dim3 grid((unsigned)blocks, (unsigned)n_active, 1);
+            tfn<<<grid, 256, smem, (cudaStream_t)stream>>>(bd);
+            err = cudaGetLastError();
+        } else {
+            const int64_t threads = (int64_t)B * H * max_new;
+            dim3 grid((unsigned)((threads + 127) / 128), (unsigned)n_active, 1);
+            fn<<<grid, 128, 0, (cudaStream_t)stream>>>(bd);
+            err = cudaGetLastError();
+        }
         if (err != cudaSuccess) return cuda_fail(err, "kvc_slab_append_kernel launch");
         g_launches.fetch_add(1);
     }
