@@ -497,3 +497,39 @@ def test_full_baseline_size_checksums(name, calls, L, B, H, S, D):
         if method != "adaptive_l2":
             assert all(a[0] is b[0] for a, b in zip(again, out))
         del out, idx, again
+
+
+# ----------------------------------------------------------------------------------------------
+# §8f rows 2 and 3 against outputs of the real reference (tests/golden/make_extras_golden.py)
+def test_evict_for_space_and_h2o_attention_manager_match_reference():
+    import json
+    import os
+
+    import extras_cases as E
+
+    want = json.load(open(os.path.join(os.path.dirname(cases.GOLDEN_NPZ), "extras_golden.json")))
+
+    def rows_of(v):
+        return v[0, :, :, 0].long().tolist()
+
+    for name, seq_lens, num_coming, start, recent, skip in E.EVICT_CASES:
+        kv = [(k.cuda(), v.cuda()) for k, v in E.evict_cache(seq_lens)]
+        out = kvcompress.evict_for_space(kv, num_coming, start_size=start, recent_size=recent, skip_layers=skip)
+        assert [k.size(2) for k, _ in out] == want["evict"][name]["lengths"], name
+        assert [o[0] is i[0] for o, i in zip(out, kv)] == want["evict"][name]["untouched"], name
+        assert [rows_of(v) for _, v in out] == want["evict"][name]["rows"], name
+        for (k_in, _), (k_out, v_out) in zip(kv, out):
+            assert torch.equal(k_out, gather_rows(k_in, v_out[..., 0].long()))
+
+    c = E.H2O_CASE
+    mgr = kvcompress.H2OAttentionManager(start_size=c["start_size"], heavy_hitter_size=c["heavy_hitter_size"],
+                                         recent_size=c["recent_size"], num_layers=c["layers"], num_heads=c["heads"],
+                                         decay_factor=c["decay_factor"])
+    for step, ref in enumerate(want["h2o"]):
+        kv, attn = E.h2o_inputs(step, ref["seq_len"])
+        kv = [(k.cuda(), v.cuda()) for k, v in kv]
+        out = kvcompress.h2o_attention_compress(kv, attention_scores=[a.cuda() for a in attn], h2o_manager=mgr,
+                                                start_size=c["start_size"], heavy_hitter_size=c["heavy_hitter_size"],
+                                                recent_size=c["recent_size"], skip_layers=c["skip_layers"])
+        assert [k.size(2) for k, _ in out] == ref["lengths"], step
+        assert [rows_of(v) for _, v in out] == ref["rows"], step

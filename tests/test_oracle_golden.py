@@ -104,3 +104,25 @@ def test_bf16_rounding_is_round_to_nearest_even():
     back = O.f32_from_bf16_bits(bits)
     # 1.00390625 = 1 + 2^-8 is a halfway case -> even mantissa (1.0); 1.01171875 = 1 + 3*2^-8 -> 1.015625
     np.testing.assert_array_equal(back[:4], np.array([1.0, 1.0, 1.015625, -2.5], dtype=np.float32))
+
+
+# ----------------------------------------------------------------------------------------------
+# evict_for_space (reference streaming_llm.py:114-170): oracle and host planner vs the real reference
+def test_evict_for_space_oracle_and_planner_match_reference():
+    import json
+    import os
+
+    import extras_cases as E
+    from kvcompress import _planner as P
+
+    want = json.load(open(os.path.join(os.path.dirname(cases.GOLDEN_NPZ), "extras_golden.json")))["evict"]
+    for name, seq_lens, num_coming, start, recent, skip in E.EVICT_CASES:
+        layers = [(k.numpy(), v.numpy()) for k, v in E.evict_cache(seq_lens)]
+        res = O.evict_for_space(layers, "f32", num_coming, start_size=start, recent_size=recent, skip_layers=skip)
+        assert O.out_lengths(layers, res) == want[name]["lengths"], name
+        assert [r.untouched for r in res] == want[name]["untouched"], name
+        plans = P.plan_evict_for_space(seq_lens, num_coming, start, recent, skip)
+        assert [p.out_len for p in plans] == want[name]["lengths"], name
+        for li, r in enumerate(res):
+            if not r.untouched:
+                assert r.rows[0].tolist() == want[name]["rows"][li], (name, li)
