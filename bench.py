@@ -53,6 +53,10 @@ CONFIGS = {
     "c4_vote": dict(LLAMA, B=16, S=32768, dtype="bf16", calls=[
         ("snapkv_lite", dict(observation_window=32, keep_size=512, _vote_group=4)),
     ]),
+    # the vote on an MHA model: Pythia shape, one query head per KV head (32 of the 128 query rows in use)
+    "c2_vote": dict(PYTHIA, B=32, S=4096, dtype="bf16", calls=[
+        ("snapkv_lite", dict(observation_window=32, keep_size=512, _vote_group=1)),
+    ]),
     # configs[4]: B=64 total = 8 ranks x 8 streams (34 GB per rank)
     "c5": dict(LLAMA, B=8, S=32768, dtype="bf16", calls=[
         ("pyramid_kv", dict(base_size=512)),

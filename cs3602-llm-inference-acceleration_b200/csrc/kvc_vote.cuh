@@ -249,7 +249,9 @@ __global__ void __launch_bounds__(256, 2) kvc_snapkv_vote_kernel(const __grid_co
             if (more) stage_tile(t + 2);  // the operand buffer is free: copies fly under the math below
             const int key0 = t * kVoteTile;
             uint32_t v[32];
-            if (!keys_are_rows) {
+            if (!keys_are_rows && (warp & 3) * 32 >= rows_q) {
+                // this warp's 32 TMEM lanes are padding query rows (G*W < 128, e.g. MHA with W = 32): nothing to reduce
+            } else if (!keys_are_rows) {
                 // ---------------- pass 1: lane = query row, columns = keys of this tile (online softmax statistics)
                 const int limit = P + ((gt < rows_q) ? (gt % W) : 0);  // causal inside the window
                 const bool masked = key0 + kVoteTile > P;               // only the last tiles meet the mask / S
@@ -286,7 +288,7 @@ __global__ void __launch_bounds__(256, 2) kvc_snapkv_vote_kernel(const __grid_co
                 // ---------------- pass 2: lane = key, columns = query rows
                 float vote0 = 0.f, vote1 = 0.f, vote2 = 0.f, vote3 = 0.f;
 #pragma unroll 1
-                for (int cb = 0; cb < kVoteM; cb += 32) {
+                for (int cb = 0; cb < rows_q; cb += 32) {  // padding query rows (columns >= G*W) never vote
                     tmem_ld32(t_lane + cb, v);
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
