@@ -1,7 +1,6 @@
 set -x
-for rep in 1 2; do
-for v in A B; do
-  if [ $v = B ]; then export KVC_LIBRARY=$PWD/cs3602-llm-inference-acceleration_b200/csrc/libkvc_variantB.so; else unset KVC_LIBRARY; fi
-  timeout 900 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline --config c4_vote 2>/dev/null | python -c "
-import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('VOTE $v rep$rep', d['us_per_step'], d['value'], d['clocks']['sm_mhz'], d['clocks']['reasons'], d['library'])"
-done; done
+KVC_VOTE_W8=1 timeout 600 python -m pytest tests/test_gpu_vote.py -x -q 2>&1 | tail -4
+for rep in 1 2; do for v in 0 1; do for c in c4_vote c2_vote; do
+  KVC_VOTE_W8=$v timeout 900 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline --config $c 2>/dev/null | python -c "
+import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('VOTE w8=$v $c rep$rep', d['us_per_step'], d['value'], d['roofline']['frac'])"
+done; done; done
