@@ -26,10 +26,40 @@ def normalize_kv_cache(past_key_values) -> List[Tuple[torch.Tensor, torch.Tensor
     return items
 
 
+def _adopt_layers(past_key_values):
+    """A ``DynamicCache`` whose layers hold the given tensors themselves.  ``cache.update`` on an empty layer
+    concatenates with an empty tensor, i.e. copies every layer once more (transformers cache_utils.py:119-120);
+    the compressed tensors are fresh already, so the layers can simply own them."""
+    from transformers.cache_utils import DynamicLayer
+
+    layers = []
+    for keys, values in past_key_values:
+        layer = DynamicLayer()
+        if not hasattr(layer, "is_initialized") or not hasattr(layer, "keys"):
+            return None  # a transformers version with a different layer object: use the portable path
+        layer.dtype, layer.device = keys.dtype, keys.device
+        layer.keys, layer.values = keys, values
+        layer.is_initialized = True
+        layers.append(layer)
+    cache = DynamicCache()
+    if getattr(cache, "layers", None) != []:
+        return None
+    cache.layers.extend(layers)
+    return cache
+
+
 def to_dynamic_cache(past_key_values: List[Tuple[torch.Tensor, torch.Tensor]]):
-    """List of ``(K, V)`` pairs -> ``DynamicCache`` via ``cache.update`` (reference utils.py:12-27)."""
+    """List of ``(K, V)`` pairs -> ``DynamicCache`` (reference utils.py:12-27, which goes through
+    ``cache.update``).  The layers adopt the tensors without the extra copy when the installed transformers
+    exposes its layer objects; otherwise the reference's ``cache.update`` path is used."""
     if DynamicCache is None:
         raise RuntimeError("transformers is required for to_dynamic_cache")
+    try:
+        cache = _adopt_layers(past_key_values)
+        if cache is not None:
+            return cache
+    except Exception:
+        pass
     cache = DynamicCache()
     for layer_idx, (keys, values) in enumerate(past_key_values):
         cache.update(keys, values, layer_idx)
