@@ -58,6 +58,14 @@ struct AppendBatchDev {
     AppendLayerDev layers[KVC_MAX_LAYERS_PER_LAUNCH];
 };
 
+// One-layer form of the append parameters (the per-layer `update` of a decode loop): 160 bytes of kernel
+// parameters instead of 9 KB, so the launch itself is as cheap as the torch.cat it replaces.
+struct AppendOneDev {
+    int32_t B, H;
+    int32_t max_new, pad;
+    AppendLayerDev layers[1];
+};
+
 constexpr int kMiscFirst = 3;  // misc[] slot: first output row whose source row differs from it
 
 // Same value as row_sumsq_smem (chunk sums + balanced tree; the tree is invariant under the
@@ -87,8 +95,8 @@ __device__ __forceinline__ float row_sumsq_copy(const char* src, char* dst) {
     return tot;
 }
 
-template <int DT, int CPR>
-__global__ void __launch_bounds__(128) kvc_slab_append_kernel(const __grid_constant__ AppendBatchDev bd) {
+template <int DT, int CPR, typename Params>
+__global__ void __launch_bounds__(128) kvc_slab_append_kernel(const __grid_constant__ Params bd) {
     using Tr = Traits<DT>;
     using Key = typename Tr::Key;
     constexpr int RB = CPR * 16;

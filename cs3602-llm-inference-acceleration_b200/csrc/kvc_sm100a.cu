@@ -486,12 +486,31 @@ static SlabFn pick_slab(int dtype, int cpr, int nt) {
 template <int DT>
 static AppendFn pick_append_cpr(int cpr) {
     switch (cpr) {
-        case 8: return kvc_slab_append_kernel<DT, 8>;
-        case 10: return kvc_slab_append_kernel<DT, 10>;
-        case 16: return kvc_slab_append_kernel<DT, 16>;
-        case 20: return kvc_slab_append_kernel<DT, 20>;
-        case 32: return kvc_slab_append_kernel<DT, 32>;
+        case 8: return kvc_slab_append_kernel<DT, 8, AppendBatchDev>;
+        case 10: return kvc_slab_append_kernel<DT, 10, AppendBatchDev>;
+        case 16: return kvc_slab_append_kernel<DT, 16, AppendBatchDev>;
+        case 20: return kvc_slab_append_kernel<DT, 20, AppendBatchDev>;
+        case 32: return kvc_slab_append_kernel<DT, 32, AppendBatchDev>;
         default: return nullptr;
+    }
+}
+using AppendOneFn = void (*)(const AppendOneDev);
+template <int DT>
+static AppendOneFn pick_append_one_cpr(int cpr) {
+    switch (cpr) {
+        case 8: return kvc_slab_append_kernel<DT, 8, AppendOneDev>;
+        case 10: return kvc_slab_append_kernel<DT, 10, AppendOneDev>;
+        case 16: return kvc_slab_append_kernel<DT, 16, AppendOneDev>;
+        case 20: return kvc_slab_append_kernel<DT, 20, AppendOneDev>;
+        case 32: return kvc_slab_append_kernel<DT, 32, AppendOneDev>;
+        default: return nullptr;
+    }
+}
+static AppendOneFn pick_append_one(int dtype, int cpr) {
+    switch (dtype) {
+        case KVC_DTYPE_F32: return pick_append_one_cpr<KVC_DTYPE_F32>(cpr);
+        case KVC_DTYPE_F16: return pick_append_one_cpr<KVC_DTYPE_F16>(cpr);
+        default: return pick_append_one_cpr<KVC_DTYPE_BF16>(cpr);
     }
 }
 template <int DT>
@@ -849,6 +868,42 @@ int kvc_slab_append(const kvc_shape* shape, int32_t n_layers, const kvc_slab_lay
     }
     st = set_device(shape->device);
     if (st != KVC_OK) return st;
+    auto fill = [&](AppendLayerDev& d, const kvc_slab_layer& sl, const kvc_slab_new_rows& r) {
+        d.k_new = (const char*)r.k_new;
+        d.v_new = (const char*)r.v_new;
+        d.k = (char*)sl.k;
+        d.v = (char*)sl.v;
+        d.n = (char*)sl.norms;
+        d.nksb = r.k_stride_b * e;
+        d.nksh = r.k_stride_h * e;
+        d.nkss = r.k_stride_s * e;
+        d.nvsb = r.v_stride_b * e;
+        d.nvsh = r.v_stride_h * e;
+        d.nvss = r.v_stride_s * e;
+        d.ksb = sl.k_stride_b * e;
+        d.ksh = sl.k_stride_h * e;
+        d.vsb = sl.v_stride_b * e;
+        d.vsh = sl.v_stride_h * e;
+        d.nsb = sl.n_stride_b * key_bytes(dt);
+        d.nsh = sl.n_stride_h * key_bytes(dt);
+        d.cur_len = r.cur_len;
+        d.n_new = r.n_new;
+    };
+    if (n_layers == 1 && rows[0].n_new > 0 && rows[0].n_new < 32) {
+        // the per-layer update of a decode loop: small parameter block, one small launch
+        AppendOneDev one;
+        one.B = B;
+        one.H = H;
+        one.max_new = rows[0].n_new;
+        one.pad = 0;
+        fill(one.layers[0], slabs[0], rows[0]);
+        const int64_t threads = (int64_t)B * H * rows[0].n_new;
+        pick_append_one(dt, cpr)<<<(unsigned)((threads + 127) / 128), 128, 0, (cudaStream_t)stream>>>(one);
+        cudaError_t err = cudaGetLastError();
+        if (err != cudaSuccess) return cuda_fail(err, "kvc_slab_append_kernel launch");
+        g_launches.fetch_add(1);
+        return KVC_OK;
+    }
     AppendFn fn = pick_append(dt, cpr);
     for (int l0 = 0; l0 < n_layers; l0 += KVC_MAX_LAYERS_PER_LAUNCH) {
         const int nl = (n_layers - l0) < KVC_MAX_LAYERS_PER_LAUNCH ? (n_layers - l0) : KVC_MAX_LAYERS_PER_LAUNCH;
@@ -861,26 +916,7 @@ int kvc_slab_append(const kvc_shape* shape, int32_t n_layers, const kvc_slab_lay
             const kvc_slab_layer& sl = slabs[l0 + l];
             const kvc_slab_new_rows& r = rows[l0 + l];
             if (r.n_new == 0) continue;
-            AppendLayerDev& d = bd.layers[n_active++];
-            d.k_new = (const char*)r.k_new;
-            d.v_new = (const char*)r.v_new;
-            d.k = (char*)sl.k;
-            d.v = (char*)sl.v;
-            d.n = (char*)sl.norms;
-            d.nksb = r.k_stride_b * e;
-            d.nksh = r.k_stride_h * e;
-            d.nkss = r.k_stride_s * e;
-            d.nvsb = r.v_stride_b * e;
-            d.nvsh = r.v_stride_h * e;
-            d.nvss = r.v_stride_s * e;
-            d.ksb = sl.k_stride_b * e;
-            d.ksh = sl.k_stride_h * e;
-            d.vsb = sl.v_stride_b * e;
-            d.vsh = sl.v_stride_h * e;
-            d.nsb = sl.n_stride_b * key_bytes(dt);
-            d.nsh = sl.n_stride_h * key_bytes(dt);
-            d.cur_len = r.cur_len;
-            d.n_new = r.n_new;
+            fill(bd.layers[n_active++], sl, r);
             if (r.n_new > max_new) max_new = r.n_new;
         }
         if (n_active == 0) continue;

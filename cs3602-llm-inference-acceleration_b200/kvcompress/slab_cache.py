@@ -249,9 +249,8 @@ class KVSlabCache:
         ks, vs = key_states.stride(), value_states.stride()
         rows = _ROWS.pack(key_states.data_ptr(), value_states.data_ptr(), ks[0], ks[1], ks[2], vs[0], vs[1], vs[2], n, T)
         if self._lib is None:
-            self._lib = _engine.load_library()
-        status = self._lib.kvc_slab_append(self._shape, 1, self._recs[layer_idx], rows,
-                                           ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+            self._lib = _engine.load_library().kvc_slab_append
+        status = self._lib(self._shape, 1, self._recs[layer_idx], rows, torch.cuda.current_stream(self.device).cuda_stream)
         if status:
             _engine._check(status, "kvc_slab_append")
         self.lengths[layer_idx] = n + T
