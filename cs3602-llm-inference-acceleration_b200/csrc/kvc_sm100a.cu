@@ -1045,6 +1045,77 @@ int kvc_slab_compress(const kvc_shape* shape, int32_t n_layers, const kvc_layer_
     return KVC_OK;
 }
 
+// cuTensorMapEncodeTiled through the runtime (the library links cudart statically and never links libcuda).
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+// TMA-fed vote kernel (kvc_vote.cuh): returns KVC_ERR_UNSUPPORTED when a tensor map cannot describe the keys,
+// in which case the caller falls back to the cp.async-fed kernel.
+static int launch_vote_tma(const kvc_shape* shape, int32_t n_layers, const kvc_vote_layer* layers, int32_t group,
+                           int32_t window, int cpr, void* stream) {
+    EncodeTiledFn encode = tensor_map_encoder();
+    if (!encode) return KVC_ERR_UNSUPPORTED;
+    const int B = shape->batch, H = shape->heads, D = shape->head_dim, dt = shape->dtype;
+    using Fn = void (*)(const VoteTmaBatchDev);
+    Fn fn = nullptr;
+    if (dt == KVC_DTYPE_BF16)
+        fn = cpr == 8 ? kvc_snapkv_vote_tma_kernel<KVC_DTYPE_BF16, 8> : kvc_snapkv_vote_tma_kernel<KVC_DTYPE_BF16, 16>;
+    else
+        fn = cpr == 8 ? kvc_snapkv_vote_tma_kernel<KVC_DTYPE_F16, 8> : kvc_snapkv_vote_tma_kernel<KVC_DTYPE_F16, 16>;
+    const size_t smem = 6144 + (size_t)(kVoteM / 8) * cpr * kVoteLBO + (size_t)kWsRing * (cpr / 8) * kVoteTile * 128;
+    int st = ensure_tma_attrs((const void*)fn, shape->device);
+    if (st != KVC_OK) return st;
+    for (int l0 = 0; l0 < n_layers; l0 += 32) {
+        const int nl = (n_layers - l0) < 32 ? (n_layers - l0) : 32;
+        VoteTmaBatchDev bd;
+        memset(&bd, 0, sizeof(bd));
+        bd.B = B;
+        bd.H = H;
+        bd.G = group;
+        bd.W = window;
+        bd.scale_log2e = 1.4426950408889634f / sqrtf((float)D);
+        bd.pad[0] = env_int("KVC_VOTE_DEBUG", 0);
+        for (int l = 0; l < nl; ++l) {
+            const kvc_vote_layer& v = layers[l0 + l];
+            VoteTmaLayerDev& d = bd.layers[l];
+            const cuuint64_t dims[4] = {(cuuint64_t)D, (cuuint64_t)v.seq_len, (cuuint64_t)H, (cuuint64_t)B};
+            const cuuint64_t strides[3] = {(cuuint64_t)v.k_stride_s * 2, (cuuint64_t)v.k_stride_h * 2,
+                                           (cuuint64_t)v.k_stride_b * 2};
+            const cuuint32_t box[4] = {64, (cuuint32_t)kVoteTile, 1, 1};
+            const cuuint32_t estr[4] = {1, 1, 1, 1};
+            const CUresult r = encode(&d.map, dt == KVC_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                                      4, const_cast<void*>(v.k_in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return KVC_ERR_UNSUPPORTED;
+            d.q = (const char*)v.q_obs;
+            d.votes = (char*)v.votes_out;
+            d.qsb = v.q_stride_b * 2;
+            d.qsh = v.q_stride_h * 2;
+            d.qss = v.q_stride_s * 2;
+            d.S = v.seq_len;
+        }
+        dim3 grid((unsigned)((int64_t)B * H), (unsigned)nl, 1);
+        fn<<<grid, 576, smem, (cudaStream_t)stream>>>(bd);
+        cudaError_t err = cudaGetLastError();
+        if (err != cudaSuccess) return cuda_fail(err, "kvc_snapkv_vote_tma_kernel launch");
+        g_launches.fetch_add(1);
+    }
+    return KVC_OK;
+}
+
 int kvc_snapkv_vote(const kvc_shape* shape, int32_t n_layers, const kvc_vote_layer* layers, int32_t group,
                     int32_t window, void* stream) {
     int cpr = 0;
@@ -1073,7 +1144,24 @@ int kvc_snapkv_vote(const kvc_shape* shape, int32_t n_layers, const kvc_vote_lay
     else
         fn = cpr == 8 ? kvc_snapkv_vote_kernel<KVC_DTYPE_F16, 8> : cpr == 10 ? kvc_snapkv_vote_kernel<KVC_DTYPE_F16, 10>
                                                                             : kvc_snapkv_vote_kernel<KVC_DTYPE_F16, 16>;
-    const size_t smem = 2304 + 3 * (size_t)(kVoteTile / 8) * cpr * kVoteLBO;
+    if ((cpr == 8 || cpr == 16) && env_int("KVC_VOTE_TMA", 1)) {
+        // head_dim 64 / 128: key tiles arrive through TMA tensor loads; strided layouts a tensor map cannot
+        // describe fall through to the cp.async-fed kernel below
+        st = launch_vote_tma(shape, n_layers, layers, group, window, cpr, stream);
+        if (st != KVC_ERR_UNSUPPORTED) return st;
+    }
+    size_t smem = 2304 + 3 * (size_t)(kVoteTile / 8) * cpr * kVoteLBO;
+    int threads = 256;
+    if (env_int("KVC_VOTE_WS", 0)) {  // A/B: warp-specialised form, one CTA per SM
+        if (dt == KVC_DTYPE_BF16)
+            fn = cpr == 8 ? kvc_snapkv_vote_ws_kernel<KVC_DTYPE_BF16, 8> : cpr == 10 ? kvc_snapkv_vote_ws_kernel<KVC_DTYPE_BF16, 10>
+                                                                                    : kvc_snapkv_vote_ws_kernel<KVC_DTYPE_BF16, 16>;
+        else
+            fn = cpr == 8 ? kvc_snapkv_vote_ws_kernel<KVC_DTYPE_F16, 8> : cpr == 10 ? kvc_snapkv_vote_ws_kernel<KVC_DTYPE_F16, 10>
+                                                                                   : kvc_snapkv_vote_ws_kernel<KVC_DTYPE_F16, 16>;
+        smem = 6144 + (1 + kWsRing) * (size_t)(kVoteTile / 8) * cpr * kVoteLBO;
+        threads = 672;
+    }
     st = ensure_tma_attrs((const void*)fn, shape->device);
     if (st != KVC_OK) return st;
     for (int l0 = 0; l0 < n_layers; l0 += KVC_MAX_LAYERS_PER_LAUNCH) {
@@ -1085,6 +1173,7 @@ int kvc_snapkv_vote(const kvc_shape* shape, int32_t n_layers, const kvc_vote_lay
         bd.G = group;
         bd.W = window;
         bd.scale_log2e = 1.4426950408889634f / sqrtf((float)shape->head_dim);
+        bd.pad[0] = env_int("KVC_VOTE_DEBUG", 0);  // stage isolation for profiling: 1 = no math, 2 = no math, no MMA
         for (int l = 0; l < nl; ++l) {
             const kvc_vote_layer& v = layers[l0 + l];
             VoteLayerDev& d = bd.layers[l];
@@ -1100,7 +1189,7 @@ int kvc_snapkv_vote(const kvc_shape* shape, int32_t n_layers, const kvc_vote_lay
             d.S = v.seq_len;
         }
         dim3 grid((unsigned)((int64_t)B * H), (unsigned)nl, 1);
-        fn<<<grid, 256, smem, (cudaStream_t)stream>>>(bd);
+        fn<<<grid, threads, smem, (cudaStream_t)stream>>>(bd);
         cudaError_t err = cudaGetLastError();
         if (err != cudaSuccess) return cuda_fail(err, "kvc_snapkv_vote_kernel launch");
         g_launches.fetch_add(1);

@@ -24,6 +24,8 @@
 // Intensity is ~2*128 flop per key byte at most: the kernel stays HBM/MUFU-bound, not tensor-bound
 // (SURVEY.md §7 "SnapKV vote spec gap") — the tensor pipe is reported, not chased.
 #pragma once
+#include <cuda.h>  // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "kvc_device.cuh"
 #include "kvc_tma.cuh"
 
@@ -85,6 +87,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "memory");
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+
+// 32 lanes x 16 consecutive fp32 columns, asynchronous: tmem_ld_wait() before the registers are read.
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, no swizzle: 8x16-byte core matrices; LBO = step between the two 16-byte K chunks of one
 // K=16 instruction, SBO = step between 8-row groups (cute/arch/mma_sm100_desc.hpp, SmemDescriptor).
@@ -340,6 +353,522 @@ __global__ void __launch_bounds__(256, 2) kvc_snapkv_vote_kernel(const __grid_co
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(*s_tmem, 256);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Warp-specialised form: ONE CTA per SM, 21 warps.
+//   warps 0-15  four math groups (128 threads = the 128 TMEM lanes); group g owns accumulator g (128 of the 512
+//               TMEM columns) and reduces work items g, g+4, g+8, ...;
+//   warps 16-19 copy warps: cp.async 16-byte copies of the key tiles straight into the canonical layout of a
+//               5-slot shared-memory ring, three tiles in flight, never waiting on math;
+//   warp 20     one thread issues every tcgen05.mma (waits: slot full, accumulator drained) and commits to the
+//               accumulator-full and slot-empty mbarriers.
+// Work items are the tiles of pass 1 (all S keys, A = Q) followed by the tiles of pass 2 (P keys, A = keys); the
+// copy and MMA warps run ahead across the pass boundary, only the math groups meet there to merge the row statistics.
+constexpr int kWsRing = 5;
+constexpr int kWsDepth = 3;  // tiles a copy thread keeps in flight beyond the one it is issuing
+constexpr int kWsMathThreads = 512;
+constexpr int kWsCopyThreads = 128;
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+
+template <int DT, int CPR>
+__global__ void __launch_bounds__(672, 1) kvc_snapkv_vote_ws_kernel(const __grid_constant__ VoteBatchDev bd) {
+    using Tr = Traits<DT>;
+    using Key = typename Tr::Key;
+    static_assert(DT != KVC_DTYPE_F32, "the vote runs on 16-bit caches (kind::f16)");
+    constexpr int TILE_BYTES = (kVoteTile / 8) * CPR * kVoteLBO;
+    constexpr int CHC = kVoteTile * CPR / kWsCopyThreads;  // 16-byte chunks per copy thread per tile
+    constexpr uint32_t IDESC = umma_idesc_f16(DT == KVC_DTYPE_BF16 ? 1 : 0, kVoteM, kVoteTile);
+
+    const VoteLayerDev& L = bd.layers[blockIdx.y];
+    const int bh = blockIdx.x;
+    const int b = bh / bd.H, h = bh - b * bd.H;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int S = L.S, W = bd.W, G = bd.G;
+    const int P = S - W;
+    const int rows_q = G * W;
+    const int n1 = (S + kVoteTile - 1) / kVoteTile, n2 = (P + kVoteTile - 1) / kVoteTile;
+    const int n_items = n1 + n2;
+
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem);
+    const uint32_t bar_full = smem_u32(smem + 64);        // [kWsRing]  count = copy threads
+    const uint32_t bar_empty = bar_full + 8 * kWsRing;    // [kWsRing]  count = 1 (tcgen05.commit)
+    const uint32_t bar_tfull = bar_empty + 8 * kWsRing;   // [4]        count = 1 (tcgen05.commit)
+    const uint32_t bar_tempty = bar_tfull + 8 * 4;        // [4]        count = 128 (math threads)
+    float* s_m = reinterpret_cast<float*>(smem + 512);
+    float* s_invl = reinterpret_cast<float*>(smem + 1024);
+    float* s_part = reinterpret_cast<float*>(smem + 1536);  // [4 groups][2][128]
+    unsigned char* s_q = smem + 6144;
+    unsigned char* s_ring = s_q + TILE_BYTES;
+
+    if (tid == 0) {
+        for (int i = 0; i < kWsRing; ++i) {
+            mbar_init(bar_full + 8 * i, kWsCopyThreads);
+            mbar_init(bar_empty + 8 * i, 1);
+        }
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(bar_tfull + 8 * i, 1);
+            mbar_init(bar_tempty + 8 * i, 128);
+        }
+        mbar_init_fence();
+    }
+    if (warp == 20) tmem_alloc(smem_u32(s_tmem), 512);
+    const char* kbase = L.k + (int64_t)b * L.ksb + (int64_t)h * L.ksh;
+    for (int q = tid; q < kVoteM * CPR; q += 672) {
+        int r, c;
+        tile_item<CPR>(q, r, c);
+        int4 v = make_int4(0, 0, 0, 0);
+        if (r < rows_q) {
+            const int g = r / W, w = r - g * W;
+            v = ldg128_stream(L.q + (int64_t)b * L.qsb + (int64_t)(h * G + g) * L.qsh + (int64_t)w * L.qss + c * 16);
+        }
+        *reinterpret_cast<int4*>(s_q + umma_off<CPR>(r, c)) = v;
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *s_tmem;
+    const uint32_t q_addr = smem_u32(s_q), ring_addr = smem_u32(s_ring);
+    const float c2 = bd.scale_log2e;
+
+    if (warp < 16) {
+        // ================================================================ math groups
+        const int grp = warp >> 2, gt = tid & 127;
+        const uint32_t t_lane = tmem + grp * kVoteTile + ((uint32_t)((warp & 3) * 32) << 16);
+        float m_run = -INFINITY, l_run = 0.f;
+        // the accumulator is read 16 columns at a time with the next 16 already in flight (two register sets):
+        // TMEM reads (64 B/clk per SM) and the ex2 pipe are floors of the same size and must overlap
+        uint32_t va[16], vb[16];
+        const int limit = P + ((gt < rows_q) ? (gt % W) : 0);
+        const bool row_live = (warp & 3) * 32 < rows_q;
+        int i = grp;
+        for (; i < n1; i += 4) {
+            mbar_wait(bar_tfull + 8 * grp, (uint32_t)((i >> 2) & 1));
+            tc_fence_after();
+            if (row_live && bd.pad[0] == 0) {
+                const int key0 = i * kVoteTile;
+                const bool masked = key0 + kVoteTile > P;
+                tmem_ld16_async(t_lane, va);
+#pragma unroll
+                for (int cb = 0; cb < kVoteTile; cb += 16) {
+                    uint32_t(&v)[16] = ((cb >> 4) & 1) ? vb : va;
+                    tmem_ld_wait();
+                    if (cb + 16 < kVoteTile) tmem_ld16_async(t_lane + cb + 16, ((cb >> 4) & 1) ? va : vb);
+                    float cmax = -INFINITY;
+                    if (masked) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int key = key0 + cb + j;
+                            if (key > limit || key >= S) v[j] = 0xff800000u;
+                            cmax = fmaxf(cmax, __uint_as_float(v[j]));
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) cmax = fmaxf(cmax, __uint_as_float(v[j]));
+                    }
+                    const float m_new = fmaxf(m_run, cmax * c2);
+                    if (m_new > -INFINITY) {
+                        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            acc0 += ex2(fmaf(__uint_as_float(v[j]), c2, -m_new));
+                            acc1 += ex2(fmaf(__uint_as_float(v[j + 1]), c2, -m_new));
+                            acc2 += ex2(fmaf(__uint_as_float(v[j + 2]), c2, -m_new));
+                            acc3 += ex2(fmaf(__uint_as_float(v[j + 3]), c2, -m_new));
+                        }
+                        if (m_new != m_run) l_run *= ex2(m_run - m_new);  // the maximum settles after a few tiles
+                        l_run += (acc0 + acc1) + (acc2 + acc3);
+                        m_run = m_new;
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(bar_tempty + 8 * grp);
+        }
+        // ---------------- pass boundary: merge the four groups' partial statistics
+        s_part[(grp * 2 + 0) * 128 + gt] = m_run;
+        s_part[(grp * 2 + 1) * 128 + gt] = l_run;
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        if (tid < 128) {
+            float m = -INFINITY;
+#pragma unroll
+            for (int g4 = 0; g4 < 4; ++g4) m = fmaxf(m, s_part[(g4 * 2) * 128 + tid]);
+            float l = 0.f;
+            if (m > -INFINITY) {
+#pragma unroll
+                for (int g4 = 0; g4 < 4; ++g4) {
+                    const float mp = s_part[(g4 * 2) * 128 + tid];
+                    if (mp > -INFINITY) l += s_part[(g4 * 2 + 1) * 128 + tid] * ex2(mp - m);
+                }
+            }
+            const bool live = tid < rows_q && l > 0.f;
+            s_m[tid] = live ? m : 0.f;
+            s_invl[tid] = live ? 1.f / l : 0.f;
+        }
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        // ---------------- pass 2: lane = key, columns = query rows
+        for (; i < n_items; i += 4) {
+            mbar_wait(bar_tfull + 8 * grp, (uint32_t)((i >> 2) & 1));
+            tc_fence_after();
+            float vote0 = 0.f, vote1 = 0.f, vote2 = 0.f, vote3 = 0.f;
+            if (bd.pad[0] == 0) tmem_ld16_async(t_lane, va);
+#pragma unroll
+            for (int cb = 0; cb < kVoteM; cb += 16) {
+                if (cb < rows_q && bd.pad[0] == 0) {  // warp-uniform: padding query rows never vote
+                    uint32_t(&v)[16] = ((cb >> 4) & 1) ? vb : va;
+                    tmem_ld_wait();
+                    if (cb + 16 < rows_q) tmem_ld16_async(t_lane + cb + 16, ((cb >> 4) & 1) ? va : vb);
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 mm = *reinterpret_cast<const float4*>(s_m + cb + j);
+                        const float4 il = *reinterpret_cast<const float4*>(s_invl + cb + j);
+                        vote0 = fmaf(ex2(fmaf(__uint_as_float(v[j + 0]), c2, -mm.x)), il.x, vote0);
+                        vote1 = fmaf(ex2(fmaf(__uint_as_float(v[j + 1]), c2, -mm.y)), il.y, vote1);
+                        vote2 = fmaf(ex2(fmaf(__uint_as_float(v[j + 2]), c2, -mm.z)), il.z, vote2);
+                        vote3 = fmaf(ex2(fmaf(__uint_as_float(v[j + 3]), c2, -mm.w)), il.w, vote3);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(bar_tempty + 8 * grp);
+            const int key = (i - n1) * kVoteTile + gt;
+            if (key < P) {
+                Key* out = reinterpret_cast<Key*>(L.votes) + (int64_t)bh * P;
+                out[key] = (Key)Tr::to_raw((vote0 + vote1) + (vote2 + vote3));
+            }
+        }
+    } else if (warp < 20) {
+        // ================================================================ copy warps
+        const int ct = tid - kWsMathThreads;
+        int64_t kss = L.kss;
+        asm volatile("" : "+l"(kss));
+        for (int i = 0; i < n_items; ++i) {
+            const int slot = i % kWsRing;
+            mbar_wait(bar_empty + 8 * slot, (uint32_t)(((i / kWsRing) & 1) ^ 1));  // fresh barrier: passes
+            const int t = i < n1 ? i : i - n1;
+            const int r0 = t * kVoteTile;
+            const char* tile = kbase + (int64_t)r0 * kss;
+            const uint32_t dst = ring_addr + slot * TILE_BYTES;
+            if (CPR == 16 && r0 + kVoteTile <= S) {
+                // full tile, 128 copy threads: thread ct always takes row (ct & 7) of every 8-row group and chunk
+                // ct >> 3, so source and destination advance by constants (two adds per copy)
+                const char* src = tile + (int64_t)(ct & 7) * kss + (ct >> 3) * 16;
+                uint32_t d = dst + (uint32_t)((ct >> 3) * kVoteLBO + (ct & 7) * 16);
+                const int64_t step = 8 * kss;
+#pragma unroll
+                for (int k = 0; k < CHC; ++k) {
+                    cp_async16(d, src, true);
+                    src += step;
+                    d += CPR * kVoteLBO;
+                }
+            } else {
+#pragma unroll 4
+                for (int k = 0; k < CHC; ++k) {
+                    int r, c;
+                    tile_item<CPR>(k * kWsCopyThreads + ct, r, c);
+                    const bool ok = r0 + r < S;
+                    cp_async16(dst + umma_off<CPR>(r, c), ok ? tile + r * kss + c * 16 : kbase, ok);
+                }
+            }
+            cp_async_commit();
+            if (i >= kWsDepth) {  // at most kWsDepth + 1 tiles in flight per copy thread
+                cp_async_wait_group<kWsDepth>();
+                fence_proxy_async_smem();
+                mbar_arrive(bar_full + 8 * ((i - kWsDepth) % kWsRing));
+            }
+        }
+        cp_async_wait_group<0>();
+        fence_proxy_async_smem();
+        for (int j = (n_items > kWsDepth ? n_items - kWsDepth : 0); j < n_items; ++j) mbar_arrive(bar_full + 8 * (j % kWsRing));
+    } else if (warp == 20 && lane == 0) {
+        // ================================================================ MMA issuer
+        for (int i = 0; i < n_items; ++i) {
+            const int slot = i % kWsRing, acc = i & 3;
+            mbar_wait(bar_tempty + 8 * acc, (uint32_t)(((i >> 2) & 1) ^ 1));  // accumulator drained (fresh: passes)
+            mbar_wait(bar_full + 8 * slot, (uint32_t)((i / kWsRing) & 1));    // tile landed
+            tc_fence_after();
+            const bool keys_are_rows = i >= n1;
+            const uint32_t kb = ring_addr + slot * TILE_BYTES;
+            const uint32_t a0 = keys_are_rows ? kb : q_addr;
+            const uint32_t b0 = keys_are_rows ? q_addr : kb;
+            if (bd.pad[0] < 2) {
+#pragma unroll
+                for (int ks = 0; ks < CPR / 2; ++ks) {
+                    const uint64_t ad = umma_smem_desc(a0 + ks * 2 * kVoteLBO, kVoteLBO, CPR * kVoteLBO);
+                    const uint64_t bdsc = umma_smem_desc(b0 + ks * 2 * kVoteLBO, kVoteLBO, CPR * kVoteLBO);
+                    umma_f16(tmem + acc * kVoteTile, ad, bdsc, IDESC, ks > 0 ? 1u : 0u);
+                }
+            }
+            umma_commit(bar_tfull + 8 * acc);
+            umma_commit(bar_empty + 8 * slot);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 20) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA-fed warp-specialised form (head_dim * 2 bytes a multiple of 128: D = 64, 128).  Stage isolation of the
+// cp.async-fed kernels showed the copy stage alone at 4.3 TB/s (16 of 22 ms at c4): 16-byte copies into the
+// layout are the bottleneck, not the tensor core or the softmax math.  Here ONE thread feeds the ring with
+// `cp.async.bulk.tensor.4d` loads through a per-layer tensor map (boxes of 128 rows x 64 elements, 128-byte
+// swizzle = the K-major SW128 UMMA layout; rows beyond S are zero-filled by the TMA unit), warps 0-15 do the
+// softmax math exactly as above and one thread issues the MMAs (keys: SW128 descriptors, queries: no-swizzle).
+struct VoteTmaLayerDev {
+    alignas(64) CUtensorMap map;  // keys [B,H,S,D] as a 4-D tensor (D, S, H, B), box (64, 128, 1, 1), SWIZZLE_128B
+    const char* q;
+    char* votes;
+    int64_t qsb, qsh, qss;
+    int32_t S, pad;
+};
+struct VoteTmaBatchDev {
+    int32_t B, H, G, W;
+    float scale_log2e;
+    int32_t pad[3];
+    VoteTmaLayerDev layers[32];
+};
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst_smem, const CUtensorMap* map, int c0, int c1, int c2, int c3,
+                                            uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+        ::"r"(dst_smem), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+        : "memory");
+}
+// K-major, 128-byte swizzle: rows 128 B apart inside an 8-row atom, atoms 1024 B apart (SBO), LBO = 16 B.
+__device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+    d |= (uint64_t)1 << 16;           // leading byte offset 16 B (unused by swizzled K-major layouts)
+    d |= (uint64_t)(1024 >> 4) << 32;  // stride byte offset: 8 rows x 128 B
+    d |= (uint64_t)1 << 46;           // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;           // layout type SWIZZLE_128B
+    return d;
+}
+
+template <int DT, int CPR>
+__global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __grid_constant__ VoteTmaBatchDev bd) {
+    using Tr = Traits<DT>;
+    using Key = typename Tr::Key;
+    static_assert(DT != KVC_DTYPE_F32, "the vote runs on 16-bit caches (kind::f16)");
+    static_assert(CPR % 8 == 0, "128-byte swizzled boxes: head_dim * 2 bytes must be a multiple of 128");
+    constexpr int KH = CPR / 8;                       // 64-element (128-byte) boxes per key row
+    constexpr int BOX_BYTES = kVoteTile * 128;        // one box: 128 rows x 128 B, 128B-swizzled
+    constexpr int TILE_BYTES = KH * BOX_BYTES;
+    constexpr int Q_BYTES = (kVoteM / 8) * CPR * kVoteLBO;
+    constexpr uint32_t IDESC = umma_idesc_f16(DT == KVC_DTYPE_BF16 ? 1 : 0, kVoteM, kVoteTile);
+
+    const VoteTmaLayerDev& L = bd.layers[blockIdx.y];
+    const int bh = blockIdx.x;
+    const int b = bh / bd.H, h = bh - b * bd.H;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int S = L.S, W = bd.W, G = bd.G;
+    const int P = S - W;
+    const int rows_q = G * W;
+    const int n1 = (S + kVoteTile - 1) / kVoteTile, n2 = (P + kVoteTile - 1) / kVoteTile;
+    const int n_items = n1 + n2;
+
+    extern __shared__ __align__(1024) unsigned char smem_tma[];  // swizzle atoms need 1024-byte alignment
+    unsigned char* smem = smem_tma;
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem);
+    const uint32_t bar_full = smem_u32(smem + 64);        // [kWsRing]  count = 1 (+ transaction bytes of the TMA loads)
+    const uint32_t bar_empty = bar_full + 8 * kWsRing;    // [kWsRing]  count = 1 (tcgen05.commit)
+    const uint32_t bar_tfull = bar_empty + 8 * kWsRing;   // [4]        count = 1 (tcgen05.commit)
+    const uint32_t bar_tempty = bar_tfull + 8 * 4;        // [4]        count = 128 (math threads)
+    float* s_m = reinterpret_cast<float*>(smem + 512);
+    float* s_invl = reinterpret_cast<float*>(smem + 1024);
+    float* s_part = reinterpret_cast<float*>(smem + 1536);  // [4 groups][2][128]
+    unsigned char* s_q = smem + 6144;
+    unsigned char* s_ring = s_q + Q_BYTES;  // 1024-byte aligned: swizzle atoms are 8 rows x 128 B
+
+    if (tid == 0) {
+        for (int i = 0; i < kWsRing; ++i) {
+            mbar_init(bar_full + 8 * i, 1);
+            mbar_init(bar_empty + 8 * i, 1);
+        }
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(bar_tfull + 8 * i, 1);
+            mbar_init(bar_tempty + 8 * i, 128);
+        }
+        mbar_init_fence();
+    }
+    if (warp == 17) tmem_alloc(smem_u32(s_tmem), 512);
+    for (int q = tid; q < kVoteM * CPR; q += 576) {
+        int r, c;
+        tile_item<CPR>(q, r, c);
+        int4 v = make_int4(0, 0, 0, 0);
+        if (r < rows_q) {
+            const int g = r / W, w = r - g * W;
+            v = ldg128_stream(L.q + (int64_t)b * L.qsb + (int64_t)(h * G + g) * L.qsh + (int64_t)w * L.qss + c * 16);
+        }
+        *reinterpret_cast<int4*>(s_q + umma_off<CPR>(r, c)) = v;
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *s_tmem;
+    const uint32_t q_addr = smem_u32(s_q), ring_addr = smem_u32(s_ring);
+    const float c2 = bd.scale_log2e;
+
+    if (warp < 16) {
+        // ================================================================ math groups
+        const int grp = warp >> 2, gt = tid & 127;
+        const uint32_t t_lane = tmem + grp * kVoteTile + ((uint32_t)((warp & 3) * 32) << 16);
+        float m_run = -INFINITY, l_run = 0.f;
+        // the accumulator is read 16 columns at a time with the next 16 already in flight (two register sets):
+        // TMEM reads (64 B/clk per SM) and the ex2 pipe are floors of the same size and must overlap
+        uint32_t va[16], vb[16];
+        const int limit = P + ((gt < rows_q) ? (gt % W) : 0);
+        const bool row_live = (warp & 3) * 32 < rows_q;
+        int i = grp;
+        for (; i < n1; i += 4) {
+            mbar_wait(bar_tfull + 8 * grp, (uint32_t)((i >> 2) & 1));
+            tc_fence_after();
+            if (row_live && bd.pad[0] == 0) {
+                const int key0 = i * kVoteTile;
+                const bool masked = key0 + kVoteTile > P;
+                tmem_ld16_async(t_lane, va);
+#pragma unroll
+                for (int cb = 0; cb < kVoteTile; cb += 16) {
+                    uint32_t(&v)[16] = ((cb >> 4) & 1) ? vb : va;
+                    tmem_ld_wait();
+                    if (cb + 16 < kVoteTile) tmem_ld16_async(t_lane + cb + 16, ((cb >> 4) & 1) ? va : vb);
+                    float cmax = -INFINITY;
+                    if (masked) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const int key = key0 + cb + j;
+                            if (key > limit || key >= S) v[j] = 0xff800000u;
+                            cmax = fmaxf(cmax, __uint_as_float(v[j]));
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) cmax = fmaxf(cmax, __uint_as_float(v[j]));
+                    }
+                    const float m_new = fmaxf(m_run, cmax * c2);
+                    if (m_new > -INFINITY) {
+                        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 16; j += 4) {
+                            acc0 += ex2(fmaf(__uint_as_float(v[j]), c2, -m_new));
+                            acc1 += ex2(fmaf(__uint_as_float(v[j + 1]), c2, -m_new));
+                            acc2 += ex2(fmaf(__uint_as_float(v[j + 2]), c2, -m_new));
+                            acc3 += ex2(fmaf(__uint_as_float(v[j + 3]), c2, -m_new));
+                        }
+                        if (m_new != m_run) l_run *= ex2(m_run - m_new);  // the maximum settles after a few tiles
+                        l_run += (acc0 + acc1) + (acc2 + acc3);
+                        m_run = m_new;
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(bar_tempty + 8 * grp);
+        }
+        // ---------------- pass boundary: merge the four groups' partial statistics
+        s_part[(grp * 2 + 0) * 128 + gt] = m_run;
+        s_part[(grp * 2 + 1) * 128 + gt] = l_run;
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        if (tid < 128) {
+            float m = -INFINITY;
+#pragma unroll
+            for (int g4 = 0; g4 < 4; ++g4) m = fmaxf(m, s_part[(g4 * 2) * 128 + tid]);
+            float l = 0.f;
+            if (m > -INFINITY) {
+#pragma unroll
+                for (int g4 = 0; g4 < 4; ++g4) {
+                    const float mp = s_part[(g4 * 2) * 128 + tid];
+                    if (mp > -INFINITY) l += s_part[(g4 * 2 + 1) * 128 + tid] * ex2(mp - m);
+                }
+            }
+            const bool live = tid < rows_q && l > 0.f;
+            s_m[tid] = live ? m : 0.f;
+            s_invl[tid] = live ? 1.f / l : 0.f;
+        }
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+        // ---------------- pass 2: lane = key, columns = query rows
+        for (; i < n_items; i += 4) {
+            mbar_wait(bar_tfull + 8 * grp, (uint32_t)((i >> 2) & 1));
+            tc_fence_after();
+            float vote0 = 0.f, vote1 = 0.f, vote2 = 0.f, vote3 = 0.f;
+            if (bd.pad[0] == 0) tmem_ld16_async(t_lane, va);
+#pragma unroll
+            for (int cb = 0; cb < kVoteM; cb += 16) {
+                if (cb < rows_q && bd.pad[0] == 0) {  // warp-uniform: padding query rows never vote
+                    uint32_t(&v)[16] = ((cb >> 4) & 1) ? vb : va;
+                    tmem_ld_wait();
+                    if (cb + 16 < rows_q) tmem_ld16_async(t_lane + cb + 16, ((cb >> 4) & 1) ? va : vb);
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        const float4 mm = *reinterpret_cast<const float4*>(s_m + cb + j);
+                        const float4 il = *reinterpret_cast<const float4*>(s_invl + cb + j);
+                        vote0 = fmaf(ex2(fmaf(__uint_as_float(v[j + 0]), c2, -mm.x)), il.x, vote0);
+                        vote1 = fmaf(ex2(fmaf(__uint_as_float(v[j + 1]), c2, -mm.y)), il.y, vote1);
+                        vote2 = fmaf(ex2(fmaf(__uint_as_float(v[j + 2]), c2, -mm.z)), il.z, vote2);
+                        vote3 = fmaf(ex2(fmaf(__uint_as_float(v[j + 3]), c2, -mm.w)), il.w, vote3);
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(bar_tempty + 8 * grp);
+            const int key = (i - n1) * kVoteTile + gt;
+            if (key < P) {
+                Key* out = reinterpret_cast<Key*>(L.votes) + (int64_t)bh * P;
+                out[key] = (Key)Tr::to_raw((vote0 + vote1) + (vote2 + vote3));
+            }
+        }
+    } else if (warp == 16) {
+        // ================================================================ TMA producer (one thread)
+        if (lane == 0) {
+            for (int i = 0; i < n_items; ++i) {
+                const int slot = i % kWsRing;
+                mbar_wait(bar_empty + 8 * slot, (uint32_t)(((i / kWsRing) & 1) ^ 1));  // fresh barrier: passes
+                const int t = i < n1 ? i : i - n1;
+                mbar_arrive_expect_tx(bar_full + 8 * slot, TILE_BYTES);
+#pragma unroll
+                for (int kh = 0; kh < KH; ++kh)  // rows beyond S are zero-filled by the TMA unit
+                    tma_load_4d(ring_addr + slot * TILE_BYTES + kh * BOX_BYTES, &L.map, kh * 64, t * kVoteTile, h, b,
+                                bar_full + 8 * slot);
+            }
+        }
+    } else if (warp == 17 && lane == 0) {
+        // ================================================================ MMA issuer
+        for (int i = 0; i < n_items; ++i) {
+            const int slot = i % kWsRing, acc = i & 3;
+            mbar_wait(bar_tempty + 8 * acc, (uint32_t)(((i >> 2) & 1) ^ 1));  // accumulator drained (fresh: passes)
+            mbar_wait(bar_full + 8 * slot, (uint32_t)((i / kWsRing) & 1));    // tile landed
+            tc_fence_after();
+            const bool keys_are_rows = i >= n1;
+            const uint32_t kb = ring_addr + slot * TILE_BYTES;
+            if (bd.pad[0] < 2) {
+#pragma unroll
+                for (int ks = 0; ks < CPR / 2; ++ks) {
+                    // keys: 128B-swizzled K-major box (8-row groups 1024 B apart), 32 bytes per K step inside the
+                    // box; queries: dense no-swizzle core matrices
+                    const uint64_t kd = umma_smem_desc_sw128(kb + (ks >> 2) * BOX_BYTES + (ks & 3) * 32);
+                    const uint64_t qd = umma_smem_desc(q_addr + ks * 2 * kVoteLBO, kVoteLBO, CPR * kVoteLBO);
+                    umma_f16(tmem + acc * kVoteTile, keys_are_rows ? kd : qd, keys_are_rows ? qd : kd, IDESC,
+                             ks > 0 ? 1u : 0u);
+                }
+            }
+            umma_commit(bar_tfull + 8 * acc);
+            umma_commit(bar_empty + 8 * slot);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 17) tmem_dealloc(tmem, 512);
 }
 
 }  // namespace kvc
