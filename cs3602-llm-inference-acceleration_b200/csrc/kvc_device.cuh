@@ -326,6 +326,50 @@ __device__ __forceinline__ void block_radix_select(const Key* __restrict__ keys,
 }
 
 
+// ---------------------------------------------------------------- per-row scores from global memory
+// Calls emit(i, raw) for every element of src[0..R) (dtype bits, 2 or 4 bytes): 16-byte loads, 4 in flight per
+// thread (a one-element-per-thread loop is latency-bound: profiles/r01_slab_ncu_full_c5_before_vec.json — 48 % of
+// stall samples on 2-byte loads).  Lines that straddle the ends are read element by element; short arrays keep
+// one element per thread so that every thread is busy.
+template <int DT, int NT, typename Emit>
+__device__ __forceinline__ void load_keys_vectorised(const typename Traits<DT>::Key* src, int R,
+                                                     typename Traits<DT>::Key* /*keys*/, Emit emit) {
+    using Key = typename Traits<DT>::Key;
+    constexpr int KV = 16 / (int)sizeof(Key);
+    constexpr int U = 4;
+    const int tid = threadIdx.x;
+    if (R < 8 * NT) {
+        for (int i = tid; i < R; i += NT) emit(i, (uint32_t)src[i]);
+        return;
+    }
+    const int a = (int)(((uintptr_t)src & 15) / sizeof(Key));  // elements of the first line before the array
+    const int4* lines = reinterpret_cast<const int4*>((uintptr_t)src & ~(uintptr_t)15);
+    const int nline = (a + R + KV - 1) / KV;
+    for (int c0 = tid; c0 < nline; c0 += NT * U) {
+        int4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int c = c0 + u * NT;
+            const bool whole = c < nline && c * KV - a >= 0 && (c + 1) * KV - a <= R;
+            v[u] = whole ? __ldg(lines + c) : make_int4(0, 0, 0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int c = c0 + u * NT;
+            if (c >= nline) continue;
+            const int i0 = c * KV - a;
+            if (i0 >= 0 && i0 + KV <= R) {
+                const Key* kk = reinterpret_cast<const Key*>(&v[u]);
+#pragma unroll
+                for (int e = 0; e < KV; ++e) emit(i0 + e, (uint32_t)kk[e]);
+            } else {
+                for (int e = 0; e < KV; ++e)
+                    if (i0 + e >= 0 && i0 + e < R) emit(i0 + e, (uint32_t)src[i0 + e]);
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------- snapkv score transform
 // keys[0..R) hold the RAW norms (dtype bits) and misc[kMiscMaxRaw] their maximum.  Rewrites them
 // in place as descending-order radix keys of

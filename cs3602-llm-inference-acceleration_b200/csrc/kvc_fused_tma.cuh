@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(NT, MINB) kvc_fused_tma_kernel(const __grid_co
         // ---------------------------------------------------------- caller-supplied scores: pool -> keep the highest
         for (int i = tid; i < kHistBins; i += NT) hist[i] = 0;
         const Key* src = reinterpret_cast<const Key*>(L.idx_in) + (int64_t)bh * R;
-        for (int i = tid; i < R; i += NT) keys[i] = src[i];
+        load_keys_vectorised<DT, NT>(src, R, keys, [&](int i, uint32_t raw) { keys[i] = (Key)raw; });
         __syncthreads();
         snapkv_transform<DT, NT>(keys, R, L.pool, hist, misc, /*invert=*/false);
         block_radix_select<Key, NT>(keys, R, ksel, hist, misc, sidx, L.lo);

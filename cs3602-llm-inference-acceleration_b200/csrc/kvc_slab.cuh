@@ -240,53 +240,16 @@ __global__ void __launch_bounds__(NT, MINB) kvc_slab_compress_kernel(const __gri
         const bool snap = (score == KVC_SCORE_SNAPKV_POOL);
         const bool desc = (score == KVC_SCORE_L2_HIGH);
         uint32_t local_max = 0;
-        {
-            // 16-byte loads of the stored norms, 4 in flight per thread (the loop is latency-bound
-            // otherwise: profiles/r01_slab_c5 — 48 % of stall samples on 2-byte loads).  Lines that
-            // straddle the region's ends are read element by element.
-            constexpr int KV = 16 / (int)sizeof(Key);
-            constexpr int U = 4;
-            const Key* nreg = nbase + L.lo;
-            const int a = (int)(((uintptr_t)nreg & 15) / sizeof(Key));  // elements of the first line before the region
-            const int4* lines = reinterpret_cast<const int4*>((uintptr_t)nreg & ~(uintptr_t)15);
-            const int nline = (a + R + KV - 1) / KV;
-            auto emit = [&](int i, uint32_t raw) {
-                if (snap) {
-                    keys[i] = (Key)raw;
-                    local_max = max(local_max, raw);
-                } else {
-                    const Key key = ordered_key<Key>(raw, desc);
-                    keys[i] = key;
-                    atomicAdd(&hist[(uint32_t)key >> kShift0], 1u);
-                }
-            };
-            if (R < 8 * NT) {  // short regions (steady-state decode): one key per thread keeps every thread busy
-                for (int i = tid; i < R; i += NT) emit(i, (uint32_t)nreg[i]);
-            } else
-            for (int c0 = tid; c0 < nline; c0 += NT * U) {
-                int4 v[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int c = c0 + u * NT;
-                    const bool whole = c < nline && c * KV - a >= 0 && (c + 1) * KV - a <= R;
-                    v[u] = whole ? __ldg(lines + c) : make_int4(0, 0, 0, 0);
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int c = c0 + u * NT;
-                    if (c >= nline) continue;
-                    const int i0 = c * KV - a;
-                    if (i0 >= 0 && i0 + KV <= R) {
-                        const Key* kk = reinterpret_cast<const Key*>(&v[u]);
-#pragma unroll
-                        for (int e = 0; e < KV; ++e) emit(i0 + e, (uint32_t)kk[e]);
-                    } else {
-                        for (int e = 0; e < KV; ++e)
-                            if (i0 + e >= 0 && i0 + e < R) emit(i0 + e, (uint32_t)nreg[i0 + e]);
-                    }
-                }
+        load_keys_vectorised<DT, NT>(nbase + L.lo, R, keys, [&](int i, uint32_t raw) {
+            if (snap) {
+                keys[i] = (Key)raw;
+                local_max = max(local_max, raw);
+            } else {
+                const Key key = ordered_key<Key>(raw, desc);
+                keys[i] = key;
+                atomicAdd(&hist[(uint32_t)key >> kShift0], 1u);
             }
-        }
+        });
         if (snap) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));

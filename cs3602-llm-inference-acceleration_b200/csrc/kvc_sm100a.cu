@@ -719,7 +719,8 @@ int kvc_compress_layers_ws(const kvc_shape* shape, int32_t n_layers, const kvc_l
         bool given_score = false;
         for (int l = 0; l < nl; ++l) given_score |= plans[l0 + l].k_sel > 0 && plans[l0 + l].score == KVC_SCORE_GIVEN_SCORE;
         if (tma_supported_cpr(cpr) && (given_score || !env_int("KVC_FORCE_LDG", 0))) {
-            tp = plan_tma(dt, cpr, max_region, bd.idx_cap, any_select);
+            // caller-supplied scores: no K scan, the launch moves only the kept rows -> residency over slot depth
+            tp = plan_tma(dt, cpr, max_region, bd.idx_cap, any_select, /*light_traffic=*/given_score);
             if (any_select && workspace != nullptr && !onchip_plan_ok(tp, cpr, false)) {
                 // keys and kept indices go to the workspace; shared memory keeps the histogram and the slots
                 const WsLayout w = ws_layout(dt, max_region, bd.idx_cap);
