@@ -1072,14 +1072,18 @@ static int launch_vote_tma(const kvc_shape* shape, int32_t n_layers, const kvc_v
     using Fn = void (*)(const VoteTmaBatchDev);
     Fn fn = nullptr;
     if (dt == KVC_DTYPE_BF16)
-        fn = cpr == 8 ? kvc_snapkv_vote_tma_kernel<KVC_DTYPE_BF16, 8> : kvc_snapkv_vote_tma_kernel<KVC_DTYPE_BF16, 16>;
+        fn = cpr == 8 ? kvc_snapkv_vote_tma_kernel<KVC_DTYPE_BF16, 8>
+                      : cpr == 10 ? kvc_snapkv_vote_tma_kernel<KVC_DTYPE_BF16, 10> : kvc_snapkv_vote_tma_kernel<KVC_DTYPE_BF16, 16>;
     else
-        fn = cpr == 8 ? kvc_snapkv_vote_tma_kernel<KVC_DTYPE_F16, 8> : kvc_snapkv_vote_tma_kernel<KVC_DTYPE_F16, 16>;
-    const size_t smem = 6144 + (size_t)(kVoteM / 8) * cpr * kVoteLBO + (size_t)kWsRing * (cpr / 8) * kVoteTile * 128;
+        fn = cpr == 8 ? kvc_snapkv_vote_tma_kernel<KVC_DTYPE_F16, 8>
+                      : cpr == 10 ? kvc_snapkv_vote_tma_kernel<KVC_DTYPE_F16, 10> : kvc_snapkv_vote_tma_kernel<KVC_DTYPE_F16, 16>;
+    const size_t tile = (size_t)(cpr / 8) * kVoteTile * 128 + (size_t)(cpr % 8) * kVoteTile * 16;
+    const size_t smem = 6144 + (size_t)(kVoteM / 8) * cpr * kVoteLBO + (size_t)kWsRing * tile;
     int st = ensure_tma_attrs((const void*)fn, shape->device);
     if (st != KVC_OK) return st;
     for (int l0 = 0; l0 < n_layers; l0 += 32) {
         const int nl = (n_layers - l0) < 32 ? (n_layers - l0) : 32;
+        static_assert(sizeof(VoteTmaBatchDev) < 32 * 1024, "kernel parameters are limited to 32 KB");
         VoteTmaBatchDev bd;
         memset(&bd, 0, sizeof(bd));
         bd.B = B;
@@ -1101,6 +1105,14 @@ static int launch_vote_tma(const kvc_shape* shape, int32_t n_layers, const kvc_v
                                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return KVC_ERR_UNSUPPORTED;
+            if (cpr % 8) {  // D = 80: the last 16 elements of every row through a 32-byte-swizzled box
+                const cuuint32_t box_tail[4] = {16, (cuuint32_t)kVoteTile, 1, 1};
+                const CUresult r2 = encode(&d.map_tail, dt == KVC_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                                           4, const_cast<void*>(v.k_in), dims, strides, box_tail, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                           CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r2 != CUDA_SUCCESS) return KVC_ERR_UNSUPPORTED;
+            }
             d.q = (const char*)v.q_obs;
             d.votes = (char*)v.votes_out;
             d.qsb = v.q_stride_b * 2;
@@ -1145,8 +1157,8 @@ int kvc_snapkv_vote(const kvc_shape* shape, int32_t n_layers, const kvc_vote_lay
     else
         fn = cpr == 8 ? kvc_snapkv_vote_kernel<KVC_DTYPE_F16, 8> : cpr == 10 ? kvc_snapkv_vote_kernel<KVC_DTYPE_F16, 10>
                                                                             : kvc_snapkv_vote_kernel<KVC_DTYPE_F16, 16>;
-    if ((cpr == 8 || cpr == 16) && env_int("KVC_VOTE_TMA", 1)) {
-        // head_dim 64 / 128: key tiles arrive through TMA tensor loads; strided layouts a tensor map cannot
+    if (env_int("KVC_VOTE_TMA", 1)) {
+        // head_dim 64 / 80 / 128: key tiles arrive through TMA tensor loads; strided layouts a tensor map cannot
         // describe fall through to the cp.async-fed kernel below
         st = launch_vote_tma(shape, n_layers, layers, group, window, cpr, stream);
         if (st != KVC_ERR_UNSUPPORTED) return st;

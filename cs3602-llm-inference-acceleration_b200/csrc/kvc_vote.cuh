@@ -627,6 +627,7 @@ __global__ void __launch_bounds__(672, 1) kvc_snapkv_vote_ws_kernel(const __grid
 // softmax math exactly as above and one thread issues the MMAs (keys: SW128 descriptors, queries: no-swizzle).
 struct VoteTmaLayerDev {
     alignas(64) CUtensorMap map;  // keys [B,H,S,D] as a 4-D tensor (D, S, H, B), box (64, 128, 1, 1), SWIZZLE_128B
+    alignas(64) CUtensorMap map_tail;  // D % 64 == 16 (D = 80): box (16, 128, 1, 1), SWIZZLE_32B, for the last 16 elements
     const char* q;
     char* votes;
     int64_t qsb, qsh, qss;
@@ -646,6 +647,16 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst_smem, const CUtensorMap
         ::"r"(dst_smem), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
         : "memory");
 }
+// K-major, 32-byte swizzle: rows 32 B apart inside an 8-row atom, atoms 256 B apart (SBO), LBO = 16 B.
+__device__ __forceinline__ uint64_t umma_smem_desc_sw32(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(256 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)6 << 61;  // layout type SWIZZLE_32B
+    return d;
+}
 // K-major, 128-byte swizzle: rows 128 B apart inside an 8-row atom, atoms 1024 B apart (SBO), LBO = 16 B.
 __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr) {
     uint64_t d = 0;
@@ -662,10 +673,12 @@ __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __gri
     using Tr = Traits<DT>;
     using Key = typename Tr::Key;
     static_assert(DT != KVC_DTYPE_F32, "the vote runs on 16-bit caches (kind::f16)");
-    static_assert(CPR % 8 == 0, "128-byte swizzled boxes: head_dim * 2 bytes must be a multiple of 128");
+    static_assert(CPR % 8 == 0 || CPR % 8 == 2, "key rows = 128-byte boxes (+ one 32-byte box for D % 64 == 16)");
     constexpr int KH = CPR / 8;                       // 64-element (128-byte) boxes per key row
+    constexpr int REM = CPR % 8;                      // 16-byte chunks left over: 0, or 2 (one 32-byte-swizzled box)
     constexpr int BOX_BYTES = kVoteTile * 128;        // one box: 128 rows x 128 B, 128B-swizzled
-    constexpr int TILE_BYTES = KH * BOX_BYTES;
+    constexpr int TAIL_BYTES = kVoteTile * 16 * REM;  // tail box: 128 rows x 32 B, 32B-swizzled
+    constexpr int TILE_BYTES = KH * BOX_BYTES + TAIL_BYTES;
     constexpr int Q_BYTES = (kVoteM / 8) * CPR * kVoteLBO;
     constexpr uint32_t IDESC = umma_idesc_f16(DT == KVC_DTYPE_BF16 ? 1 : 0, kVoteM, kVoteTile);
 
@@ -840,6 +853,9 @@ __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __gri
                 for (int kh = 0; kh < KH; ++kh)  // rows beyond S are zero-filled by the TMA unit
                     tma_load_4d(ring_addr + slot * TILE_BYTES + kh * BOX_BYTES, &L.map, kh * 64, t * kVoteTile, h, b,
                                 bar_full + 8 * slot);
+                if (REM > 0)
+                    tma_load_4d(ring_addr + slot * TILE_BYTES + KH * BOX_BYTES, &L.map_tail, KH * 64, t * kVoteTile, h, b,
+                                bar_full + 8 * slot);
             }
         }
     } else if (warp == 17 && lane == 0) {
@@ -856,7 +872,8 @@ __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __gri
                 for (int ks = 0; ks < CPR / 2; ++ks) {
                     // keys: 128B-swizzled K-major box (8-row groups 1024 B apart), 32 bytes per K step inside the
                     // box; queries: dense no-swizzle core matrices
-                    const uint64_t kd = umma_smem_desc_sw128(kb + (ks >> 2) * BOX_BYTES + (ks & 3) * 32);
+                    const uint64_t kd = (ks >> 2) < KH ? umma_smem_desc_sw128(kb + (ks >> 2) * BOX_BYTES + (ks & 3) * 32)
+                                                       : umma_smem_desc_sw32(kb + KH * BOX_BYTES);
                     const uint64_t qd = umma_smem_desc(q_addr + ks * 2 * kVoteLBO, kVoteLBO, CPR * kVoteLBO);
                     umma_f16(tmem + acc * kVoteTile, keys_are_rows ? kd : qd, keys_are_rows ? qd : kd, IDESC,
                              ks > 0 ? 1u : 0u);
