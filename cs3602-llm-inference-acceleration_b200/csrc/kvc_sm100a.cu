@@ -22,6 +22,7 @@
 #include "kvc_fused_tma.cuh"
 #include "kvc_slab.cuh"
 #include "kvc_vote.cuh"
+#include "kvc_vote_split.cuh"
 
 #define KVC_STR2(x) #x
 #define KVC_STR(x) KVC_STR2(x)
@@ -1129,8 +1130,135 @@ static int launch_vote_tma(const kvc_shape* shape, int32_t n_layers, const kvc_v
     return KVC_OK;
 }
 
+// ---- persistent split-sequence vote (kvc_vote_split.cuh) -----------------------------------------------------
+// Slices per unit: a CTA holds ~2-3 slices between their passes, 148 CTAs at once, and all of it has to stay in L2.
+static int vote_slices(int cpr, int seq_len) {
+    const int n1 = (seq_len + kVoteTile - 1) / kVoteTile;
+    const int tile_bytes = cpr * 16 * kVoteTile;
+    int ts = env_int("KVC_VOTE_TS", 0);
+    if (ts <= 0) ts = std::max(4, (int)(((size_t)40 << 20) / 148 / tile_bytes));  // ~40 MB of fresh key tiles chip-wide
+    int ns = (n1 + ts - 1) / ts;
+    return std::min(std::max(ns, 1), 64);
+}
+struct VoteWsLayout {
+    int64_t units, tickets;
+    size_t off_final, off_part, bytes;
+};
+static VoteWsLayout vote_ws_layout(const kvc_shape* shape, int nl, const kvc_vote_layer* layers, int cpr) {
+    VoteWsLayout w{};
+    w.units = (int64_t)shape->batch * shape->heads * nl;
+    for (int l = 0; l < nl; ++l) w.tickets += (int64_t)shape->batch * shape->heads * vote_slices(cpr, layers[l].seq_len);
+    w.off_final = (size_t)((64 + 8 * w.units + 255) & ~(int64_t)255);  // ticket counter, arrivals, ready flags
+    w.off_part = w.off_final + (size_t)w.units * 1024;
+    w.bytes = w.off_part + (size_t)w.tickets * 1024;
+    return w;
+}
+
+static int launch_vote_split(const kvc_shape* shape, int32_t n_layers, const kvc_vote_layer* layers, int32_t group,
+                             int32_t window, int cpr, void* workspace, int64_t workspace_bytes, void* stream) {
+    EncodeTiledFn encode = tensor_map_encoder();
+    if (!encode) return KVC_ERR_UNSUPPORTED;
+    const int B = shape->batch, H = shape->heads, D = shape->head_dim, dt = shape->dtype;
+    using Fn = void (*)(const VoteSplitBatchDev);
+    Fn fn = nullptr;
+    if (dt == KVC_DTYPE_BF16)
+        fn = cpr == 8 ? kvc_snapkv_vote_split_kernel<KVC_DTYPE_BF16, 8>
+                      : cpr == 10 ? kvc_snapkv_vote_split_kernel<KVC_DTYPE_BF16, 10> : kvc_snapkv_vote_split_kernel<KVC_DTYPE_BF16, 16>;
+    else
+        fn = cpr == 8 ? kvc_snapkv_vote_split_kernel<KVC_DTYPE_F16, 8>
+                      : cpr == 10 ? kvc_snapkv_vote_split_kernel<KVC_DTYPE_F16, 10> : kvc_snapkv_vote_split_kernel<KVC_DTYPE_F16, 16>;
+    const size_t tile = (size_t)(cpr / 8) * kVoteTile * 128 + (size_t)(cpr % 8) * kVoteTile * 16;
+    const size_t smem = kSpHeader + (2 + kSpRing) * tile;
+    int st = ensure_tma_attrs((const void*)fn, shape->device);
+    if (st != KVC_OK) return st;
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, shape->device) != cudaSuccess || sms <= 0) sms = 148;
+    const CUtensorMapDataType tdt = dt == KVC_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    size_t ws_used = 0;
+    for (int l0 = 0; l0 < n_layers; l0 += 32) {
+        const int nl = (n_layers - l0) < 32 ? (n_layers - l0) : 32;
+        static_assert(sizeof(VoteSplitBatchDev) < 32 * 1024, "kernel parameters are limited to 32 KB");
+        const VoteWsLayout w = vote_ws_layout(shape, nl, layers + l0, cpr);
+        if (w.tickets > 0x7fffffff) return KVC_ERR_TOO_LARGE;
+        if (ws_used + w.bytes > (size_t)workspace_bytes) return KVC_ERR_INVALID_ARG;
+        VoteSplitBatchDev bd;
+        memset(&bd, 0, sizeof(bd));
+        bd.B = B;
+        bd.H = H;
+        bd.G = group;
+        bd.W = window;
+        bd.scale_log2e = 1.4426950408889634f / sqrtf((float)D);
+        bd.n_layers = nl;
+        bd.total = (int32_t)w.tickets;
+        bd.pend_max = std::min(std::max(env_int("KVC_VOTE_PEND", 2), 1), kSpPend);
+        bd.ws = reinterpret_cast<uint32_t*>((char*)workspace + ws_used);
+        bd.off_final = (int64_t)w.off_final;
+        bd.off_part = (int64_t)w.off_part;
+        ws_used += (w.bytes + 255) & ~(size_t)255;
+        int64_t tickets = 0;
+        for (int l = 0; l < nl; ++l) {
+            const kvc_vote_layer& v = layers[l0 + l];
+            VoteSplitLayerDev& d = bd.layers[l];
+            const cuuint32_t estr[4] = {1, 1, 1, 1};
+            const cuuint64_t kdims[4] = {(cuuint64_t)D, (cuuint64_t)v.seq_len, (cuuint64_t)H, (cuuint64_t)B};
+            const cuuint64_t kstr[3] = {(cuuint64_t)v.k_stride_s * 2, (cuuint64_t)v.k_stride_h * 2, (cuuint64_t)v.k_stride_b * 2};
+            const cuuint64_t qdims[4] = {(cuuint64_t)D, (cuuint64_t)window, (cuuint64_t)H * group, (cuuint64_t)B};
+            const cuuint64_t qstr[3] = {(cuuint64_t)v.q_stride_s * 2, (cuuint64_t)v.q_stride_h * 2, (cuuint64_t)v.q_stride_b * 2};
+            const cuuint32_t kbox[4] = {64, (cuuint32_t)kVoteTile, 1, 1}, kbox_tail[4] = {16, (cuuint32_t)kVoteTile, 1, 1};
+            const cuuint32_t qbox[4] = {64, (cuuint32_t)window, (cuuint32_t)group, 1};
+            const cuuint32_t qbox_tail[4] = {16, (cuuint32_t)window, (cuuint32_t)group, 1};
+            auto enc = [&](CUtensorMap* m, const void* base, const cuuint64_t* dims, const cuuint64_t* str,
+                           const cuuint32_t* box, CUtensorMapSwizzle sw) {
+                return encode(m, tdt, 4, const_cast<void*>(base), dims, str, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+            };
+            if (!enc(&d.kmap, v.k_in, kdims, kstr, kbox, CU_TENSOR_MAP_SWIZZLE_128B)) return KVC_ERR_UNSUPPORTED;
+            if (!enc(&d.qmap, v.q_obs, qdims, qstr, qbox, CU_TENSOR_MAP_SWIZZLE_128B)) return KVC_ERR_UNSUPPORTED;
+            if (cpr % 8) {  // D = 80: the last 16 elements of every row through 32-byte-swizzled boxes
+                if (!enc(&d.kmap_tail, v.k_in, kdims, kstr, kbox_tail, CU_TENSOR_MAP_SWIZZLE_32B)) return KVC_ERR_UNSUPPORTED;
+                if (!enc(&d.qmap_tail, v.q_obs, qdims, qstr, qbox_tail, CU_TENSOR_MAP_SWIZZLE_32B)) return KVC_ERR_UNSUPPORTED;
+            }
+            d.votes = (char*)v.votes_out;
+            d.S = v.seq_len;
+            d.first = (int32_t)tickets;
+            d.ns = vote_slices(cpr, v.seq_len);
+            tickets += (int64_t)B * H * d.ns;
+            if (l == 0) bd.per_layer = (int32_t)tickets;
+            else if (d.ns != bd.layers[0].ns) bd.per_layer = 0;
+        }
+        cudaError_t err = cudaMemsetAsync(bd.ws, 0, w.off_final, (cudaStream_t)stream);  // counters and flags
+        if (err != cudaSuccess) return cuda_fail(err, "vote workspace memset");
+        const unsigned grid = (unsigned)std::min<int64_t>(tickets, sms);
+        fn<<<grid, kSpThreads, smem, (cudaStream_t)stream>>>(bd);
+        err = cudaGetLastError();
+        if (err != cudaSuccess) return cuda_fail(err, "kvc_snapkv_vote_split_kernel launch");
+        g_launches.fetch_add(1);
+    }
+    return KVC_OK;
+}
+
+int64_t kvc_vote_workspace_bytes(const kvc_shape* shape, int32_t n_layers, const kvc_vote_layer* layers) {
+    int cpr = 0;
+    if (check_shape(shape, &cpr) != KVC_OK || n_layers <= 0 || !layers) return 0;
+    if (shape->dtype == KVC_DTYPE_F32 || (cpr != 8 && cpr != 10 && cpr != 16)) return 0;
+    // Opt-in (KVC_VOTE_SPLIT=1): the split form halves the HBM traffic of the vote but, at the slice sizes L2 can
+    // hold, its cross-CTA hand-offs cost more than the second HBM read (profiles/r01_vote_split_sweep.json).
+    if (!env_int("KVC_VOTE_SPLIT", 0)) return 0;
+    size_t total = 0;
+    for (int l0 = 0; l0 < n_layers; l0 += 32) {
+        const int nl = (n_layers - l0) < 32 ? (n_layers - l0) : 32;
+        total += (vote_ws_layout(shape, nl, layers + l0, cpr).bytes + 255) & ~(size_t)255;
+    }
+    return (int64_t)total;
+}
+
 int kvc_snapkv_vote(const kvc_shape* shape, int32_t n_layers, const kvc_vote_layer* layers, int32_t group,
                     int32_t window, void* stream) {
+    return kvc_snapkv_vote_ws(shape, n_layers, layers, group, window, nullptr, 0, stream);
+}
+
+int kvc_snapkv_vote_ws(const kvc_shape* shape, int32_t n_layers, const kvc_vote_layer* layers, int32_t group,
+                       int32_t window, void* workspace, int64_t workspace_bytes, void* stream) {
     int cpr = 0;
     int st = check_shape(shape, &cpr);
     if (st != KVC_OK) return st;
@@ -1157,6 +1285,12 @@ int kvc_snapkv_vote(const kvc_shape* shape, int32_t n_layers, const kvc_vote_lay
     else
         fn = cpr == 8 ? kvc_snapkv_vote_kernel<KVC_DTYPE_F16, 8> : cpr == 10 ? kvc_snapkv_vote_kernel<KVC_DTYPE_F16, 10>
                                                                             : kvc_snapkv_vote_kernel<KVC_DTYPE_F16, 16>;
+    if (workspace != nullptr && workspace_bytes > 0 && env_int("KVC_VOTE_TMA", 1)) {
+        // with a workspace: persistent CTAs, every (b, h) split along S so that the second pass hits L2
+        if (((uintptr_t)workspace & 255) != 0) return KVC_ERR_INVALID_ARG;
+        st = launch_vote_split(shape, n_layers, layers, group, window, cpr, workspace, workspace_bytes, stream);
+        if (st != KVC_ERR_UNSUPPORTED) return st;
+    }
     if (env_int("KVC_VOTE_TMA", 1)) {
         // head_dim 64 / 80 / 128: key tiles arrive through TMA tensor loads; strided layouts a tensor map cannot
         // describe fall through to the cp.async-fed kernel below

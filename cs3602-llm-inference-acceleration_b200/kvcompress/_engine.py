@@ -30,7 +30,7 @@ _PLAN = struct.Struct("8i")        # kvc_layer_plan: seq_len sink sel_lo sel_hi 
 _IO = struct.Struct("4P6q3P")      # kvc_layer_io: k_in v_in k_out v_out | 6 strides | idx_out idx_in score_in
 _SHAPE = struct.Struct("5i")       # kvc_shape: batch heads head_dim dtype device
 assert _PLAN.size == 32 and _IO.size == 104 and _SHAPE.size == 20
-KVC_ABI_VERSION = 3
+KVC_ABI_VERSION = 4
 
 KVC_DTYPE = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
 KVC_OK = 0
@@ -86,6 +86,11 @@ def load_library():
     lib.kvc_snapkv_vote.restype = ctypes.c_int
     lib.kvc_snapkv_vote.argtypes = [ctypes.c_char_p, ctypes.c_int32, ctypes.c_char_p, ctypes.c_int32, ctypes.c_int32,
                                     ctypes.c_void_p]
+    lib.kvc_vote_workspace_bytes.restype = ctypes.c_int64
+    lib.kvc_vote_workspace_bytes.argtypes = [ctypes.c_char_p, ctypes.c_int32, ctypes.c_char_p]
+    lib.kvc_snapkv_vote_ws.restype = ctypes.c_int
+    lib.kvc_snapkv_vote_ws.argtypes = [ctypes.c_char_p, ctypes.c_int32, ctypes.c_char_p, ctypes.c_int32, ctypes.c_int32,
+                                       ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
     if lib.kvc_abi_version() != KVC_ABI_VERSION:
         raise RuntimeError(f"{_LIB_NAME}: ABI version {lib.kvc_abi_version()} != {KVC_ABI_VERSION} — rebuild the library")
     _lib = lib
@@ -379,7 +384,12 @@ def snapkv_votes(layers: Sequence[Tuple[torch.Tensor, torch.Tensor]], window: in
         _VOTE.pack_into(buf, m * _VOTE.size, keys.data_ptr(), q.data_ptr(), votes.data_ptr(), ks[0], ks[1], ks[2],
                         qs[0], qs[1], qs[2], keys.size(2), 0)
     shape = _SHAPE.pack(B, H, D, KVC_DTYPE[k0.dtype], k0.device.index)
-    status = load_library().kvc_snapkv_vote(shape, len(layers), bytes(buf), G, window,
-                                            ctypes.c_void_p(_stream_ptr(k0.device)))
+    lib, desc = load_library(), bytes(buf)
+    # long sequences: every (b, h) is split along S over several CTAs that meet through this scratch buffer
+    need = int(lib.kvc_vote_workspace_bytes(shape, len(layers), desc))
+    ws = torch.empty(need, dtype=torch.uint8, device=k0.device) if need else None
+    status = lib.kvc_snapkv_vote_ws(shape, len(layers), desc, G, window,
+                                    ctypes.c_void_p(ws.data_ptr() if need else 0), need,
+                                    ctypes.c_void_p(_stream_ptr(k0.device)))
     _check(status, "kvc_snapkv_vote")
     return out

@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define KVC_ABI_VERSION 3
+#define KVC_ABI_VERSION 4
 
 typedef enum kvc_status {
     KVC_OK = 0,
@@ -156,6 +156,13 @@ typedef struct kvc_vote_layer {
 } kvc_vote_layer;
 int kvc_snapkv_vote(const kvc_shape* shape, int32_t n_layers, const kvc_vote_layer* layers, int32_t group,
                     int32_t window, void* stream);
+/* With a device workspace of kvc_vote_workspace_bytes(...) bytes (256-byte aligned) the vote runs as persistent CTAs
+ * that split every (b,h) along S and exchange their softmax row statistics through the workspace, so that the second
+ * read of a key tile hits L2 instead of HBM.  Same votes up to fp32 summation order, reproducible run to run; without
+ * a workspace (kvc_snapkv_vote) one CTA walks a whole sequence.  The workspace is scratch: nothing survives the call. */
+int64_t kvc_vote_workspace_bytes(const kvc_shape* shape, int32_t n_layers, const kvc_vote_layer* layers);
+int kvc_snapkv_vote_ws(const kvc_shape* shape, int32_t n_layers, const kvc_vote_layer* layers, int32_t group,
+                       int32_t window, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Slab cache: the container step on both sides of the compress call.

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_library_metadata_and_argument_checks():
     lib = _engine.load_library()
-    assert lib.kvc_abi_version() == 3
+    assert lib.kvc_abi_version() == 4
     assert b"sm_100a" in lib.kvc_build_info()
     assert lib.kvc_status_string(0) == b"ok"
     assert lib.kvc_launch_count() >= 0

@@ -55,6 +55,45 @@ def test_votes_match_torch_reference(B, H, G, W, S, D, dtype):
         assert torch.all(want.sum(-1) <= G * W + 1e-3)
 
 
+SPLIT_CASES = [
+    # B, H, G, W, S, D, dtype, key tiles per slice (0: the library's choice)
+    (2, 2, 4, 32, 1040, 128, torch.bfloat16, 1),   # 9 one-tile slices per unit; the last holds window keys only
+    (2, 3, 1, 32, 1500, 80, torch.bfloat16, 4),    # 12 tiles -> 3 slices, 32 live query rows
+    (1, 2, 2, 16, 2100, 64, torch.float16, 8),     # 17 tiles -> 3 slices of 6, 6, 5
+    (1, 1, 4, 32, 20000, 128, torch.bfloat16, 0),
+    (4, 8, 4, 32, 3000, 128, torch.bfloat16, 2),   # more slices than SMs: CTAs loop over tickets
+]
+
+
+@pytest.mark.parametrize("pend", [1, 2, 3])
+@pytest.mark.parametrize("B,H,G,W,S,D,dtype,ts", SPLIT_CASES, ids=[f"S{c[4]}D{c[5]}ts{c[7]}" for c in SPLIT_CASES])
+def test_split_sequence_votes_match_torch_reference(B, H, G, W, S, D, dtype, ts, pend, monkeypatch):
+    """Opt-in form (KVC_VOTE_SPLIT=1): persistent CTAs, every (b, h) split along S, softmax row statistics merged
+    through the workspace.  Votes match the fp32 reference, are reproducible run to run, and agree with the shipped
+    one-CTA-per-unit kernel (no workspace) within one spacing of the cache dtype."""
+    monkeypatch.setenv("KVC_VOTE_SPLIT", "1")
+    if ts:
+        monkeypatch.setenv("KVC_VOTE_TS", str(ts))
+    monkeypatch.setenv("KVC_VOTE_PEND", str(pend))
+    gen = torch.Generator(device="cuda").manual_seed(S)
+    keys = [torch.randn(B, H, S, D, generator=gen, device="cuda").to(dtype) for _ in range(3)]
+    qs = [(1.5 * torch.randn(B, H * G, W, D, generator=gen, device="cuda")).to(dtype) for _ in range(3)]
+    n0 = _engine.launch_count()
+    votes = _engine.snapkv_votes(list(zip(keys, qs)), W)
+    assert _engine.launch_count() - n0 == 1
+    again = _engine.snapkv_votes(list(zip(keys, qs)), W)
+    ulp = 2.0 ** -8 if dtype == torch.bfloat16 else 2.0 ** -11
+    for k, q, v, v2 in zip(keys, qs, votes, again):
+        want = vote_reference(k, q, W)
+        got = v.float()
+        assert torch.all((got - want).abs() <= 2.5 * ulp * want + 1e-7), float(((got - want).abs() / (want + 1e-12)).max())
+        assert torch.equal(v, v2)
+    monkeypatch.setenv("KVC_VOTE_SPLIT", "0")
+    whole = _engine.snapkv_votes(list(zip(keys, qs)), W)
+    for v, u in zip(votes, whole):
+        assert torch.all((v.float() - u.float()).abs() <= 2.02 * ulp * u.float() + 1e-7)  # at most one spacing of the dtype
+
+
 def test_strided_keys_and_queries():
     B, H, G, W, S, D = 1, 2, 4, 32, 600, 128
     k = torch.randn(B, S, H, D, device="cuda").bfloat16().permute(0, 2, 1, 3)      # [B,S,H,D] storage
