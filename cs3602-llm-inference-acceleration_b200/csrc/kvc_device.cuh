@@ -379,6 +379,101 @@ __device__ __forceinline__ void load_keys_vectorised(const typename Traits<DT>::
 // at a time holding the previous / current / next 32 raw norms in registers (window taps are warp
 // shuffles), so the rewrite is in place without per-tile barriers; only the two segment-boundary
 // windows are read before a single __syncthreads().  All NT threads must call; ends synchronised.
+// Pooling kernels 2..9 (the reference's default is 5), R >= PK.  Every lane owns FOUR consecutive rows of a 128-row
+// block: each raw norm is turned into its score once, a window needs at most the four scores of the lane on either
+// side (two shuffles up, two down for PK = 5; the block edges come from the previous block's lane 31 and the next
+// block's lane 0, already in registers), and the taps are compile-time register indices.  ~0.9 warp instructions per
+// row against 5.3 for the one-row-per-lane form below (profiles/r01_slab_ncu_full_c4.json: 57 % of the in-place
+// kernel's samples sat in that loop).  Same left-to-right fp32 sums: a tap outside [0, R) adds +0.0f, which leaves a
+// sum that started from +0.0f unchanged bit for bit.
+template <int DT, int NT, int PK>
+__device__ __forceinline__ void snapkv_transform_rows4(typename Traits<DT>::Key* keys, int R, uint32_t* hist,
+                                                       float mxe, bool invert) {
+    using Tr = Traits<DT>;
+    using Key = typename Tr::Key;
+    constexpr int kShift0 = Tr::kKeyBits - kHistBits;
+    constexpr int NW = NT / 32;
+    constexpr int PAD = PK / 2;
+    static_assert(PK >= 2 && PK <= 9, "window reaches at most four rows to either side");
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float den = (float)PK;
+    const int blocks = (R + 127) >> 7;
+    const int bpw = (blocks + NW - 1) / NW;
+    const int w_lo = warp * bpw * 128;
+    const int w_hi = min(R, w_lo + bpw * 128);
+    auto score = [&](uint32_t raw, int i) -> float {
+        if (i < 0 || i >= R) return 0.f;
+        return invert ? round_dt<DT>(mxe - Tr::from_raw(raw)) : Tr::from_raw(raw);
+    };
+    auto load4 = [&](int i0, float (&out)[4]) {  // scores of rows i0..i0+3 (i0 a multiple of 4)
+        Key r[4] = {0, 0, 0, 0};
+        if (i0 < R) {
+            if (sizeof(Key) == 2)
+                *reinterpret_cast<uint2*>(r) = *reinterpret_cast<const uint2*>(keys + i0);
+            else
+                *reinterpret_cast<uint4*>(r) = *reinterpret_cast<const uint4*>(keys + i0);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) out[k] = score((uint32_t)r[k], i0 + k);
+    };
+    float left_edge[4], after[4], s[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int il = w_lo - 4 + k, ia = w_hi + k;
+        left_edge[k] = score(il >= 0 && il < R ? (uint32_t)keys[il] : 0u, il);
+        after[k] = score(ia >= 0 && ia < R ? (uint32_t)keys[ia] : 0u, ia);
+    }
+    load4(w_lo + 4 * lane, s);
+    __syncthreads();  // every warp holds its boundary rows before any segment is rewritten
+    for (int b0 = w_lo; b0 < w_hi; b0 += 128) {
+        float n[4];
+        if (b0 + 128 < w_hi) {
+            load4(b0 + 128 + 4 * lane, n);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) n[k] = after[k];
+        }
+        float win[12];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float up = __shfl_up_sync(0xffffffffu, s[k], 1);
+            const float dn = __shfl_down_sync(0xffffffffu, s[k], 1);
+            const float nx = __shfl_sync(0xffffffffu, n[k], 0);
+            win[k] = lane == 0 ? left_edge[k] : up;
+            win[4 + k] = s[k];
+            win[8 + k] = lane == 31 ? nx : dn;
+        }
+        const int i0 = b0 + 4 * lane;
+        Key out[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            float acc = 0.f;
+#pragma unroll
+            for (int t = 0; t < PK; ++t) acc += win[4 + r + t - PAD];
+            out[r] = ordered_key<Key>(Tr::to_raw(round_dt<DT>(acc / den)), /*descending=*/true);
+        }
+        if (i0 + 4 <= R) {
+            if (sizeof(Key) == 2)
+                *reinterpret_cast<uint2*>(keys + i0) = *reinterpret_cast<const uint2*>(out);
+            else
+                *reinterpret_cast<uint4*>(keys + i0) = *reinterpret_cast<const uint4*>(out);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            if (i0 + r < R) {
+                if (i0 + 4 > R) keys[i0 + r] = out[r];
+                atomicAdd(&hist[(uint32_t)out[r] >> kShift0], 1u);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            left_edge[k] = __shfl_sync(0xffffffffu, s[k], 31);
+            s[k] = n[k];
+        }
+    }
+    __syncthreads();
+}
+
 template <int DT, int NT>
 __device__ __forceinline__ void snapkv_transform(typename Traits<DT>::Key* keys, int R, int pk, uint32_t* hist,
                                                  int32_t* misc, bool invert = true) {
@@ -389,6 +484,14 @@ __device__ __forceinline__ void snapkv_transform(typename Traits<DT>::Key* keys,
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const float mx = Tr::from_raw((uint32_t)misc[kMiscMaxRaw]);
     const float mxe = round_dt<DT>(mx + 1e-6f);
+    if (R >= pk) {  // block-uniform
+        switch (pk) {
+            case 3: return snapkv_transform_rows4<DT, NT, 3>(keys, R, hist, mxe, invert);
+            case 5: return snapkv_transform_rows4<DT, NT, 5>(keys, R, hist, mxe, invert);
+            case 7: return snapkv_transform_rows4<DT, NT, 7>(keys, R, hist, mxe, invert);
+            default: break;  // other kernel sizes (and no pooling) take the generic form
+        }
+    }
     const bool pooling = pk > 1 && R >= pk;
     const int pad = pooling ? pk / 2 : 0;
     const int taps = pooling ? pk : 1;
