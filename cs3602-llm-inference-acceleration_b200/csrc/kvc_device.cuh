@@ -280,16 +280,26 @@ __device__ __forceinline__ void block_radix_select(const Key* __restrict__ keys,
         pbits += nb;
     }
     // prefix == T, the k-th smallest key; take every key < T and the first `krem` keys == T.
+    // Both passes read 16 bytes per lane (kVec consecutive keys), so a warp step covers 32 * kVec keys in index
+    // order: lane-major, element-minor.  (One key per lane per step cost 0.9 warp instructions per key, a fifth of
+    // the in-place kernel at 32K rows: profiles/r01_slab_ncu_full_c4.json.)
     const uint32_t T = prefix;
     const int r = (int)krem;
-    const int chunk = (((R + NW - 1) / NW) + 31) & ~31;  // tokens per warp, multiple of 32
+    constexpr int kStep = 32 * kVec;
+    const int chunk = (((R + NW - 1) / NW) + kStep - 1) / kStep * kStep;  // keys per warp, multiple of a warp step
     const int w_lo = warp * chunk;
     const int w_hi = min(R, w_lo + chunk);
     int lt = 0, eq = 0;
-    for (int i = w_lo + lane; i < w_hi; i += 32) {
-        const uint32_t key = keys[i];
-        lt += key < T;
-        eq += key == T;
+    for (int i = w_lo + lane * kVec; i < w_hi; i += kStep) {
+        const int4 raw = *reinterpret_cast<const int4*>(keys + i);  // the array is padded to 16 bytes
+        const Key* kk = reinterpret_cast<const Key*>(&raw);
+#pragma unroll
+        for (int e = 0; e < kVec; ++e) {
+            const uint32_t key = kk[e];
+            const bool in = i + e < w_hi;
+            lt += in && key < T;
+            eq += in && key == T;
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -308,19 +318,52 @@ __device__ __forceinline__ void block_radix_select(const Key* __restrict__ keys,
         out_pos += misc[kMiscWarpA + w] + max(0, min(e, r - eq_before));
         eq_before += e;
     }
-    const uint32_t lane_lt = (1u << lane) - 1u;
-    for (int i0 = w_lo; i0 < w_hi; i0 += 32) {
-        const int i = i0 + lane;
-        const bool in = i < w_hi;
-        const uint32_t key = in ? (uint32_t)keys[i] : 0xffffffffu;
-        const bool is_lt = in && key < T;
-        const bool is_eq = in && key == T;
-        const uint32_t eqb = __ballot_sync(0xffffffffu, is_eq);
-        const bool take = is_lt || (is_eq && (eq_before + __popc(eqb & lane_lt)) < r);
-        const uint32_t tb = __ballot_sync(0xffffffffu, take);
-        if (take) out_idx[out_pos + __popc(tb & lane_lt)] = base + i;
-        eq_before += __popc(eqb);
-        out_pos += __popc(tb);
+    auto warp_inclusive = [&](int v) {
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += t;
+        }
+        return v;
+    };
+    for (int i0 = w_lo; i0 < w_hi; i0 += kStep) {
+        const int i = i0 + lane * kVec;
+        uint32_t m_lt = 0, m_eq = 0;  // bit e: element e of this lane is < T / == T
+        if (i < w_hi) {
+            const int4 raw = *reinterpret_cast<const int4*>(keys + i);
+            const Key* kk = reinterpret_cast<const Key*>(&raw);
+#pragma unroll
+            for (int e = 0; e < kVec; ++e) {
+                const uint32_t key = kk[e];
+                const bool in = i + e < w_hi;
+                m_lt |= (uint32_t)(in && key < T) << e;
+                m_eq |= (uint32_t)(in && key == T) << e;
+            }
+        }
+        uint32_t m_take = m_lt;
+        const bool any_eq = __any_sync(0xffffffffu, m_eq != 0);
+        if (any_eq) {  // ties: the first r keys equal to T, in index order
+            const int c_eq = __popc(m_eq);
+            const int incl = warp_inclusive(c_eq);
+            int seen = eq_before + incl - c_eq;
+#pragma unroll
+            for (int e = 0; e < kVec; ++e) {
+                if ((m_eq >> e) & 1u) {
+                    if (seen < r) m_take |= 1u << e;
+                    ++seen;
+                }
+            }
+            eq_before += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (__any_sync(0xffffffffu, m_take != 0)) {
+            const int c_take = __popc(m_take);
+            const int incl = warp_inclusive(c_take);
+            int pos = out_pos + incl - c_take;
+#pragma unroll
+            for (int e = 0; e < kVec; ++e)
+                if ((m_take >> e) & 1u) out_idx[pos++] = base + i + e;
+            out_pos += __shfl_sync(0xffffffffu, incl, 31);
+        }
     }
     __syncthreads();
 }

@@ -1,9 +1,18 @@
-F="--steps 10 --warmup 3 --no-e2e --no-cpu-baseline"
-timeout 300 python bench.py $F --config c4 > gpurun_out/r_c4.json 2>/dev/null
-timeout 300 python bench.py $F --config c4_vote > gpurun_out/r_c4_vote.json 2>/dev/null
-timeout 300 python bench.py $F --config c2_vote > gpurun_out/r_c2_vote.json 2>/dev/null
-timeout 300 python bench.py --mode slab --config c4 --steps 10 > gpurun_out/r_slab_c4.json 2>/dev/null
-for f in r_c4 r_c4_vote r_c2_vote; do python -c "
-import json; d=json.loads(open('gpurun_out/$f.json').read().strip().splitlines()[-1]); print('R $f', d['us_per_step'], d['value'], d['roofline']['frac'], d.get('tensor_tflops'))"; done
-python -c "
-import json; d=json.loads(open('gpurun_out/r_slab_c4.json').read().strip().splitlines()[-1]); print('R slab_c4', d['per_call'])"
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+run() { # config batch env...
+  c=$1; b=$2; shift; shift
+  env "$@" timeout 300 python bench.py --steps 20 --warmup 5 --no-e2e --no-cpu-baseline --config $c --batch $b > gpurun_out/ab.json 2> gpurun_out/ab.err
+  python -c "
+import json; d=json.loads(open('gpurun_out/ab.json').read().strip().splitlines()[-1]); print('AB $c B=$b $*', d['us_per_step'], d['value'], [(k, v['us_mean'], v['frac_of_peak']) for k,v in d['per_call'].items()])"
+}
+run c2 32
+run c3 32
+run c4 16
+run c4 1
+run c5 8
+run c5 1
+run c1 1
+for c in c4 c5 c3 c2; do
+timeout 300 python bench.py --mode slab --config $c --steps 10 > gpurun_out/slab_$c.json 2>/dev/null; python -c "
+import json; d=json.loads(open('gpurun_out/slab_$c.json').read().strip().splitlines()[-1]); print('SLAB $c', {k:v['compress_us_mean'] for k,v in d['per_call'].items()})"
+done
