@@ -24,6 +24,18 @@
 #include "kvc_vote.cuh"
 #include "kvc_vote_split.cuh"
 
+// The library is ONE source file, but its ~170 kernel instantiations compile serially: the build compiles it three
+// times in parallel, each pass keeping one group of entry points (and only the kernels they launch), and links the
+// objects.  KVC_PART is a bit mask: 1 = compress / select / norms (+ the library-wide state), 2 = slab cache, 4 = vote,
+// 8 = the LDG-form fused kernels (generic row widths) behind pick_fused_dt().
+#ifndef KVC_PART
+#define KVC_PART 15
+#endif
+#define KVC_HAS_CORE (KVC_PART & 1)
+#define KVC_HAS_SLAB (KVC_PART & 2)
+#define KVC_HAS_VOTE (KVC_PART & 4)
+#define KVC_HAS_LDG (KVC_PART & 8)
+
 #define KVC_STR2(x) #x
 #define KVC_STR(x) KVC_STR2(x)
 
@@ -257,8 +269,13 @@ __global__ void __launch_bounds__(NT) kvc_select_kernel(const typename Traits<DT
 }
 
 // ------------------------------------------------------------------ host side
-static thread_local char g_last_error[256] = "";
-static std::atomic<int64_t> g_launches{0};
+#if KVC_HAS_CORE
+thread_local char g_last_error[256] = "";
+std::atomic<int64_t> g_launches{0};
+#else
+extern thread_local char g_last_error[256];
+extern std::atomic<int64_t> g_launches;
+#endif
 constexpr int kMaxSmemOptin = 227 * 1024;
 
 static int cuda_fail(cudaError_t e, const char* what) {
@@ -274,9 +291,10 @@ struct FusedVariant {
     FusedFn fn;
     int threads;
 };
-
 constexpr int kNT = 512;
+FusedVariant pick_fused_dt(int dtype, int cpr);  // LDG-form kernel for a row width (cpr = 16-byte chunks per row)
 
+#if KVC_HAS_LDG
 template <int DT>
 static FusedVariant pick_fused(int cpr) {
     switch (cpr) {
@@ -289,13 +307,14 @@ static FusedVariant pick_fused(int cpr) {
     }
 }
 
-static FusedVariant pick_fused_dt(int dtype, int cpr) {
+FusedVariant pick_fused_dt(int dtype, int cpr) {
     switch (dtype) {
         case KVC_DTYPE_F32: return pick_fused<KVC_DTYPE_F32>(cpr);
         case KVC_DTYPE_F16: return pick_fused<KVC_DTYPE_F16>(cpr);
         default: return pick_fused<KVC_DTYPE_BF16>(cpr);
     }
 }
+#endif  // KVC_HAS_LDG
 
 static int set_device(int device) {
     int cur = -1;
@@ -415,11 +434,13 @@ static bool onchip_plan_ok(const TmaPlan& tp, int cpr, bool light_traffic) {
     return (long)tp.ctas * tp.nsw * 32 * cpr * 16 >= 48 * 1024;
 }
 
+#if KVC_HAS_CORE
 template <int DT, int NT, int MINB>
 static FusedFn pick_tma_cpr(int cpr) {
     switch (cpr) {
         case 8: return kvc_fused_tma_kernel<DT, 8, NT, MINB>;
         case 10: return kvc_fused_tma_kernel<DT, 10, NT, MINB>;
+        case 12: return kvc_fused_tma_kernel<DT, 12, NT, MINB>;
         case 16: return kvc_fused_tma_kernel<DT, 16, NT, MINB>;
         case 20: return kvc_fused_tma_kernel<DT, 20, NT, MINB>;
         case 32: return kvc_fused_tma_kernel<DT, 32, NT, MINB>;
@@ -437,7 +458,11 @@ static FusedFn pick_tma(int dtype, int cpr, int nt) {
         default: return pick_tma_nt<KVC_DTYPE_BF16>(cpr, nt);
     }
 }
-static bool tma_supported_cpr(int cpr) { return cpr == 8 || cpr == 10 || cpr == 16 || cpr == 20 || cpr == 32; }
+#endif  // KVC_HAS_CORE
+
+static bool tma_supported_cpr(int cpr) {  // 128/160/192/256/320/512-byte rows
+    return cpr == 8 || cpr == 10 || cpr == 12 || cpr == 16 || cpr == 20 || cpr == 32;
+}
 
 static int ensure_tma_attrs(const void* fn, int device) {
     // Function attributes are sticky per (function, device): set them once, not on every decode step.
@@ -459,6 +484,7 @@ static int ensure_tma_attrs(const void* fn, int device) {
 
 
 // ------------------------------------------------------------------ slab kernels: variant tables
+#if KVC_HAS_SLAB
 using SlabFn = void (*)(const SlabBatchDev);
 using AppendFn = void (*)(const AppendBatchDev);
 
@@ -467,6 +493,7 @@ static SlabFn pick_slab_cpr(int cpr) {
     switch (cpr) {
         case 8: return kvc_slab_compress_kernel<DT, 8, NT, MINB>;
         case 10: return kvc_slab_compress_kernel<DT, 10, NT, MINB>;
+        case 12: return kvc_slab_compress_kernel<DT, 12, NT, MINB>;
         case 16: return kvc_slab_compress_kernel<DT, 16, NT, MINB>;
         case 20: return kvc_slab_compress_kernel<DT, 20, NT, MINB>;
         case 32: return kvc_slab_compress_kernel<DT, 32, NT, MINB>;
@@ -489,6 +516,7 @@ static AppendFn pick_append_cpr(int cpr) {
     switch (cpr) {
         case 8: return kvc_slab_append_kernel<DT, 8, AppendBatchDev>;
         case 10: return kvc_slab_append_kernel<DT, 10, AppendBatchDev>;
+        case 12: return kvc_slab_append_kernel<DT, 12, AppendBatchDev>;
         case 16: return kvc_slab_append_kernel<DT, 16, AppendBatchDev>;
         case 20: return kvc_slab_append_kernel<DT, 20, AppendBatchDev>;
         case 32: return kvc_slab_append_kernel<DT, 32, AppendBatchDev>;
@@ -501,6 +529,7 @@ static AppendOneFn pick_append_one_cpr(int cpr) {
     switch (cpr) {
         case 8: return kvc_slab_append_kernel<DT, 8, AppendOneDev>;
         case 10: return kvc_slab_append_kernel<DT, 10, AppendOneDev>;
+        case 12: return kvc_slab_append_kernel<DT, 12, AppendOneDev>;
         case 16: return kvc_slab_append_kernel<DT, 16, AppendOneDev>;
         case 20: return kvc_slab_append_kernel<DT, 20, AppendOneDev>;
         case 32: return kvc_slab_append_kernel<DT, 32, AppendOneDev>;
@@ -519,6 +548,7 @@ static AppendFn pick_append_tma_cpr(int cpr) {
     switch (cpr) {
         case 8: return kvc_slab_append_tma_kernel<DT, 8>;
         case 10: return kvc_slab_append_tma_kernel<DT, 10>;
+        case 12: return kvc_slab_append_tma_kernel<DT, 12>;
         case 16: return kvc_slab_append_tma_kernel<DT, 16>;
         case 20: return kvc_slab_append_tma_kernel<DT, 20>;
         case 32: return kvc_slab_append_tma_kernel<DT, 32>;
@@ -540,6 +570,8 @@ static AppendFn pick_append(int dtype, int cpr) {
     }
 }
 
+#endif  // KVC_HAS_SLAB
+
 static int check_shape(const kvc_shape* shape, int* cpr_out) {
     if (!shape) return KVC_ERR_INVALID_ARG;
     const int B = shape->batch, H = shape->heads, D = shape->head_dim, dt = shape->dtype;
@@ -558,6 +590,7 @@ using namespace kvc;
 
 extern "C" {
 
+#if KVC_HAS_CORE
 int kvc_abi_version(void) { return KVC_ABI_VERSION; }
 
 const char* kvc_build_info(void) {
@@ -845,6 +878,9 @@ int kvc_select(int32_t dtype, int32_t device, const void* scores, int64_t n_rows
     return KVC_OK;
 }
 
+#endif  // KVC_HAS_CORE
+
+#if KVC_HAS_SLAB
 int kvc_slab_append(const kvc_shape* shape, int32_t n_layers, const kvc_slab_layer* slabs,
                     const kvc_slab_new_rows* rows, void* stream) {
     int cpr = 0;
@@ -1047,6 +1083,9 @@ int kvc_slab_compress(const kvc_shape* shape, int32_t n_layers, const kvc_layer_
     return KVC_OK;
 }
 
+#endif  // KVC_HAS_SLAB
+
+#if KVC_HAS_VOTE
 // cuTensorMapEncodeTiled through the runtime (the library links cudart statically and never links libcuda).
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -1299,16 +1338,6 @@ int kvc_snapkv_vote_ws(const kvc_shape* shape, int32_t n_layers, const kvc_vote_
     }
     size_t smem = 2304 + 3 * (size_t)(kVoteTile / 8) * cpr * kVoteLBO;
     int threads = 256;
-    if (env_int("KVC_VOTE_WS", 0)) {  // A/B: warp-specialised form, one CTA per SM
-        if (dt == KVC_DTYPE_BF16)
-            fn = cpr == 8 ? kvc_snapkv_vote_ws_kernel<KVC_DTYPE_BF16, 8> : cpr == 10 ? kvc_snapkv_vote_ws_kernel<KVC_DTYPE_BF16, 10>
-                                                                                    : kvc_snapkv_vote_ws_kernel<KVC_DTYPE_BF16, 16>;
-        else
-            fn = cpr == 8 ? kvc_snapkv_vote_ws_kernel<KVC_DTYPE_F16, 8> : cpr == 10 ? kvc_snapkv_vote_ws_kernel<KVC_DTYPE_F16, 10>
-                                                                                   : kvc_snapkv_vote_ws_kernel<KVC_DTYPE_F16, 16>;
-        smem = 6144 + (1 + kWsRing) * (size_t)(kVoteTile / 8) * cpr * kVoteLBO;
-        threads = 672;
-    }
     st = ensure_tma_attrs((const void*)fn, shape->device);
     if (st != KVC_OK) return st;
     for (int l0 = 0; l0 < n_layers; l0 += KVC_MAX_LAYERS_PER_LAUNCH) {
@@ -1343,5 +1372,7 @@ int kvc_snapkv_vote_ws(const kvc_shape* shape, int32_t n_layers, const kvc_vote_
     }
     return KVC_OK;
 }
+
+#endif  // KVC_HAS_VOTE
 
 }  // extern "C"

@@ -356,266 +356,17 @@ __global__ void __launch_bounds__(256, 2) kvc_snapkv_vote_kernel(const __grid_co
 }
 
 // ---------------------------------------------------------------------------------------------
-// Warp-specialised form: ONE CTA per SM, 21 warps.
-//   warps 0-15  four math groups (128 threads = the 128 TMEM lanes); group g owns accumulator g (128 of the 512
-//               TMEM columns) and reduces work items g, g+4, g+8, ...;
-//   warps 16-19 copy warps: cp.async 16-byte copies of the key tiles straight into the canonical layout of a
-//               5-slot shared-memory ring, three tiles in flight, never waiting on math;
-//   warp 20     one thread issues every tcgen05.mma (waits: slot full, accumulator drained) and commits to the
-//               accumulator-full and slot-empty mbarriers.
-// Work items are the tiles of pass 1 (all S keys, A = Q) followed by the tiles of pass 2 (P keys, A = keys); the
-// copy and MMA warps run ahead across the pass boundary, only the math groups meet there to merge the row statistics.
+// Warp-specialised forms below: ONE CTA per SM; warps 0-15 are four math groups (128 threads = the 128 TMEM lanes;
+// group g owns accumulator g, 128 of the 512 TMEM columns, and reduces work items g, g+4, g+8, ...), one thread feeds
+// a shared-memory ring of key tiles, one thread issues every tcgen05.mma (waits: slot full, accumulator drained) and
+// commits to the accumulator-full and slot-empty mbarriers.  Work items are the tiles of pass 1 (all S keys, A = Q)
+// followed by the tiles of pass 2 (P keys, A = keys); the copy and MMA threads run ahead across the pass boundary,
+// only the math groups meet there to merge the row statistics.  (A cp.async-fed variant of this layout, four copy
+// warps, was measured at 21.6 ms on c4_vote against 15.6 ms for the TMA-fed one and removed.)
 constexpr int kWsRing = 5;
-constexpr int kWsDepth = 3;  // tiles a copy thread keeps in flight beyond the one it is issuing
-constexpr int kWsMathThreads = 512;
-constexpr int kWsCopyThreads = 128;
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-template <int N>
-__device__ __forceinline__ void cp_async_wait_group() {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-
-template <int DT, int CPR>
-__global__ void __launch_bounds__(672, 1) kvc_snapkv_vote_ws_kernel(const __grid_constant__ VoteBatchDev bd) {
-    using Tr = Traits<DT>;
-    using Key = typename Tr::Key;
-    static_assert(DT != KVC_DTYPE_F32, "the vote runs on 16-bit caches (kind::f16)");
-    constexpr int TILE_BYTES = (kVoteTile / 8) * CPR * kVoteLBO;
-    constexpr int CHC = kVoteTile * CPR / kWsCopyThreads;  // 16-byte chunks per copy thread per tile
-    constexpr uint32_t IDESC = umma_idesc_f16(DT == KVC_DTYPE_BF16 ? 1 : 0, kVoteM, kVoteTile);
-
-    const VoteLayerDev& L = bd.layers[blockIdx.y];
-    const int bh = blockIdx.x;
-    const int b = bh / bd.H, h = bh - b * bd.H;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int S = L.S, W = bd.W, G = bd.G;
-    const int P = S - W;
-    const int rows_q = G * W;
-    const int n1 = (S + kVoteTile - 1) / kVoteTile, n2 = (P + kVoteTile - 1) / kVoteTile;
-    const int n_items = n1 + n2;
-
-    extern __shared__ __align__(128) unsigned char smem[];
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem);
-    const uint32_t bar_full = smem_u32(smem + 64);        // [kWsRing]  count = copy threads
-    const uint32_t bar_empty = bar_full + 8 * kWsRing;    // [kWsRing]  count = 1 (tcgen05.commit)
-    const uint32_t bar_tfull = bar_empty + 8 * kWsRing;   // [4]        count = 1 (tcgen05.commit)
-    const uint32_t bar_tempty = bar_tfull + 8 * 4;        // [4]        count = 128 (math threads)
-    float* s_m = reinterpret_cast<float*>(smem + 512);
-    float* s_invl = reinterpret_cast<float*>(smem + 1024);
-    float* s_part = reinterpret_cast<float*>(smem + 1536);  // [4 groups][2][128]
-    unsigned char* s_q = smem + 6144;
-    unsigned char* s_ring = s_q + TILE_BYTES;
-
-    if (tid == 0) {
-        for (int i = 0; i < kWsRing; ++i) {
-            mbar_init(bar_full + 8 * i, kWsCopyThreads);
-            mbar_init(bar_empty + 8 * i, 1);
-        }
-        for (int i = 0; i < 4; ++i) {
-            mbar_init(bar_tfull + 8 * i, 1);
-            mbar_init(bar_tempty + 8 * i, 128);
-        }
-        mbar_init_fence();
-    }
-    if (warp == 20) tmem_alloc(smem_u32(s_tmem), 512);
-    const char* kbase = L.k + (int64_t)b * L.ksb + (int64_t)h * L.ksh;
-    for (int q = tid; q < kVoteM * CPR; q += 672) {
-        int r, c;
-        tile_item<CPR>(q, r, c);
-        int4 v = make_int4(0, 0, 0, 0);
-        if (r < rows_q) {
-            const int g = r / W, w = r - g * W;
-            v = ldg128_stream(L.q + (int64_t)b * L.qsb + (int64_t)(h * G + g) * L.qsh + (int64_t)w * L.qss + c * 16);
-        }
-        *reinterpret_cast<int4*>(s_q + umma_off<CPR>(r, c)) = v;
-    }
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *s_tmem;
-    const uint32_t q_addr = smem_u32(s_q), ring_addr = smem_u32(s_ring);
-    const float c2 = bd.scale_log2e;
-
-    if (warp < 16) {
-        // ================================================================ math groups
-        const int grp = warp >> 2, gt = tid & 127;
-        const uint32_t t_lane = tmem + grp * kVoteTile + ((uint32_t)((warp & 3) * 32) << 16);
-        float m_run = -INFINITY, l_run = 0.f;
-        // the accumulator is read 16 columns at a time with the next 16 already in flight (two register sets):
-        // TMEM reads (64 B/clk per SM) and the ex2 pipe are floors of the same size and must overlap
-        uint32_t va[16], vb[16];
-        const int limit = P + ((gt < rows_q) ? (gt % W) : 0);
-        const bool row_live = (warp & 3) * 32 < rows_q;
-        int i = grp;
-        for (; i < n1; i += 4) {
-            mbar_wait(bar_tfull + 8 * grp, (uint32_t)((i >> 2) & 1));
-            tc_fence_after();
-            if (row_live && bd.pad[0] == 0) {
-                const int key0 = i * kVoteTile;
-                const bool masked = key0 + kVoteTile > P;
-                tmem_ld16_async(t_lane, va);
-#pragma unroll
-                for (int cb = 0; cb < kVoteTile; cb += 16) {
-                    uint32_t(&v)[16] = ((cb >> 4) & 1) ? vb : va;
-                    tmem_ld_wait();
-                    if (cb + 16 < kVoteTile) tmem_ld16_async(t_lane + cb + 16, ((cb >> 4) & 1) ? va : vb);
-                    float cmax = -INFINITY;
-                    if (masked) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const int key = key0 + cb + j;
-                            if (key > limit || key >= S) v[j] = 0xff800000u;
-                            cmax = fmaxf(cmax, __uint_as_float(v[j]));
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) cmax = fmaxf(cmax, __uint_as_float(v[j]));
-                    }
-                    const float m_new = fmaxf(m_run, cmax * c2);
-                    if (m_new > -INFINITY) {
-                        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-#pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            acc0 += ex2(fmaf(__uint_as_float(v[j]), c2, -m_new));
-                            acc1 += ex2(fmaf(__uint_as_float(v[j + 1]), c2, -m_new));
-                            acc2 += ex2(fmaf(__uint_as_float(v[j + 2]), c2, -m_new));
-                            acc3 += ex2(fmaf(__uint_as_float(v[j + 3]), c2, -m_new));
-                        }
-                        if (m_new != m_run) l_run *= ex2(m_run - m_new);  // the maximum settles after a few tiles
-                        l_run += (acc0 + acc1) + (acc2 + acc3);
-                        m_run = m_new;
-                    }
-                }
-            }
-            tc_fence_before();
-            mbar_arrive(bar_tempty + 8 * grp);
-        }
-        // ---------------- pass boundary: merge the four groups' partial statistics
-        s_part[(grp * 2 + 0) * 128 + gt] = m_run;
-        s_part[(grp * 2 + 1) * 128 + gt] = l_run;
-        asm volatile("bar.sync 1, 512;" ::: "memory");
-        if (tid < 128) {
-            float m = -INFINITY;
-#pragma unroll
-            for (int g4 = 0; g4 < 4; ++g4) m = fmaxf(m, s_part[(g4 * 2) * 128 + tid]);
-            float l = 0.f;
-            if (m > -INFINITY) {
-#pragma unroll
-                for (int g4 = 0; g4 < 4; ++g4) {
-                    const float mp = s_part[(g4 * 2) * 128 + tid];
-                    if (mp > -INFINITY) l += s_part[(g4 * 2 + 1) * 128 + tid] * ex2(mp - m);
-                }
-            }
-            const bool live = tid < rows_q && l > 0.f;
-            s_m[tid] = live ? m : 0.f;
-            s_invl[tid] = live ? 1.f / l : 0.f;
-        }
-        asm volatile("bar.sync 1, 512;" ::: "memory");
-        // ---------------- pass 2: lane = key, columns = query rows
-        for (; i < n_items; i += 4) {
-            mbar_wait(bar_tfull + 8 * grp, (uint32_t)((i >> 2) & 1));
-            tc_fence_after();
-            float vote0 = 0.f, vote1 = 0.f, vote2 = 0.f, vote3 = 0.f;
-            if (bd.pad[0] == 0) tmem_ld16_async(t_lane, va);
-#pragma unroll
-            for (int cb = 0; cb < kVoteM; cb += 16) {
-                if (cb < rows_q && bd.pad[0] == 0) {  // warp-uniform: padding query rows never vote
-                    uint32_t(&v)[16] = ((cb >> 4) & 1) ? vb : va;
-                    tmem_ld_wait();
-                    if (cb + 16 < rows_q) tmem_ld16_async(t_lane + cb + 16, ((cb >> 4) & 1) ? va : vb);
-#pragma unroll
-                    for (int j = 0; j < 16; j += 4) {
-                        const float4 mm = *reinterpret_cast<const float4*>(s_m + cb + j);
-                        const float4 il = *reinterpret_cast<const float4*>(s_invl + cb + j);
-                        vote0 = fmaf(ex2(fmaf(__uint_as_float(v[j + 0]), c2, -mm.x)), il.x, vote0);
-                        vote1 = fmaf(ex2(fmaf(__uint_as_float(v[j + 1]), c2, -mm.y)), il.y, vote1);
-                        vote2 = fmaf(ex2(fmaf(__uint_as_float(v[j + 2]), c2, -mm.z)), il.z, vote2);
-                        vote3 = fmaf(ex2(fmaf(__uint_as_float(v[j + 3]), c2, -mm.w)), il.w, vote3);
-                    }
-                }
-            }
-            tc_fence_before();
-            mbar_arrive(bar_tempty + 8 * grp);
-            const int key = (i - n1) * kVoteTile + gt;
-            if (key < P) {
-                Key* out = reinterpret_cast<Key*>(L.votes) + (int64_t)bh * P;
-                out[key] = (Key)Tr::to_raw((vote0 + vote1) + (vote2 + vote3));
-            }
-        }
-    } else if (warp < 20) {
-        // ================================================================ copy warps
-        const int ct = tid - kWsMathThreads;
-        int64_t kss = L.kss;
-        asm volatile("" : "+l"(kss));
-        for (int i = 0; i < n_items; ++i) {
-            const int slot = i % kWsRing;
-            mbar_wait(bar_empty + 8 * slot, (uint32_t)(((i / kWsRing) & 1) ^ 1));  // fresh barrier: passes
-            const int t = i < n1 ? i : i - n1;
-            const int r0 = t * kVoteTile;
-            const char* tile = kbase + (int64_t)r0 * kss;
-            const uint32_t dst = ring_addr + slot * TILE_BYTES;
-            if (CPR == 16 && r0 + kVoteTile <= S) {
-                // full tile, 128 copy threads: thread ct always takes row (ct & 7) of every 8-row group and chunk
-                // ct >> 3, so source and destination advance by constants (two adds per copy)
-                const char* src = tile + (int64_t)(ct & 7) * kss + (ct >> 3) * 16;
-                uint32_t d = dst + (uint32_t)((ct >> 3) * kVoteLBO + (ct & 7) * 16);
-                const int64_t step = 8 * kss;
-#pragma unroll
-                for (int k = 0; k < CHC; ++k) {
-                    cp_async16(d, src, true);
-                    src += step;
-                    d += CPR * kVoteLBO;
-                }
-            } else {
-#pragma unroll 4
-                for (int k = 0; k < CHC; ++k) {
-                    int r, c;
-                    tile_item<CPR>(k * kWsCopyThreads + ct, r, c);
-                    const bool ok = r0 + r < S;
-                    cp_async16(dst + umma_off<CPR>(r, c), ok ? tile + r * kss + c * 16 : kbase, ok);
-                }
-            }
-            cp_async_commit();
-            if (i >= kWsDepth) {  // at most kWsDepth + 1 tiles in flight per copy thread
-                cp_async_wait_group<kWsDepth>();
-                fence_proxy_async_smem();
-                mbar_arrive(bar_full + 8 * ((i - kWsDepth) % kWsRing));
-            }
-        }
-        cp_async_wait_group<0>();
-        fence_proxy_async_smem();
-        for (int j = (n_items > kWsDepth ? n_items - kWsDepth : 0); j < n_items; ++j) mbar_arrive(bar_full + 8 * (j % kWsRing));
-    } else if (warp == 20 && lane == 0) {
-        // ================================================================ MMA issuer
-        for (int i = 0; i < n_items; ++i) {
-            const int slot = i % kWsRing, acc = i & 3;
-            mbar_wait(bar_tempty + 8 * acc, (uint32_t)(((i >> 2) & 1) ^ 1));  // accumulator drained (fresh: passes)
-            mbar_wait(bar_full + 8 * slot, (uint32_t)((i / kWsRing) & 1));    // tile landed
-            tc_fence_after();
-            const bool keys_are_rows = i >= n1;
-            const uint32_t kb = ring_addr + slot * TILE_BYTES;
-            const uint32_t a0 = keys_are_rows ? kb : q_addr;
-            const uint32_t b0 = keys_are_rows ? q_addr : kb;
-            if (bd.pad[0] < 2) {
-#pragma unroll
-                for (int ks = 0; ks < CPR / 2; ++ks) {
-                    const uint64_t ad = umma_smem_desc(a0 + ks * 2 * kVoteLBO, kVoteLBO, CPR * kVoteLBO);
-                    const uint64_t bdsc = umma_smem_desc(b0 + ks * 2 * kVoteLBO, kVoteLBO, CPR * kVoteLBO);
-                    umma_f16(tmem + acc * kVoteTile, ad, bdsc, IDESC, ks > 0 ? 1u : 0u);
-                }
-            }
-            umma_commit(bar_tfull + 8 * acc);
-            umma_commit(bar_empty + 8 * slot);
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 20) tmem_dealloc(tmem, 512);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -624,7 +375,7 @@ __global__ void __launch_bounds__(672, 1) kvc_snapkv_vote_ws_kernel(const __grid
 // layout are the bottleneck, not the tensor core or the softmax math.  Here ONE thread feeds the ring with
 // `cp.async.bulk.tensor.4d` loads through a per-layer tensor map (boxes of 128 rows x 64 elements, 128-byte
 // swizzle = the K-major SW128 UMMA layout; rows beyond S are zero-filled by the TMA unit), warps 0-15 do the
-// softmax math exactly as above and one thread issues the MMAs (keys: SW128 descriptors, queries: no-swizzle).
+// softmax math and one thread issues the MMAs (keys: SW128 descriptors, queries: no-swizzle).
 struct VoteTmaLayerDev {
     alignas(64) CUtensorMap map;  // keys [B,H,S,D] as a 4-D tensor (D, S, H, B), box (64, 128, 1, 1), SWIZZLE_128B
     alignas(64) CUtensorMap map_tail;  // D % 64 == 16 (D = 80): box (16, 128, 1, 1), SWIZZLE_32B, for the last 16 elements

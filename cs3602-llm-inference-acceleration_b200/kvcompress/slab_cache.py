@@ -82,9 +82,9 @@ class KVSlabCache:
         if dtype not in _engine.KVC_DTYPE:
             raise ValueError(f"dtype {dtype} is not supported (float32, float16, bfloat16)")
         row_bytes = head_dim * torch.empty((), dtype=dtype).element_size()
-        if row_bytes % 16 or row_bytes // 16 not in (8, 10, 16, 20, 32):
-            raise ValueError(f"head_dim*itemsize = {row_bytes} B: the slab kernels cover rows of 128, 160, 256, 320 "
-                             "and 512 bytes")
+        if row_bytes % 16 or row_bytes // 16 not in (8, 10, 12, 16, 20, 32):
+            raise ValueError(f"head_dim*itemsize = {row_bytes} B: the slab kernels cover rows of 128, 160, 192, 256, "
+                             "320 and 512 bytes")
         if device.index is None:
             device = torch.device("cuda", torch.cuda.current_device())
         self.num_layers, self.batch, self.heads, self.head_dim = num_layers, batch, heads, head_dim

@@ -6,13 +6,7 @@ run() { # config batch env...
 import json; d=json.loads(open('gpurun_out/ab.json').read().strip().splitlines()[-1]); print('AB $c B=$b $*', d['us_per_step'], d['value'], [(k, v['us_mean'], v['frac_of_peak']) for k,v in d['per_call'].items()])"
 }
 run c2 32
+run c2_steady 32
 run c3 32
-run c4 16
-run c4 1
-run c5 8
-run c5 1
-run c1 1
-for c in c4 c5 c3 c2; do
-timeout 300 python bench.py --mode slab --config $c --steps 10 > gpurun_out/slab_$c.json 2>/dev/null; python -c "
-import json; d=json.loads(open('gpurun_out/slab_$c.json').read().strip().splitlines()[-1]); print('SLAB $c', {k:v['compress_us_mean'] for k,v in d['per_call'].items()})"
-done
+run c4_vote 16
+run c2_vote 32

@@ -356,8 +356,9 @@ def test_pinned_host_cache_matches_device_cache(method, kwargs):
 
 # ----------------------------------------------------------------------------------------------
 # The golden cases use small head dims (rows of 32-64 B -> the LDG form).  The same presets at the
-# PRODUCT row widths (the TMA form: 128/160/256/320/512-byte rows) against the golden-pinned oracle.
-WIDTHS = [("bf16", 64), ("bf16", 80), ("bf16", 128), ("bf16", 256), ("f16", 80), ("f32", 32), ("f32", 80), ("f32", 128)]
+# PRODUCT row widths (the TMA form: 128/160/192/256/320/512-byte rows) against the golden-pinned oracle.
+WIDTHS = [("bf16", 64), ("bf16", 80), ("bf16", 96), ("bf16", 128), ("bf16", 256), ("f16", 80), ("f32", 32),
+          ("f32", 48), ("f32", 80), ("f32", 128)]
 WIDE_PRESETS = [
     ("streaming", "streaming_llm", dict(start_size=4, recent_size=508)),
     ("h2o", "h2o_l2", dict(start_size=4, heavy_hitter_size=64, recent_size=444, skip_layers=[1])),

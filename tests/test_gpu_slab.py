@@ -77,10 +77,10 @@ def test_decode_loop_matches_out_of_place(method, kwargs, dtype, D):
 
 
 @pytest.mark.parametrize("dtype", ["bf16", "f16", "f32"])
-@pytest.mark.parametrize("D", [64, 80, 128])
+@pytest.mark.parametrize("D", [64, 80, 96, 128])
 def test_append_copies_rows_and_records_torch_norms(dtype, D):
     dt = DT[dtype]
-    if D * torch.empty((), dtype=dt).element_size() // 16 not in (8, 10, 16, 20, 32):
+    if D * torch.empty((), dtype=dt).element_size() // 16 not in (8, 10, 12, 16, 20, 32):
         pytest.skip("row width not covered by the slab kernels")
     gen = torch.Generator(device="cuda").manual_seed(3)
     L, B, H = 2, 2, 4
