@@ -440,6 +440,7 @@ __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __gri
     const int S = L.S, W = bd.W, G = bd.G;
     const int P = S - W;
     const int rows_q = G * W;
+    const int RB = rows_q <= 32 ? 32 : (rows_q <= 64 ? 64 : 128);  // rows per replica block, F = 128 / RB replicas
     const int n1 = (S + kVoteTile - 1) / kVoteTile, n2 = (P + kVoteTile - 1) / kVoteTile;
     const int n_items = n1 + n2;
 
@@ -468,12 +469,18 @@ __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __gri
         mbar_init_fence();
     }
     if (warp == 17) tmem_alloc(smem_u32(s_tmem), 512);
+    // Few query rows (MHA: G*W = 32): the rows are REPLICATED down the 128 MMA rows -- F copies of a block of RB =
+    // 128 / F rows -- so that in pass 1 every lane quarter of an accumulator holds live rows and its warp takes 1/F of
+    // the tile's key columns.  Without this only the warp of quarter 0 works in pass 1, and the four groups' quarter-0
+    // warps all sit on the same SM sub-partition (a warp can only read the TMEM lanes of quarter warp_id % 4): a
+    // quarter of the ex2 pipe carries the whole pass.
     for (int q = tid; q < kVoteM * CPR; q += 576) {
         int r, c;
         tile_item<CPR>(q, r, c);
         int4 v = make_int4(0, 0, 0, 0);
-        if (r < rows_q) {
-            const int g = r / W, w = r - g * W;
+        const int qr = r & (RB - 1);  // MMA row r carries query row r mod RB
+        if (qr < rows_q) {
+            const int g = qr / W, w = qr - g * W;
             v = ldg128_stream(L.q + (int64_t)b * L.qsb + (int64_t)(h * G + g) * L.qsh + (int64_t)w * L.qss + c * 16);
         }
         *reinterpret_cast<int4*>(s_q + umma_off<CPR>(r, c)) = v;
@@ -494,8 +501,11 @@ __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __gri
         // the accumulator is read 16 columns at a time with the next 16 already in flight (two register sets):
         // TMEM reads (64 B/clk per SM) and the ex2 pipe are floors of the same size and must overlap
         uint32_t va[16], vb[16];
-        const int limit = P + ((gt < rows_q) ? (gt % W) : 0);
-        const bool row_live = (warp & 3) * 32 < rows_q;
+        const int row = gt & (RB - 1);          // query row of this TMEM lane; replica gt / RB
+        const int limit = P + ((row < rows_q) ? (row % W) : 0);
+        const bool row_live = (((warp & 3) * 32) & (RB - 1)) < rows_q;
+        const int c_lo = (gt / RB) * RB;        // this replica's share of a tile's key columns: [c_lo, c_lo + RB)
+        const int nch = RB / 16;
         int i = grp;
         for (; i < n1; i += 4) {
             mbar_wait(bar_tfull + 8 * grp, (uint32_t)((i >> 2) & 1));
@@ -503,12 +513,14 @@ __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __gri
             if (row_live && bd.pad[0] == 0) {
                 const int key0 = i * kVoteTile;
                 const bool masked = key0 + kVoteTile > P;
-                tmem_ld16_async(t_lane, va);
+                tmem_ld16_async(t_lane + c_lo, va);
 #pragma unroll
-                for (int cb = 0; cb < kVoteTile; cb += 16) {
-                    uint32_t(&v)[16] = ((cb >> 4) & 1) ? vb : va;
+                for (int ch = 0; ch < kVoteTile / 16; ++ch) {
+                    if (ch >= nch) break;  // warp-uniform
+                    const int cb = c_lo + ch * 16;
+                    uint32_t(&v)[16] = (ch & 1) ? vb : va;
                     tmem_ld_wait();
-                    if (cb + 16 < kVoteTile) tmem_ld16_async(t_lane + cb + 16, ((cb >> 4) & 1) ? va : vb);
+                    if (ch + 1 < nch) tmem_ld16_async(t_lane + cb + 16, (ch & 1) ? va : vb);
                     float cmax = -INFINITY;
                     if (masked) {
 #pragma unroll
@@ -545,15 +557,22 @@ __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __gri
         s_part[(grp * 2 + 1) * 128 + gt] = l_run;
         asm volatile("bar.sync 1, 512;" ::: "memory");
         if (tid < 128) {
+            // query row `tid`: four groups x F replicas, always in the same order
             float m = -INFINITY;
+            if (tid < RB) {
+                for (int f = tid; f < 128; f += RB) {
 #pragma unroll
-            for (int g4 = 0; g4 < 4; ++g4) m = fmaxf(m, s_part[(g4 * 2) * 128 + tid]);
+                    for (int g4 = 0; g4 < 4; ++g4) m = fmaxf(m, s_part[(g4 * 2) * 128 + f]);
+                }
+            }
             float l = 0.f;
             if (m > -INFINITY) {
+                for (int f = tid; f < 128; f += RB) {
 #pragma unroll
-                for (int g4 = 0; g4 < 4; ++g4) {
-                    const float mp = s_part[(g4 * 2) * 128 + tid];
-                    if (mp > -INFINITY) l += s_part[(g4 * 2 + 1) * 128 + tid] * ex2(mp - m);
+                    for (int g4 = 0; g4 < 4; ++g4) {
+                        const float mp = s_part[(g4 * 2) * 128 + f];
+                        if (mp > -INFINITY) l += s_part[(g4 * 2 + 1) * 128 + f] * ex2(mp - m);
+                    }
                 }
             }
             const bool live = tid < rows_q && l > 0.f;

@@ -33,6 +33,9 @@ CASES = [
     (1, 2, 2, 16, 300, 64, torch.float16),
     (1, 1, 4, 32, 129, 128, torch.bfloat16),    # P = 97: a single partial tile, window straddles it
     (2, 8, 4, 32, 4096, 128, torch.bfloat16),
+    (1, 4, 2, 32, 1500, 128, torch.bfloat16),   # 64 query rows: two replicas of a 64-row block
+    (2, 2, 3, 16, 900, 80, torch.float16),      # 48 query rows: 64-row blocks with 16 padding rows each
+    (1, 3, 1, 8, 400, 64, torch.bfloat16),      # 8 query rows: four replicas of a 32-row block, 24 padding rows
 ]
 
 
