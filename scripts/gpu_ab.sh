@@ -1,8 +1,9 @@
-set -x
-B="python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline"
-$B --config c2 --steps 2 > gpurun_out/plain_c2.log 2>&1 && \
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_c2_final.csv -k regex:kvc_ $B --config c2 --steps 2 > gpurun_out/ncu_launch.log 2>&1
-tail -2 gpurun_out/ncu_launch.log
-$B --config c2 --steps 1 > gpurun_out/plain_c2.log 2>&1 && \
-timeout 1200 ncu --set full --clock-control none --import-source on -k regex:kvc_fused -s 6 -c 2 -o gpurun_out/prof_c2_final -f $B --config c2 --steps 1 > gpurun_out/ncu_full.log 2>&1
-tail -3 gpurun_out/ncu_full.log
+timeout 600 python -m pytest tests/test_gpu_vote.py -x -q 2>&1 | tail -4
+run() { # config batch env...
+  c=$1; b=$2; shift; shift
+  env "$@" timeout 300 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline --config $c --batch $b > gpurun_out/ab_$c.json 2> gpurun_out/ab.err
+  python -c "
+import json; d=json.loads(open('gpurun_out/ab_$c.json').read().strip().splitlines()[-1]); print('AB $c B=$b $*', d['us_per_step'], d['value'], d['roofline']['frac'], d.get('tensor_tflops'))"
+}
+run c4_vote 16
+run c2_vote 32
