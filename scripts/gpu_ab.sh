@@ -1,9 +1,4 @@
-timeout 600 python -m pytest tests/test_gpu_vote.py -x -q 2>&1 | tail -4
-run() { # config batch env...
-  c=$1; b=$2; shift; shift
-  env "$@" timeout 300 python bench.py --steps 10 --warmup 3 --no-e2e --no-cpu-baseline --config $c --batch $b > gpurun_out/ab_$c.json 2> gpurun_out/ab.err
-  python -c "
-import json; d=json.loads(open('gpurun_out/ab_$c.json').read().strip().splitlines()[-1]); print('AB $c B=$b $*', d['us_per_step'], d['value'], d['roofline']['frac'], d.get('tensor_tflops'))"
-}
-run c4_vote 16
-run c2_vote 32
+N="--steps 1 --warmup 3 --no-e2e --no-cpu-baseline --config c2_vote --batch 8"
+python bench.py $N > gpurun_out/plain_vote.log 2>&1 && \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:kvc_snapkv_vote -s 3 -c 1 -o gpurun_out/prof_vote_c2 -f python bench.py $N > gpurun_out/ncu_vote.log 2>&1
+tail -2 gpurun_out/ncu_vote.log
