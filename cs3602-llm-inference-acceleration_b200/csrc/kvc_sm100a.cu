@@ -1118,7 +1118,7 @@ static int launch_vote_tma(const kvc_shape* shape, int32_t n_layers, const kvc_v
         fn = cpr == 8 ? kvc_snapkv_vote_tma_kernel<KVC_DTYPE_F16, 8>
                       : cpr == 10 ? kvc_snapkv_vote_tma_kernel<KVC_DTYPE_F16, 10> : kvc_snapkv_vote_tma_kernel<KVC_DTYPE_F16, 16>;
     const size_t tile = (size_t)(cpr / 8) * kVoteTile * 128 + (size_t)(cpr % 8) * kVoteTile * 16;
-    const size_t smem = 6144 + (size_t)(kVoteM / 8) * cpr * kVoteLBO + (size_t)kWsRing * tile;
+    const size_t smem = 6144 + (size_t)(kVoteM / 8) * cpr * kVoteLBO + (size_t)vote_tma_ring(cpr) * tile;
     int st = ensure_tma_attrs((const void*)fn, shape->device);
     if (st != KVC_OK) return st;
     for (int l0 = 0; l0 < n_layers; l0 += 32) {

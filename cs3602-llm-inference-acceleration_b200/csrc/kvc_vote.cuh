@@ -25,6 +25,7 @@
 // (SURVEY.md §7 "SnapKV vote spec gap") — the tensor pipe is reported, not chased.
 #pragma once
 #include <cuda.h>  // CUtensorMap (type only; the encoder is fetched through cudaGetDriverEntryPoint)
+#include <type_traits>
 
 #include "kvc_device.cuh"
 #include "kvc_tma.cuh"
@@ -419,6 +420,16 @@ __device__ __forceinline__ uint64_t umma_smem_desc_sw128(uint32_t smem_addr) {
     return d;
 }
 
+// Ring depth of the TMA-fed kernel.  A slot is held from the issue of its load until its MMAs have completed, ~3 us,
+// so the ring depth bounds the tile rate: 5 slots of 20 KB (D = 80) left the MHA shape latency-bound (copies alone
+// 6.0 ms, copies + MMAs 8.4 ms); narrower rows get as many slots as fit next to the Q operand.
+__host__ __device__ constexpr int vote_tma_ring(int cpr) {
+    const int tile = (cpr / 8) * kVoteTile * 128 + (cpr % 8) * kVoteTile * 16;
+    const int q = (kVoteM / 8) * cpr * kVoteLBO;
+    const int n = (225 * 1024 - 6144 - q) / tile;
+    return n > 12 ? 12 : n;
+}
+
 template <int DT, int CPR>
 __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __grid_constant__ VoteTmaBatchDev bd) {
     using Tr = Traits<DT>;
@@ -431,6 +442,7 @@ __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __gri
     constexpr int TAIL_BYTES = kVoteTile * 16 * REM;  // tail box: 128 rows x 32 B, 32B-swizzled
     constexpr int TILE_BYTES = KH * BOX_BYTES + TAIL_BYTES;
     constexpr int Q_BYTES = (kVoteM / 8) * CPR * kVoteLBO;
+    constexpr int RING = vote_tma_ring(CPR);  // key-tile slots: as many as shared memory holds
     constexpr uint32_t IDESC = umma_idesc_f16(DT == KVC_DTYPE_BF16 ? 1 : 0, kVoteM, kVoteTile);
 
     const VoteTmaLayerDev& L = bd.layers[blockIdx.y];
@@ -440,6 +452,9 @@ __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __gri
     const int S = L.S, W = bd.W, G = bd.G;
     const int P = S - W;
     const int rows_q = G * W;
+    const bool no_tail = bd.pad[0] == 3;            // profiling: every stage on, tail box not loaded
+    const bool one_k = bd.pad[0] == 4;              // profiling: no math, ONE K step per tile
+    const int dbg = no_tail ? 0 : (one_k ? 1 : bd.pad[0]);  // profiling: 1 = no math, 2 = no math, no MMA
     const int RB = rows_q <= 32 ? 32 : (rows_q <= 64 ? 64 : 128);  // rows per replica block, F = 128 / RB replicas
     const int n1 = (S + kVoteTile - 1) / kVoteTile, n2 = (P + kVoteTile - 1) / kVoteTile;
     const int n_items = n1 + n2;
@@ -447,9 +462,9 @@ __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __gri
     extern __shared__ __align__(1024) unsigned char smem_tma[];  // swizzle atoms need 1024-byte alignment
     unsigned char* smem = smem_tma;
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem);
-    const uint32_t bar_full = smem_u32(smem + 64);        // [kWsRing]  count = 1 (+ transaction bytes of the TMA loads)
-    const uint32_t bar_empty = bar_full + 8 * kWsRing;    // [kWsRing]  count = 1 (tcgen05.commit)
-    const uint32_t bar_tfull = bar_empty + 8 * kWsRing;   // [4]        count = 1 (tcgen05.commit)
+    const uint32_t bar_full = smem_u32(smem + 64);        // [RING]  count = 1 (+ transaction bytes of the TMA loads)
+    const uint32_t bar_empty = bar_full + 8 * RING;    // [RING]  count = 1 (tcgen05.commit)
+    const uint32_t bar_tfull = bar_empty + 8 * RING;   // [4]        count = 1 (tcgen05.commit)
     const uint32_t bar_tempty = bar_tfull + 8 * 4;        // [4]        count = 128 (math threads)
     float* s_m = reinterpret_cast<float*>(smem + 512);
     float* s_invl = reinterpret_cast<float*>(smem + 1024);
@@ -458,7 +473,7 @@ __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __gri
     unsigned char* s_ring = s_q + Q_BYTES;  // 1024-byte aligned: swizzle atoms are 8 rows x 128 B
 
     if (tid == 0) {
-        for (int i = 0; i < kWsRing; ++i) {
+        for (int i = 0; i < RING; ++i) {
             mbar_init(bar_full + 8 * i, 1);
             mbar_init(bar_empty + 8 * i, 1);
         }
@@ -510,7 +525,7 @@ __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __gri
         for (; i < n1; i += 4) {
             mbar_wait(bar_tfull + 8 * grp, (uint32_t)((i >> 2) & 1));
             tc_fence_after();
-            if (row_live && bd.pad[0] == 0) {
+            if (row_live && dbg == 0) {
                 const int key0 = i * kVoteTile;
                 const bool masked = key0 + kVoteTile > P;
                 tmem_ld16_async(t_lane + c_lo, va);
@@ -585,10 +600,10 @@ __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __gri
             mbar_wait(bar_tfull + 8 * grp, (uint32_t)((i >> 2) & 1));
             tc_fence_after();
             float vote0 = 0.f, vote1 = 0.f, vote2 = 0.f, vote3 = 0.f;
-            if (bd.pad[0] == 0) tmem_ld16_async(t_lane, va);
+            if (dbg == 0) tmem_ld16_async(t_lane, va);
 #pragma unroll
             for (int cb = 0; cb < kVoteM; cb += 16) {
-                if (cb < rows_q && bd.pad[0] == 0) {  // warp-uniform: padding query rows never vote
+                if (cb < rows_q && dbg == 0) {  // warp-uniform: padding query rows never vote
                     uint32_t(&v)[16] = ((cb >> 4) & 1) ? vb : va;
                     tmem_ld_wait();
                     if (cb + 16 < rows_q) tmem_ld16_async(t_lane + cb + 16, ((cb >> 4) & 1) ? va : vb);
@@ -615,43 +630,67 @@ __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __gri
         // ================================================================ TMA producer (one thread)
         if (lane == 0) {
             for (int i = 0; i < n_items; ++i) {
-                const int slot = i % kWsRing;
-                mbar_wait(bar_empty + 8 * slot, (uint32_t)(((i / kWsRing) & 1) ^ 1));  // fresh barrier: passes
+                const int slot = i % RING;
+                mbar_wait(bar_empty + 8 * slot, (uint32_t)(((i / RING) & 1) ^ 1));  // fresh barrier: passes
                 const int t = i < n1 ? i : i - n1;
-                mbar_arrive_expect_tx(bar_full + 8 * slot, TILE_BYTES);
+                const bool tail = REM > 0 && !no_tail;  // KVC_VOTE_DEBUG=3: timing without the 32-byte tail box
+                mbar_arrive_expect_tx(bar_full + 8 * slot, tail || REM == 0 ? TILE_BYTES : KH * BOX_BYTES);
 #pragma unroll
                 for (int kh = 0; kh < KH; ++kh)  // rows beyond S are zero-filled by the TMA unit
                     tma_load_4d(ring_addr + slot * TILE_BYTES + kh * BOX_BYTES, &L.map, kh * 64, t * kVoteTile, h, b,
                                 bar_full + 8 * slot);
-                if (REM > 0)
+                if (tail)
                     tma_load_4d(ring_addr + slot * TILE_BYTES + KH * BOX_BYTES, &L.map_tail, KH * 64, t * kVoteTile, h, b,
                                 bar_full + 8 * slot);
             }
         }
     } else if (warp == 17 && lane == 0) {
         // ================================================================ MMA issuer
-        for (int i = 0; i < n_items; ++i) {
-            const int slot = i % kWsRing, acc = i & 3;
+        // ONE thread issues everything, and a lone warp retires an instruction every ~5 clocks: stage isolation on the
+        // MHA shape showed copies + MMAs (no math) at 8.9 ms of the 9.4 ms call and copies alone at 6.0 ms, i.e. the
+        // ~180 instructions per tile spent building shared-memory descriptors were the bottleneck.  The descriptors
+        // are affine in the shared address, so the Q descriptors and the slot-0 key descriptors are built once and
+        // a tile costs one 32-bit add per K step.
+        uint32_t qd_lo[CPR / 2], kd_lo0[CPR / 2];  // low words; the high words are per-layout constants
+#pragma unroll
+        for (int ks = 0; ks < CPR / 2; ++ks) {
+            qd_lo[ks] = (uint32_t)umma_smem_desc(q_addr + ks * 2 * kVoteLBO, kVoteLBO, CPR * kVoteLBO);
+            kd_lo0[ks] = (ks >> 2) < KH ? (uint32_t)umma_smem_desc_sw128(ring_addr + (ks >> 2) * BOX_BYTES + (ks & 3) * 32)
+                                        : (uint32_t)umma_smem_desc_sw32(ring_addr + KH * BOX_BYTES);
+        }
+        const uint32_t qd_hi = (uint32_t)(umma_smem_desc(q_addr, kVoteLBO, CPR * kVoteLBO) >> 32);
+        const uint32_t k128_hi = (uint32_t)(umma_smem_desc_sw128(ring_addr) >> 32);
+        const uint32_t k32_hi = (uint32_t)(umma_smem_desc_sw32(ring_addr) >> 32);
+        auto pack = [](uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; };
+        // pass 2 only needs the live query rows as columns: N = G*W rounded up to 16 instead of 128 (MHA: 32) cuts the
+        // tensor time and the shared-memory reads of the Q operand by the same factor
+        const int n2cols = min(kVoteTile, (rows_q + 15) & ~15);
+        const uint32_t idesc2 = umma_idesc_f16(DT == KVC_DTYPE_BF16 ? 1 : 0, kVoteM, n2cols);
+        auto issue = [&](int i, auto keys_are_rows) {
+            const int slot = i % RING, acc = i & 3;
             mbar_wait(bar_tempty + 8 * acc, (uint32_t)(((i >> 2) & 1) ^ 1));  // accumulator drained (fresh: passes)
-            mbar_wait(bar_full + 8 * slot, (uint32_t)((i / kWsRing) & 1));    // tile landed
+            mbar_wait(bar_full + 8 * slot, (uint32_t)((i / RING) & 1));    // tile landed
             tc_fence_after();
-            const bool keys_are_rows = i >= n1;
-            const uint32_t kb = ring_addr + slot * TILE_BYTES;
-            if (bd.pad[0] < 2) {
+            const uint32_t slot16 = (uint32_t)(slot * TILE_BYTES) >> 4;  // start-address field counts 16-byte units
+            if (dbg < 2) {
 #pragma unroll
                 for (int ks = 0; ks < CPR / 2; ++ks) {
+                    if (one_k && ks > 0) break;
                     // keys: 128B-swizzled K-major box (8-row groups 1024 B apart), 32 bytes per K step inside the
-                    // box; queries: dense no-swizzle core matrices
-                    const uint64_t kd = (ks >> 2) < KH ? umma_smem_desc_sw128(kb + (ks >> 2) * BOX_BYTES + (ks & 3) * 32)
-                                                       : umma_smem_desc_sw32(kb + KH * BOX_BYTES);
-                    const uint64_t qd = umma_smem_desc(q_addr + ks * 2 * kVoteLBO, kVoteLBO, CPR * kVoteLBO);
-                    umma_f16(tmem + acc * kVoteTile, keys_are_rows ? kd : qd, keys_are_rows ? qd : kd, IDESC,
-                             ks > 0 ? 1u : 0u);
+                    // box (D = 80: one 32B-swizzled tail box); queries: dense no-swizzle core matrices
+                    const uint64_t kd = pack(kd_lo0[ks] + slot16, (ks >> 2) < KH ? k128_hi : k32_hi);
+                    const uint64_t qd = pack(qd_lo[ks], qd_hi);
+                    if (decltype(keys_are_rows)::value)
+                        umma_f16(tmem + acc * kVoteTile, kd, qd, idesc2, ks > 0 ? 1u : 0u);
+                    else
+                        umma_f16(tmem + acc * kVoteTile, qd, kd, IDESC, ks > 0 ? 1u : 0u);
                 }
             }
             umma_commit(bar_tfull + 8 * acc);
             umma_commit(bar_empty + 8 * slot);
-        }
+        };
+        for (int i = 0; i < n1; ++i) issue(i, std::false_type{});        // pass 1: A = Q, B = key tile
+        for (int i = n1; i < n_items; ++i) issue(i, std::true_type{});   // pass 2: A = key tile, B = Q
     }
     tc_fence_before();
     __syncthreads();

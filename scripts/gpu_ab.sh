@@ -1,4 +1,13 @@
-N="--steps 1 --warmup 3 --no-e2e --no-cpu-baseline --config c2_vote --batch 8"
-python bench.py $N > gpurun_out/plain_vote.log 2>&1 && \
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:kvc_snapkv_vote -s 3 -c 1 -o gpurun_out/prof_vote_c2 -f python bench.py $N > gpurun_out/ncu_vote.log 2>&1
-tail -2 gpurun_out/ncu_vote.log
+run() { # config batch env...
+  c=$1; b=$2; shift; shift
+  env "$@" timeout 300 python bench.py --steps 20 --warmup 3 --no-e2e --no-cpu-baseline --config $c --batch $b > gpurun_out/ab_$c.json 2> gpurun_out/ab.err
+  python -c "
+import json; d=json.loads(open('gpurun_out/ab_$c.json').read().strip().splitlines()[-1]); print('AB $c B=$b $*', d['us_per_step'], d['roofline']['launch_us_min'], d['roofline']['frac'], d['clocks']['sm_mhz'], d['clocks']['reasons'])"
+}
+OLD=KVC_LIBRARY=$PWD/scripts/ab/libkvc_old.so
+run c4_vote 16 $OLD
+run c4_vote 16
+run c4_vote 16 $OLD
+run c4_vote 16
+run c2_vote 32 $OLD
+run c2_vote 32
