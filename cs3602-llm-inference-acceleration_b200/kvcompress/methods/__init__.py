@@ -1,52 +1,57 @@
-"""Registry of compression methods — the drop-in plugin surface (reference methods/__init__.py:21-78)."""
+"""Registry of compression methods — the drop-in plugin surface (reference methods/__init__.py:21-78).
 
+Every entry is a callable ``fn(past_key_values, <method kwargs>, skip_layers=..., **kwargs)`` returning a new list of
+per-layer ``(K, V)`` tuples; all of them plan on the host and run one fused sm_100a launch per call."""
+
+from importlib import import_module
 from typing import Callable, Dict, List
 
-from .l2_compress import l2_compress
-from .fix_size_l2 import fix_size_l2_compress
-from .streaming_llm import streaming_llm_compress, evict_for_space
-from .recent_only import recent_only_compress
-from .h2o_l2 import h2o_l2_compress
-from .h2o_attention import h2o_attention_compress, H2OAttentionManager, create_h2o_manager_from_model
-from .snapkv_lite import snapkv_lite_compress
-from .pyramid_kv import pyramid_kv_compress
-from .adaptive_l2 import adaptive_l2_compress
+# registry name, defining module, function name — in the order list_methods() reports (reference :21-33)
+_METHOD_TABLE = (
+    ("l2_compress", "l2_compress", "l2_compress"),
+    ("fix_size_l2", "fix_size_l2", "fix_size_l2_compress"),
+    ("streaming_llm", "streaming_llm", "streaming_llm_compress"),
+    ("recent_only", "recent_only", "recent_only_compress"),
+    ("h2o_l2", "h2o_l2", "h2o_l2_compress"),
+    ("h2o_attention", "h2o_attention", "h2o_attention_compress"),
+    ("snapkv_lite", "snapkv_lite", "snapkv_lite_compress"),
+    ("pyramid_kv", "pyramid_kv", "pyramid_kv_compress"),
+    ("adaptive_l2", "adaptive_l2", "adaptive_l2_compress"),
+)
+# helpers the reference exports next to the compress functions
+_EXTRA_EXPORTS = (
+    ("streaming_llm", "evict_for_space"),
+    ("h2o_attention", "H2OAttentionManager"),
+    ("h2o_attention", "create_h2o_manager_from_model"),
+)
 
-# name -> callable; insertion order is the order list_methods() reports (reference :21-33)
-COMPRESS_METHODS: Dict[str, Callable] = {
-    "l2_compress": l2_compress,
-    "fix_size_l2": fix_size_l2_compress,
-    "streaming_llm": streaming_llm_compress,
-    "recent_only": recent_only_compress,
-    "h2o_l2": h2o_l2_compress,
-    "h2o_attention": h2o_attention_compress,
-    "snapkv_lite": snapkv_lite_compress,
-    "pyramid_kv": pyramid_kv_compress,
-    "adaptive_l2": adaptive_l2_compress,
-}
+COMPRESS_METHODS: Dict[str, Callable] = {}
+__all__ = ["get_compress_fn", "list_methods", "register_method", "COMPRESS_METHODS"]
+
+for _name, _module, _attr in _METHOD_TABLE:
+    _fn = getattr(import_module(f"{__name__}.{_module}"), _attr)
+    COMPRESS_METHODS[_name] = _fn
+    globals()[_attr] = _fn
+    __all__.append(_attr)
+for _module, _attr in _EXTRA_EXPORTS:
+    globals()[_attr] = getattr(import_module(f"{__name__}.{_module}"), _attr)
+    __all__.append(_attr)
+del _name, _module, _attr, _fn
 
 
 def get_compress_fn(method: str) -> Callable:
-    """Look a method up by name; unknown names raise ``ValueError`` listing what exists (:36-61)."""
-    if method not in COMPRESS_METHODS:
-        available = list(COMPRESS_METHODS.keys())
-        raise ValueError(f"Unknown method: {method}. Available: {available}")
-    return COMPRESS_METHODS[method]
+    """The callable registered under ``method``; an unknown name raises ``ValueError`` naming what exists (:36-61)."""
+    try:
+        return COMPRESS_METHODS[method]
+    except KeyError:
+        raise ValueError(f"Unknown method: {method}. Available: {list(COMPRESS_METHODS)}") from None
 
 
 def list_methods() -> List[str]:
-    """Registered method names (:64-66)."""
-    return list(COMPRESS_METHODS.keys())
+    """Registered names, registration order (:64-66)."""
+    return list(COMPRESS_METHODS)
 
 
 def register_method(name: str, fn: Callable) -> None:
-    """Add or replace a method: ``fn(past_key_values, **kwargs) -> List[Tuple[Tensor, Tensor]]`` (:69-78)."""
+    """Add or replace ``name``; ``fn(past_key_values, **kwargs) -> List[Tuple[Tensor, Tensor]]`` (:69-78)."""
     COMPRESS_METHODS[name] = fn
-
-
-__all__ = [
-    "l2_compress", "fix_size_l2_compress", "streaming_llm_compress", "evict_for_space", "recent_only_compress",
-    "h2o_l2_compress", "h2o_attention_compress", "H2OAttentionManager", "create_h2o_manager_from_model",
-    "snapkv_lite_compress", "pyramid_kv_compress", "adaptive_l2_compress",
-    "get_compress_fn", "list_methods", "register_method", "COMPRESS_METHODS",
-]
