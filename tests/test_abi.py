@@ -47,3 +47,27 @@ def test_library_metadata_and_argument_checks():
 
 def test_structs_match_header_sizes():
     assert _engine._PLAN.size == 32 and _engine._IO.size == 104 and _engine._SHAPE.size == 20
+
+
+def test_vote_workspace_sizing_is_opt_in_and_grows_with_the_sequence(monkeypatch):
+    """kvc_vote_workspace_bytes is pure host arithmetic: 0 unless the split-sequence form is asked for, then one
+    1 KB row-statistics record per (unit, slice) plus per-unit counters and final rows."""
+    lib = _engine.load_library()
+
+    def need(B, H, D, S, n_layers=2):
+        shape = _engine._SHAPE.pack(B, H, D, 2, 0)
+        layer = _engine._VOTE.pack(16, 16, 16, H * S * D, S * D, D, 4 * H * 32 * D, 32 * D, D, S, 0)
+        return int(lib.kvc_vote_workspace_bytes(shape, n_layers, layer * n_layers))
+
+    monkeypatch.delenv("KVC_VOTE_SPLIT", raising=False)
+    assert need(2, 8, 128, 32768) == 0
+    monkeypatch.setenv("KVC_VOTE_SPLIT", "1")
+    monkeypatch.setenv("KVC_VOTE_TS", "8")
+    small, big = need(2, 8, 128, 4096), need(2, 8, 128, 32768)
+    units = 2 * 8 * 2
+    assert small >= units * (4096 // 128 // 8) * 1024 and big >= units * (32768 // 128 // 8) * 1024
+    assert small < big and big % 256 == 0
+    assert need(2, 8, 96, 4096) == 0                       # head_dim 96: no vote kernel for that row width
+    shape32 = _engine._SHAPE.pack(2, 8, 128, 0, 0)        # fp32 caches: the vote runs on 16-bit data only
+    layer = _engine._VOTE.pack(16, 16, 16, 1, 1, 128, 1, 1, 128, 4096, 0)
+    assert lib.kvc_vote_workspace_bytes(shape32, 1, layer) == 0
