@@ -406,6 +406,80 @@ def test_oracle_parity_at_product_row_widths(name, method, kwargs, dtype, D, sty
 
 
 # ----------------------------------------------------------------------------------------------
+# Region lengths around the block sizes of the select (32 x 8 keys per warp step) and of the pooling transform
+# (128 rows per warp step, 4 per lane), for every specialised pooling kernel and the generic one.
+EDGE_R = [5, 7, 8, 33, 127, 128, 129, 255, 256, 257, 511, 513, 1023, 1025, 2047, 2049, 4100]
+
+
+@pytest.mark.parametrize("dtype,D", [("bf16", 128), ("f32", 80), ("f16", 64)], ids=["bf16-D128", "f32-D80", "f16-D64"])
+@pytest.mark.parametrize("pk", [1, 3, 4, 5, 7, 9])
+def test_snapkv_region_lengths_around_block_boundaries(pk, dtype, D):
+    w = 8
+    for style in ("spread", "ties"):
+        if style == "ties" and dtype == "f32":
+            continue
+        seq_lens = [r + w for r in EDGE_R]
+        kwargs = dict(observation_window=w, keep_size=w + 3, pooling_kernel=pk, skip_layers=[])
+        case = cases._case(f"edge/snapkv/pk{pk}/{dtype}/{style}", "snapkv_lite", kwargs, seq_lens, dtype=dtype, style=style,
+                           B=1, H=2, D=D, seed=pk * 131 + D)
+        layers = cases.case_cache(case)
+        kv = kv_to_torch(layers, dtype)
+        results = O.METHODS["snapkv_lite"](layers, dtype, **kwargs)
+        plans = plan_for("snapkv_lite", seq_lens, kwargs)
+        out, idx = _engine.run_plans(kv, plans, return_indices=True)
+        for li, res in enumerate(results):
+            if plans[li].kind != P.GATHER:
+                continue
+            k_in, v_in = kv[li]
+            rows = idx[li]
+            assert torch.equal(out[li][0], gather_rows(k_in, rows)) and torch.equal(out[li][1], gather_rows(v_in, rows))
+            info = O.check_layer(layers[li][0], dtype, res, rows.cpu().numpy())
+            assert info["valid"], (case["name"], seq_lens[li], info)
+            if dtype == "f32":
+                assert info["identical_heads"] == info["heads"], (case["name"], seq_lens[li], info)
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "f32"])
+def test_select_region_lengths_and_large_k(dtype):
+    """Few rows kept (h2o_l2) and nearly all rows kept (l2_compress at 0.97) on every edge length, ties included."""
+    for style in ("spread", "ties"):
+        if style == "ties" and dtype == "f32":
+            continue
+        seq_lens = [r + 12 for r in EDGE_R if r > 8]
+        kwargs = dict(start_size=4, heavy_hitter_size=3, recent_size=8, skip_layers=[])  # a handful of rows of each region
+        case = cases._case(f"edge/h2o/{dtype}/{style}", "h2o_l2", kwargs, seq_lens, dtype=dtype, style=style,
+                           B=1, H=2, D=64 if dtype == "bf16" else 32, seed=20)
+        layers = cases.case_cache(case)
+        kv = kv_to_torch(layers, dtype)
+        results = O.METHODS["h2o_l2"](layers, dtype, **kwargs)
+        plans = plan_for("h2o_l2", seq_lens, kwargs)
+        out, idx = _engine.run_plans(kv, plans, return_indices=True)
+        for li, res in enumerate(results):
+            if plans[li].kind != P.GATHER:
+                continue
+            rows = idx[li]
+            assert torch.equal(out[li][0], gather_rows(kv[li][0], rows))
+            info = O.check_layer(layers[li][0], dtype, res, rows.cpu().numpy())
+            assert info["valid"], (case["name"], seq_lens[li], info)
+    # keep most of a region (l2_compress, keep_ratio 0.97): k close to R on every edge length
+    seq_lens = [r for r in EDGE_R if r >= 127]
+    kwargs = dict(keep_ratio=0.97, prune_after=10, skip_layers=[])
+    case = cases._case(f"edge/l2/{dtype}", "l2_compress", kwargs, seq_lens, dtype=dtype, style="ties" if dtype == "bf16" else "spread",
+                       B=1, H=2, D=64, seed=5)
+    layers = cases.case_cache(case)
+    kv = kv_to_torch(layers, dtype)
+    results = O.METHODS["l2_compress"](layers, dtype, **kwargs)
+    plans = plan_for("l2_compress", seq_lens, kwargs)
+    out, idx = _engine.run_plans(kv, plans, return_indices=True)
+    for li, res in enumerate(results):
+        if plans[li].kind != P.GATHER:
+            continue
+        info = O.check_layer(layers[li][0], dtype, res, idx[li].cpu().numpy())
+        assert info["valid"], (case["name"], seq_lens[li], info)
+        assert torch.equal(out[li][0], gather_rows(kv[li][0], idx[li]))
+
+
+# ----------------------------------------------------------------------------------------------
 # Selections larger than shared memory: radix keys / kept indices fall back to a device workspace
 BIG = [
     ("l2_08_32k_f32", "l2_compress", dict(keep_ratio=0.8, prune_after=100, skip_layers=[]), 2, 1, 2, 32768, 64, torch.float32),
