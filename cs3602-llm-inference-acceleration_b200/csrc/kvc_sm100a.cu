@@ -360,6 +360,19 @@ struct TmaPlan {
     size_t smem = 0;
 };
 
+static int env_int(const char* name, int dflt);
+// KVC_VOTE_DEBUG switches stages of the vote kernels off for stage-isolation timing (1 = no math, 2 = no math, no
+// MMA, 3 = no tail box, 4 = one K step): the votes it produces are NOT valid, so say so, once, on stderr.
+static int vote_debug_mode() {
+    const int d = env_int("KVC_VOTE_DEBUG", 0);
+    static bool warned = false;
+    if (d != 0 && !warned) {
+        warned = true;
+        fprintf(stderr, "libkvc_sm100a: KVC_VOTE_DEBUG=%d is a profiling mode, kvc_snapkv_vote results are not valid\n", d);
+    }
+    return d;
+}
+
 static int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     return (v && *v) ? atoi(v) : dflt;
@@ -1131,7 +1144,7 @@ static int launch_vote_tma(const kvc_shape* shape, int32_t n_layers, const kvc_v
         bd.G = group;
         bd.W = window;
         bd.scale_log2e = 1.4426950408889634f / sqrtf((float)D);
-        bd.pad[0] = env_int("KVC_VOTE_DEBUG", 0);
+        bd.pad[0] = vote_debug_mode();
         for (int l = 0; l < nl; ++l) {
             const kvc_vote_layer& v = layers[l0 + l];
             VoteTmaLayerDev& d = bd.layers[l];
@@ -1349,7 +1362,7 @@ int kvc_snapkv_vote_ws(const kvc_shape* shape, int32_t n_layers, const kvc_vote_
         bd.G = group;
         bd.W = window;
         bd.scale_log2e = 1.4426950408889634f / sqrtf((float)shape->head_dim);
-        bd.pad[0] = env_int("KVC_VOTE_DEBUG", 0);  // stage isolation for profiling: 1 = no math, 2 = no math, no MMA
+        bd.pad[0] = vote_debug_mode();  // stage isolation for profiling: 1 = no math, 2 = no math, no MMA
         for (int l = 0; l < nl; ++l) {
             const kvc_vote_layer& v = layers[l0 + l];
             VoteLayerDev& d = bd.layers[l];
