@@ -208,13 +208,11 @@ __global__ void __launch_bounds__(NT, MINB) kvc_slab_compress_kernel(const __gri
     const uint32_t slot = smem_u32(smem + bd.off_stage) + (uint32_t)warp * (32 * RB);
     const uint32_t bar = smem_u32(smem + kMiscInts * 4) + (uint32_t)warp * 8;
     uint32_t parity = 0;
-    if (stager) {
-        if (lane == 0) {
-            mbar_init(bar, 1);
-            mbar_init_fence();
-        }
-        __syncwarp();
+    if (lane == 0) {  // every warp: the slide below stages rows in more slots than the launch plan has (see there)
+        mbar_init(bar, 1);
+        mbar_init_fence();
     }
+    __syncwarp();
 
     const int R = L.hi - L.lo;
     const int ksel = L.ksel;
@@ -281,10 +279,22 @@ __global__ void __launch_bounds__(NT, MINB) kvc_slab_compress_kernel(const __gri
     if (jf >= C) return;  // nothing moves (CTA-uniform)
 
     // ---------------------------------------------------------- slide rows down, K then V, in rounds
+    // The radix keys are dead once the kept indices exist: when they live on chip their shared memory joins the
+    // staging area, so a round moves up to NT/32 blocks of 32 rows instead of `nsw` (at 32K rows the plan leaves 4
+    // slots next to 64 KB of keys: 8 rounds of load -> barrier -> store per unit become 4).
+    int g_nsw = nsw;
+    uint32_t g_slot = slot;
+    if (bd.ws == nullptr) {
+        const int lo = (bd.off_keys + 127) & ~127;
+        const int room = bd.off_stage + nsw * (32 * RB) - lo;
+        g_nsw = min(NT / 32, room / (32 * RB));
+        g_slot = smem_u32(smem + lo) + (uint32_t)warp * (32 * RB);
+    }
+    const bool g_stager = warp < g_nsw;
     const int nb = (C - jf + 31) >> 5;
-    for (int t0 = 0; t0 < 2 * nb; t0 += nsw) {
+    for (int t0 = 0; t0 < 2 * nb; t0 += g_nsw) {
         const int t = t0 + warp;
-        const bool active = stager && t < 2 * nb;
+        const bool active = g_stager && t < 2 * nb;
         const bool isv = t >= nb;
         const int j0 = jf + ((isv ? t - nb : t) << 5);
         const int rows = min(32, C - j0);
@@ -292,14 +302,14 @@ __global__ void __launch_bounds__(NT, MINB) kvc_slab_compress_kernel(const __gri
             const int j = j0 + lane;
             const int row = lane < rows ? src_row(j) : 0;
             const char* src = (isv ? vbase : kbase) + (int64_t)row * RB;
-            warp_load_rows<RB>(slot, bar, src, rows, true, lane);
+            warp_load_rows<RB>(g_slot, bar, src, rows, true, lane);
             mbar_wait(bar, parity);
             parity ^= 1;
         }
         __syncthreads();  // every source row of this round is on chip before any destination is written
         if (active) {
             if (lane == 0) {
-                bulk_s2g((isv ? vbase : kbase) + (int64_t)j0 * RB, slot, (uint32_t)rows * RB);
+                bulk_s2g((isv ? vbase : kbase) + (int64_t)j0 * RB, g_slot, (uint32_t)rows * RB);
                 bulk_commit();
                 bulk_wait_read<0>();
             }
