@@ -1,7 +1,7 @@
 // kvc_device.cuh — device-side building blocks of the sm_100a KV-compression path.
 //
-//   K1  row_sumsq / group_sum     128-bit coalesced loads of key rows, fp32 sum of squares,
-//                                 warp-shuffle reduction over the lanes that share a row
+//   K1  Traits<DT>::sumsq         fp32 sum of squares of one 16-byte chunk of a key row (the rows themselves are
+//                                 staged by the TMA unit, kvc_fused_tma.cuh)
 //                                 (replaces torch.norm(K, p=2, dim=-1), e.g. l2_compress.py:70)
 //   K2  block_radix_select        per-(b,h) radix select in shared memory: 11-bit histogram
 //                                 fused into the scan, then refinement passes over the
@@ -9,9 +9,6 @@
 //                                 are emitted already ascending (replaces argsort + [:k] +
 //                                 torch.sort, e.g. h2o_l2.py:128-132, and topk + sort,
 //                                 snapkv_lite.py:134-137)
-//   K3  gather loop               row-granular 16-byte-chunk gather of K and V straight into
-//                                 the compacted output (replaces expand + gather x2 + cat x2,
-//                                 e.g. fix_size_l2.py:132-147)
 //
 // Everything here is HBM-bound byte/compare work: no tensor cores on purpose.
 #pragma once
@@ -48,14 +45,17 @@ struct LayerDev {
     int64_t ksb, ksh, kss;  // BYTE strides of K (batch, head, row)
     int64_t vsb, vsh, vss;  // BYTE strides of V
     int32_t S, sink, lo, hi, ksel, tail, score, pool;
+    const char* n_in;       // optional stored key norms [B,H,>=S] (cache dtype): scores without reading K
+    int64_t nsb, nsh;       // BYTE strides of the norm array (batch, head)
+    int64_t pad;
 };
-static_assert(sizeof(LayerDev) == 128, "LayerDev is passed by value in kernel params");
+static_assert(sizeof(LayerDev) == 160, "LayerDev is passed by value in kernel params");
 
 struct BatchDev {
     int32_t B, H;
     int32_t idx_cap;   // ints reserved for the kept-index list in shared memory
-    int32_t cpr;       // 16-byte chunks per row (generic path reads it at run time)
-    int32_t lpr, cpl;  // LDG form, generic path: lanes per row (power of two) and chunks per lane
+    int32_t cpr;       // 16-byte chunks per row (the generic-width kernels read it at run time)
+    int32_t pad0, pad1;
     int32_t nsw;       // TMA form: warps that own a staging slot (<= warps per CTA)
     int32_t off_hist, off_idx, off_keys, off_stage;  // TMA form: shared-memory layout (bytes)
     int32_t upc;       // TMA form: consecutive (batch, head) units walked by one CTA
@@ -160,29 +160,8 @@ __device__ __forceinline__ void stg128_stream(void* p, int4 v) {
                  : "memory");
 }
 
-// ---------------------------------------------------------------- K1: lane-group reduction
-// Sum `v` over groups of N consecutive lanes (group g = lanes [g*N, g*N+N)); the result is
-// valid in the first lane of each group.  The summation order is fixed, so a row's norm does
-// not depend on where in the warp the row was processed.
-template <int N>
-__device__ __forceinline__ float group_sum(float v) {
-    if constexpr (N == 1) {
-        return v;
-    } else if constexpr ((N & (N - 1)) == 0) {
-#pragma unroll
-        for (int o = N / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        return v;
-    } else if constexpr (N % 2 == 0) {
-        v += __shfl_down_sync(0xffffffffu, v, N / 2);
-        return group_sum<N / 2>(v);  // first N/2 lanes of the group now hold pair sums
-    } else {
-        float t = v;
-#pragma unroll
-        for (int j = 1; j < N; ++j) t += __shfl_down_sync(0xffffffffu, v, j);
-        return t;
-    }
-}
-// Runtime power-of-two group width (generic head_dim path).
+// ---------------------------------------------------------------- K1 (stand-alone kvc_key_norms): lane-group reduction
+// Sum over groups of n consecutive lanes (n a power of two).
 __device__ __forceinline__ float group_sum_pow2(float v, int n) {
     for (int o = n >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
@@ -374,7 +353,8 @@ __device__ __forceinline__ void block_radix_select(const Key* __restrict__ keys,
 // thread (a one-element-per-thread loop is latency-bound: profiles/r01_slab_ncu_full_c5_before_vec.json — 48 % of
 // stall samples on 2-byte loads).  Lines that straddle the ends are read element by element; short arrays keep
 // one element per thread so that every thread is busy.
-template <int DT, int NT, typename Emit>
+// NC = false: plain (coherent) loads, for values the SAME kernel wrote earlier (the fused vote's scores).
+template <int DT, int NT, bool NC = true, typename Emit>
 __device__ __forceinline__ void load_keys_vectorised(const typename Traits<DT>::Key* src, int R,
                                                      typename Traits<DT>::Key* /*keys*/, Emit emit) {
     using Key = typename Traits<DT>::Key;
@@ -394,7 +374,7 @@ __device__ __forceinline__ void load_keys_vectorised(const typename Traits<DT>::
         for (int u = 0; u < U; ++u) {
             const int c = c0 + u * NT;
             const bool whole = c < nline && c * KV - a >= 0 && (c + 1) * KV - a <= R;
-            v[u] = whole ? __ldg(lines + c) : make_int4(0, 0, 0, 0);
+            v[u] = whole ? (NC ? __ldg(lines + c) : *(lines + c)) : make_int4(0, 0, 0, 0);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {

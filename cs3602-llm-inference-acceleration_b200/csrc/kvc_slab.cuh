@@ -34,6 +34,7 @@ static_assert(sizeof(SlabLayerDev) == 128, "SlabLayerDev is passed by value in k
 struct SlabBatchDev {
     int32_t B, H;
     int32_t idx_cap, nsw;
+    int32_t cpr, pad0;  // cpr: 16-byte chunks per row (read by the generic-width kernel)
     int32_t off_hist, off_idx, off_keys, off_stage;
     char* ws;  // optional workspace (see BatchDev)
     int64_t ws_unit, ws_keys;
@@ -54,7 +55,7 @@ static_assert(sizeof(AppendLayerDev) == 144, "AppendLayerDev is passed by value 
 
 struct AppendBatchDev {
     int32_t B, H;
-    int32_t max_new, pad;
+    int32_t max_new, cpr;  // cpr: 16-byte chunks per row (read by the generic-width kernels)
     AppendLayerDev layers[KVC_MAX_LAYERS_PER_LAUNCH];
 };
 
@@ -62,7 +63,7 @@ struct AppendBatchDev {
 // parameters instead of 9 KB, so the launch itself is as cheap as the torch.cat it replaces.
 struct AppendOneDev {
     int32_t B, H;
-    int32_t max_new, pad;
+    int32_t max_new, cpr;
     AppendLayerDev layers[1];
 };
 
@@ -71,8 +72,18 @@ constexpr int kMiscFirst = 3;  // misc[] slot: first output row whose source row
 // Same value as row_sumsq_smem (chunk sums + balanced tree; the tree is invariant under the
 // scan's XOR read order), reading the row from global memory and optionally copying it.
 template <int DT, int CPR>
-__device__ __forceinline__ float row_sumsq_copy(const char* src, char* dst) {
+__device__ __forceinline__ float row_sumsq_copy(const char* src, char* dst, int cpr) {
     using Tr = Traits<DT>;
+    if constexpr (CPR == 0) {  // generic width: chunk sums in chunk order (row_sumsq_smem, CPR == 0)
+        float tot = 0.f;
+        for (int c = 0; c < cpr; ++c) {
+            const int4 v = *reinterpret_cast<const int4*>(src + c * 16);
+            const float a = Tr::sumsq(v, 0.f);
+            tot = (c == 0) ? a : tot + a;
+            *reinterpret_cast<int4*>(dst + c * 16) = v;
+        }
+        return tot;
+    } else {
     constexpr int SB = swz_bits(CPR);
     constexpr int G = 1 << SB;
     float acc[CPR];
@@ -93,13 +104,15 @@ __device__ __forceinline__ float row_sumsq_copy(const char* src, char* dst) {
         tot = (g == 0) ? acc[0] : tot + acc[g * G];
     }
     return tot;
+    }
 }
 
 template <int DT, int CPR, typename Params>
 __global__ void __launch_bounds__(128) kvc_slab_append_kernel(const __grid_constant__ Params bd) {
     using Tr = Traits<DT>;
     using Key = typename Tr::Key;
-    constexpr int RB = CPR * 16;
+    const int cpr = CPR > 0 ? CPR : bd.cpr;
+    const int RB = cpr * 16;
     const AppendLayerDev& L = bd.layers[blockIdx.y];
     const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // flat (bh, t)
     const int T = L.n_new;
@@ -111,9 +124,13 @@ __global__ void __launch_bounds__(128) kvc_slab_append_kernel(const __grid_const
     const char* vs = L.v_new + (int64_t)b * L.nvsb + (int64_t)h * L.nvsh + (int64_t)t * L.nvss;
     char* kd = L.k + (int64_t)b * L.ksb + (int64_t)h * L.ksh + (int64_t)row * RB;
     char* vd = L.v + (int64_t)b * L.vsb + (int64_t)h * L.vsh + (int64_t)row * RB;
-    const float ss = row_sumsq_copy<DT, CPR>(ks, kd);
+    const float ss = row_sumsq_copy<DT, CPR>(ks, kd, cpr);
+    if constexpr (CPR > 0) {
 #pragma unroll
-    for (int c = 0; c < CPR; ++c) *reinterpret_cast<int4*>(vd + c * 16) = *reinterpret_cast<const int4*>(vs + c * 16);
+        for (int c = 0; c < CPR; ++c) *reinterpret_cast<int4*>(vd + c * 16) = *reinterpret_cast<const int4*>(vs + c * 16);
+    } else {
+        for (int c = 0; c < cpr; ++c) *reinterpret_cast<int4*>(vd + c * 16) = *reinterpret_cast<const int4*>(vs + c * 16);
+    }
     Key* nd = reinterpret_cast<Key*>(L.n + (int64_t)b * L.nsb + (int64_t)h * L.nsh);
     nd[row] = (Key)Tr::to_raw(sqrtf(ss));
 }
@@ -126,12 +143,13 @@ template <int DT, int CPR>
 __global__ void __launch_bounds__(256, 3) kvc_slab_append_tma_kernel(const __grid_constant__ AppendBatchDev bd) {
     using Tr = Traits<DT>;
     using Key = typename Tr::Key;
-    constexpr int RB = CPR * 16;
+    const int cpr = CPR > 0 ? CPR : bd.cpr;
+    const int RB = cpr * 16;
     const AppendLayerDev& L = bd.layers[blockIdx.y];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     extern __shared__ __align__(128) unsigned char smem[];
     const uint32_t bar = smem_u32(smem) + (uint32_t)warp * 8;
-    const uint32_t slot = smem_u32(smem + 128) + (uint32_t)warp * (32 * RB);
+    const uint32_t slot = smem_u32(smem + 128) + (uint32_t)(warp * 32 * RB);
     if (lane == 0) {
         mbar_init(bar, 1);
         mbar_init_fence();
@@ -153,27 +171,27 @@ __global__ void __launch_bounds__(256, 3) kvc_slab_append_tma_kernel(const __gri
         char* kd = L.k + (int64_t)b * L.ksb + (int64_t)h * L.ksh + (int64_t)row0 * RB;
         char* vd = L.v + (int64_t)b * L.vsb + (int64_t)h * L.vsh + (int64_t)row0 * RB;
         // keys: stage, reduce, store
-        warp_load_rows<RB>(slot, bar, ks, rows, kdense, lane);
+        warp_load_rows(slot, bar, ks, rows, kdense, lane, RB);
         mbar_wait(bar, parity);
         parity ^= 1;
         if (lane < rows) {
-            const float ss = row_sumsq_smem<DT, CPR>(slot + (uint32_t)lane * RB, lane);
+            const float ss = row_sumsq_smem<DT, CPR>(slot + (uint32_t)(lane * RB), lane, cpr);
             Key* nd = reinterpret_cast<Key*>(L.n + (int64_t)b * L.nsb + (int64_t)h * L.nsh);
             nd[row0 + lane] = (Key)Tr::to_raw(sqrtf(ss));
         }
         __syncwarp();
         if (lane == 0) {
-            bulk_s2g(kd, slot, (uint32_t)rows * RB);
+            bulk_s2g(kd, slot, (uint32_t)(rows * RB));
             bulk_commit();
             bulk_wait_read<0>();
         }
         __syncwarp();
         // values: stage, store
-        warp_load_rows<RB>(slot, bar, vs, rows, vdense, lane);
+        warp_load_rows(slot, bar, vs, rows, vdense, lane, RB);
         mbar_wait(bar, parity);
         parity ^= 1;
         if (lane == 0) {
-            bulk_s2g(vd, slot, (uint32_t)rows * RB);
+            bulk_s2g(vd, slot, (uint32_t)(rows * RB));
             bulk_commit();
             bulk_wait_read<0>();
         }
@@ -185,8 +203,7 @@ template <int DT, int CPR, int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) kvc_slab_compress_kernel(const __grid_constant__ SlabBatchDev bd) {
     using Tr = Traits<DT>;
     using Key = typename Tr::Key;
-    constexpr int RB = CPR * 16;
-    constexpr int kShift0 = Tr::kKeyBits - kHistBits;
+    const int RB = (CPR > 0 ? CPR : bd.cpr) * 16;
 
     const SlabLayerDev& L = bd.layers[blockIdx.y];
     const int bh = blockIdx.x;
@@ -205,7 +222,7 @@ __global__ void __launch_bounds__(NT, MINB) kvc_slab_compress_kernel(const __gri
     }
     const int nsw = bd.nsw;
     const bool stager = warp < nsw;
-    const uint32_t slot = smem_u32(smem + bd.off_stage) + (uint32_t)warp * (32 * RB);
+    const uint32_t slot = smem_u32(smem + bd.off_stage) + (uint32_t)(warp * 32 * RB);
     const uint32_t bar = smem_u32(smem + kMiscInts * 4) + (uint32_t)warp * 8;
     uint32_t parity = 0;
     if (lane == 0) {  // every warp: the slide below stages rows in more slots than the launch plan has (see there)
@@ -229,37 +246,22 @@ __global__ void __launch_bounds__(NT, MINB) kvc_slab_compress_kernel(const __gri
         misc[kMiscFirst] = C;
     }
     if (ksel > 0 && score == KVC_SCORE_GIVEN_INDEX) {
+        // caller-supplied rows: strictly ascending absolute rows of the region (kvc.h); clamped into the slab so
+        // that a bad index can never become a wild bulk copy
         const int32_t* src = L.idx_in + (int64_t)bh * ksel;
-        for (int i = tid; i < ksel; i += NT) sidx[i] = src[i];
+        for (int i = tid; i < ksel; i += NT) sidx[i] = min(max(src[i], 0), L.S - 1);
     } else if (ksel > 0) {
         // ---------------------------------------------------------- keys from the stored norms
         for (int i = tid; i < kHistBins; i += NT) hist[i] = 0;
         __syncthreads();
-        const bool snap = (score == KVC_SCORE_SNAPKV_POOL);
-        const bool desc = (score == KVC_SCORE_L2_HIGH);
-        uint32_t local_max = 0;
-        load_keys_vectorised<DT, NT>(nbase + L.lo, R, keys, [&](int i, uint32_t raw) {
-            if (snap) {
-                keys[i] = (Key)raw;
-                local_max = max(local_max, raw);
-            } else {
-                const Key key = ordered_key<Key>(raw, desc);
-                keys[i] = key;
-                atomicAdd(&hist[(uint32_t)key >> kShift0], 1u);
-            }
-        });
-        if (snap) {
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
-            if (lane == 0) atomicMax(reinterpret_cast<uint32_t*>(&misc[kMiscMaxRaw]), local_max);
-        }
+        keys_from_values<DT, NT>(nbase + L.lo, R, score, keys, hist, misc);
         __syncthreads();
-        if (snap) snapkv_transform<DT, NT>(keys, R, L.pool, hist, misc);
+        if (score == KVC_SCORE_SNAPKV_POOL) snapkv_transform<DT, NT>(keys, R, L.pool, hist, misc);
         block_radix_select<Key, NT>(keys, R, ksel, hist, misc, sidx, L.lo);
     }
     __syncthreads();
 
-    auto src_row = [&](int j) -> int { return j < sink ? j : (j < sink + ksel ? sidx[j - sink] : j + tail0); };
+    const KeepMap src_row{sidx, sink, ksel, tail0};
     // ---------------------------------------------------------- first row that actually moves
     {
         int first = C;
@@ -288,7 +290,7 @@ __global__ void __launch_bounds__(NT, MINB) kvc_slab_compress_kernel(const __gri
         const int lo = (bd.off_keys + 127) & ~127;
         const int room = bd.off_stage + nsw * (32 * RB) - lo;
         g_nsw = min(NT / 32, room / (32 * RB));
-        g_slot = smem_u32(smem + lo) + (uint32_t)warp * (32 * RB);
+        g_slot = smem_u32(smem + lo) + (uint32_t)(warp * 32 * RB);
     }
     const bool g_stager = warp < g_nsw;
     const int nb = (C - jf + 31) >> 5;
@@ -302,14 +304,14 @@ __global__ void __launch_bounds__(NT, MINB) kvc_slab_compress_kernel(const __gri
             const int j = j0 + lane;
             const int row = lane < rows ? src_row(j) : 0;
             const char* src = (isv ? vbase : kbase) + (int64_t)row * RB;
-            warp_load_rows<RB>(g_slot, bar, src, rows, true, lane);
+            warp_load_rows(g_slot, bar, src, rows, true, lane, RB);
             mbar_wait(bar, parity);
             parity ^= 1;
         }
         __syncthreads();  // every source row of this round is on chip before any destination is written
         if (active) {
             if (lane == 0) {
-                bulk_s2g((isv ? vbase : kbase) + (int64_t)j0 * RB, g_slot, (uint32_t)rows * RB);
+                bulk_s2g((isv ? vbase : kbase) + (int64_t)j0 * RB, g_slot, (uint32_t)(rows * RB));
                 bulk_commit();
                 bulk_wait_read<0>();
             }

@@ -22,19 +22,21 @@
 #include "kvc_fused_tma.cuh"
 #include "kvc_slab.cuh"
 #include "kvc_vote.cuh"
-#include "kvc_vote_split.cuh"
 
-// The library is ONE source file, but its ~170 kernel instantiations compile serially: the build compiles it three
+// The library is ONE source file, but its kernel instantiations compile serially: the build compiles it several
 // times in parallel, each pass keeping one group of entry points (and only the kernels they launch), and links the
-// objects.  KVC_PART is a bit mask: 1 = compress / select / norms (+ the library-wide state), 2 = slab cache, 4 = vote,
-// 8 = the LDG-form fused kernels (generic row widths) behind pick_fused_dt().
+// objects.  KVC_PART is a bit mask: 1 = compress / select / norms entry points (+ the library-wide state) and the
+// bf16 fused kernels, 2 = slab entry points and the bf16 in-place kernels, 4 = vote, 8 = slab append kernels,
+// 16 = f16/f32 fused kernels, 32 = f16/f32 in-place kernels.
 #ifndef KVC_PART
-#define KVC_PART 15
+#define KVC_PART 63
 #endif
 #define KVC_HAS_CORE (KVC_PART & 1)
 #define KVC_HAS_SLAB (KVC_PART & 2)
 #define KVC_HAS_VOTE (KVC_PART & 4)
-#define KVC_HAS_LDG (KVC_PART & 8)
+#define KVC_HAS_APPEND (KVC_PART & 8)
+#define KVC_HAS_FUSED_OTHER (KVC_PART & 16)
+#define KVC_HAS_SLAB_OTHER (KVC_PART & 32)
 
 #define KVC_STR2(x) #x
 #define KVC_STR(x) KVC_STR2(x)
@@ -42,175 +44,6 @@
 namespace kvc {
 
 constexpr int kSmemFixed = kHistBins * 4 + kMiscInts * 4;
-
-// ------------------------------------------------------------------ fused kernel
-// CPR > 0: compile-time chunks per row with LPR lanes per row (CPR % LPR == 0).
-// CPR == 0: generic path, runtime cpr / lpr (power of two) / cpl.
-template <int DT, int CPR, int LPR, int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB) kvc_fused_ldg_kernel(const __grid_constant__ BatchDev bd) {
-    using Tr = Traits<DT>;
-    using Key = typename Tr::Key;
-    constexpr int NW = NT / 32;
-    constexpr bool kGeneric = (CPR == 0);
-    constexpr int kShift0 = Tr::kKeyBits - kHistBits;
-
-    const LayerDev& L = bd.layers[blockIdx.y];
-    const int bh = blockIdx.x;
-    const int b = bh / bd.H, h = bh - b * bd.H;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    extern __shared__ __align__(128) unsigned char smem[];
-    uint32_t* hist = reinterpret_cast<uint32_t*>(smem);
-    int32_t* misc = reinterpret_cast<int32_t*>(smem + kHistBins * 4);
-    int32_t* sidx = reinterpret_cast<int32_t*>(smem + kSmemFixed);
-    Key* keys = reinterpret_cast<Key*>(smem + kSmemFixed + (size_t)bd.idx_cap * 4);
-
-    const int cpr = kGeneric ? bd.cpr : CPR;
-    const int lpr = kGeneric ? bd.lpr : LPR;
-    const int cpl = kGeneric ? bd.cpl : (CPR / (LPR > 0 ? LPR : 1));
-    const int rpw = 32 / lpr;  // rows per warp step
-
-    const int R = L.hi - L.lo;
-    const int ksel = L.ksel;
-    const int score = L.score;
-    const char* kbase = L.k_in + (int64_t)b * L.ksb + (int64_t)h * L.ksh;
-    const char* vbase = L.v_in + (int64_t)b * L.vsb + (int64_t)h * L.vsh;
-
-    if (ksel > 0 && score == KVC_SCORE_GIVEN_INDEX) {
-        const int32_t* src = L.idx_in + (int64_t)bh * ksel;
-        for (int i = tid; i < ksel; i += NT) sidx[i] = src[i];
-        __syncthreads();
-    } else if (ksel > 0) {
-        // ---------------------------------------------------------- K1: scan
-        for (int i = tid; i < kHistBins; i += NT) hist[i] = 0;
-        if (tid == 0) misc[kMiscMaxRaw] = 0;
-        __syncthreads();
-        const bool snap = (score == KVC_SCORE_SNAPKV_POOL);
-        const bool desc = (score == KVC_SCORE_L2_HIGH);
-        const int sub = lane % lpr, rw = lane / lpr;
-        const bool lane_ok = rw < rpw;
-        const char* rbase = kbase + (int64_t)L.lo * L.kss + (int64_t)sub * 16;
-        uint32_t local_max = 0;
-        if constexpr (!kGeneric) {
-            constexpr int CPL = CPR / LPR;
-            constexpr int U = (8 / CPL) > 0 ? (8 / CPL) : 1;
-            constexpr int RPW = 32 / LPR;
-            for (int base = 0; base < R; base += NW * RPW * U) {
-                int4 v[U][CPL];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int row = base + (u * NW + warp) * RPW + rw;
-                    const bool ok = lane_ok && row < R;
-                    const char* p = rbase + (int64_t)row * L.kss;
-#pragma unroll
-                    for (int c = 0; c < CPL; ++c)
-                        v[u][c] = ok ? ldg128_stream(p + c * (LPR * 16)) : make_int4(0, 0, 0, 0);
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int row = base + (u * NW + warp) * RPW + rw;
-                    float acc = 0.f;
-#pragma unroll
-                    for (int c = 0; c < CPL; ++c) acc = Tr::sumsq(v[u][c], acc);
-                    acc = group_sum<LPR>(acc);
-                    if (lane_ok && sub == 0 && row < R) {
-                        const uint32_t raw = Tr::to_raw(sqrtf(acc));
-                        if (snap) {
-                            keys[row] = (Key)raw;
-                            local_max = max(local_max, raw);
-                        } else {
-                            const Key key = ordered_key<Key>(raw, desc);
-                            keys[row] = key;
-                            atomicAdd(&hist[(uint32_t)key >> kShift0], 1u);
-                        }
-                    }
-                }
-            }
-        } else {
-            constexpr int U = 4;
-            for (int base = 0; base < R; base += NW * rpw * U) {
-                float acc[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int row = base + (u * NW + warp) * rpw + rw;
-                    const bool ok = lane_ok && row < R;
-                    const char* p = rbase + (int64_t)row * L.kss;
-                    acc[u] = 0.f;
-                    for (int c = 0; c < cpl; ++c) {
-                        const int4 x = ok ? ldg128_stream(p + (int64_t)c * lpr * 16) : make_int4(0, 0, 0, 0);
-                        acc[u] = Tr::sumsq(x, acc[u]);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int row = base + (u * NW + warp) * rpw + rw;
-                    const float tot = group_sum_pow2(acc[u], lpr);
-                    if (lane_ok && sub == 0 && row < R) {
-                        const uint32_t raw = Tr::to_raw(sqrtf(tot));
-                        if (snap) {
-                            keys[row] = (Key)raw;
-                            local_max = max(local_max, raw);
-                        } else {
-                            const Key key = ordered_key<Key>(raw, desc);
-                            keys[row] = key;
-                            atomicAdd(&hist[(uint32_t)key >> kShift0], 1u);
-                        }
-                    }
-                }
-            }
-        }
-        if (snap) {
-            // norms are >= 0, so their raw bits order like unsigned integers
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
-            if (lane == 0) atomicMax(reinterpret_cast<uint32_t*>(&misc[kMiscMaxRaw]), local_max);
-        }
-        __syncthreads();
-
-        if (snap) snapkv_transform<DT, NT>(keys, R, L.pool, hist, misc);
-        // ---------------------------------------------------------- K2: select
-        block_radix_select<Key, NT>(keys, R, ksel, hist, misc, sidx, L.lo);
-    }
-
-    // -------------------------------------------------------------- K3: gather
-    const int sink = L.sink;
-    const int C = sink + ksel + L.tail;
-    const int tail0 = L.S - L.tail - sink - ksel;  // src row = j + tail0 for tail rows
-    if (L.idx_out != nullptr) {
-        int32_t* io = L.idx_out + (int64_t)bh * C;
-        for (int j = tid; j < C; j += NT) io[j] = j < sink ? j : (j < sink + ksel ? sidx[j - sink] : j + tail0);
-    }
-    const int Qh = C * cpr;  // chunks per tensor
-    const int Q = 2 * Qh;
-    char* ko = L.k_out + (int64_t)bh * Qh * 16;
-    char* vo = L.v_out + (int64_t)bh * Qh * 16;
-    constexpr int UG = 8;
-    for (int q0 = 0; q0 < Q; q0 += NT * UG) {
-        int4 v[UG];
-#pragma unroll
-        for (int u = 0; u < UG; ++u) {
-            const int q = q0 + u * NT + tid;
-            if (q < Q) {
-                const bool isv = q >= Qh;
-                const int qq = isv ? q - Qh : q;
-                const int j = kGeneric ? qq / cpr : qq / (CPR > 0 ? CPR : 1);
-                const int c = qq - j * cpr;
-                const int row = j < sink ? j : (j < sink + ksel ? sidx[j - sink] : j + tail0);
-                const char* src = isv ? vbase + (int64_t)row * L.vss : kbase + (int64_t)row * L.kss;
-                v[u] = ldg128_stream(src + c * 16);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < UG; ++u) {
-            const int q = q0 + u * NT + tid;
-            if (q < Q) {
-                const bool isv = q >= Qh;
-                const int qq = isv ? q - Qh : q;
-                stg128_stream((isv ? vo : ko) + (int64_t)qq * 16, v[u]);
-            }
-        }
-    }
-}
 
 // ------------------------------------------------------------------ standalone K1
 // One warp step = 32/lpr rows; grid-stride over row groups of one [B,H,R] problem.
@@ -287,45 +120,37 @@ static int elem_bytes(int dtype) { return dtype == KVC_DTYPE_F32 ? 4 : 2; }
 static int key_bytes(int dtype) { return dtype == KVC_DTYPE_F32 ? 4 : 2; }
 
 using FusedFn = void (*)(const BatchDev);
-struct FusedVariant {
-    FusedFn fn;
-    int threads;
-};
-constexpr int kNT = 512;
-FusedVariant pick_fused_dt(int dtype, int cpr);  // LDG-form kernel for a row width (cpr = 16-byte chunks per row)
+constexpr int kNT = 512;  // threads of the stand-alone select kernel
 
-#if KVC_HAS_LDG
-template <int DT>
-static FusedVariant pick_fused(int cpr) {
-    switch (cpr) {
-        case 8: return {kvc_fused_ldg_kernel<DT, 8, 8, kNT, 2>, kNT};
-        case 10: return {kvc_fused_ldg_kernel<DT, 10, 10, kNT, 2>, kNT};
-        case 16: return {kvc_fused_ldg_kernel<DT, 16, 8, kNT, 2>, kNT};
-        case 20: return {kvc_fused_ldg_kernel<DT, 20, 10, kNT, 2>, kNT};
-        case 32: return {kvc_fused_ldg_kernel<DT, 32, 16, kNT, 2>, kNT};
-        default: return {kvc_fused_ldg_kernel<DT, 0, 0, kNT, 2>, kNT};
-    }
-}
-
-FusedVariant pick_fused_dt(int dtype, int cpr) {
-    switch (dtype) {
-        case KVC_DTYPE_F32: return pick_fused<KVC_DTYPE_F32>(cpr);
-        case KVC_DTYPE_F16: return pick_fused<KVC_DTYPE_F16>(cpr);
-        default: return pick_fused<KVC_DTYPE_BF16>(cpr);
-    }
-}
-#endif  // KVC_HAS_LDG
-
-static int set_device(int device) {
-    int cur = -1;
-    cudaError_t e = cudaGetDevice(&cur);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaGetDevice");
-    if (cur != device) {
+// Entry points run on shape->device and leave the calling thread's current device as they found it: torch keeps its
+// own idea of the current device, and a library that moved it would send later allocations and stream queries of a
+// multi-GPU process (device_map-style placement) to the wrong GPU.
+struct DeviceGuard {
+    int prev = -1;
+    int status = KVC_OK;
+    explicit DeviceGuard(int device) {
+        cudaError_t e = cudaGetDevice(&prev);
+        if (e != cudaSuccess) {
+            prev = -1;
+            status = cuda_fail(e, "cudaGetDevice");
+            return;
+        }
+        if (prev == device) {
+            prev = -1;  // nothing to restore
+            return;
+        }
         e = cudaSetDevice(device);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+        if (e != cudaSuccess) {
+            prev = -1;
+            status = cuda_fail(e, "cudaSetDevice");
+        }
     }
-    return KVC_OK;
-}
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+    DeviceGuard(const DeviceGuard&) = delete;
+    DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
 
 static int ensure_smem(const void* fn, size_t bytes) {
     // The attribute is sticky per function and context; raising it again is cheap.
@@ -360,23 +185,20 @@ struct TmaPlan {
     size_t smem = 0;
 };
 
-static int env_int(const char* name, int dflt);
-// KVC_VOTE_DEBUG switches stages of the vote kernels off for stage-isolation timing (1 = no math, 2 = no math, no
-// MMA, 3 = no tail box, 4 = one K step): the votes it produces are NOT valid, so say so, once, on stderr.
-static int vote_debug_mode() {
-    const int d = env_int("KVC_VOTE_DEBUG", 0);
-    static bool warned = false;
-    if (d != 0 && !warned) {
-        warned = true;
-        fprintf(stderr, "libkvc_sm100a: KVC_VOTE_DEBUG=%d is a profiling mode, kvc_snapkv_vote results are not valid\n", d);
-    }
-    return d;
-}
-
+// Launch-shape overrides and stage isolation exist only in a lab build (-DKVC_LAB: scripts/build_lab.sh); the product
+// library reads no environment variable, so nothing outside the call's arguments can change what it computes.
+#ifdef KVC_LAB
 static int env_int(const char* name, int dflt) {
     const char* v = getenv(name);
     return (v && *v) ? atoi(v) : dflt;
 }
+// KVC_VOTE_DEBUG switches stages of the vote kernel off for stage-isolation timing (1 = no math, 2 = no math, no
+// MMA, 3 = no tail box, 4 = one K step): the votes it produces are NOT valid.
+static int vote_debug_mode() { return env_int("KVC_VOTE_DEBUG", 0); }
+#else
+static inline int env_int(const char*, int dflt) { return dflt; }
+static inline int vote_debug_mode() { return 0; }
+#endif
 
 // Choose threads per CTA, resident CTAs per SM and staging warps so that (a) the on-chip key
 // buffer fits, (b) as close to 128 KB of rows as possible are in flight per SM, (c) as many CTAs as possible are
@@ -447,7 +269,7 @@ static bool onchip_plan_ok(const TmaPlan& tp, int cpr, bool light_traffic) {
     return (long)tp.ctas * tp.nsw * 32 * cpr * 16 >= 48 * 1024;
 }
 
-#if KVC_HAS_CORE
+#if KVC_HAS_CORE || KVC_HAS_FUSED_OTHER
 template <int DT, int NT, int MINB>
 static FusedFn pick_tma_cpr(int cpr) {
     switch (cpr) {
@@ -457,25 +279,31 @@ static FusedFn pick_tma_cpr(int cpr) {
         case 16: return kvc_fused_tma_kernel<DT, 16, NT, MINB>;
         case 20: return kvc_fused_tma_kernel<DT, 20, NT, MINB>;
         case 32: return kvc_fused_tma_kernel<DT, 32, NT, MINB>;
-        default: return nullptr;
+        default: return kvc_fused_tma_kernel<DT, 0, NT, MINB>;  // any other row width: run-time loops
     }
 }
 template <int DT>
 static FusedFn pick_tma_nt(int cpr, int nt) {
     return nt == 512 ? pick_tma_cpr<DT, 512, 1>(cpr) : pick_tma_cpr<DT, 256, 3>(cpr);
 }
+#endif
+FusedFn pick_tma_bf16(int cpr, int nt);
+FusedFn pick_tma_other(int dtype, int cpr, int nt);
+#if KVC_HAS_CORE
+FusedFn pick_tma_bf16(int cpr, int nt) { return pick_tma_nt<KVC_DTYPE_BF16>(cpr, nt); }
 static FusedFn pick_tma(int dtype, int cpr, int nt) {
-    switch (dtype) {
-        case KVC_DTYPE_F32: return pick_tma_nt<KVC_DTYPE_F32>(cpr, nt);
-        case KVC_DTYPE_F16: return pick_tma_nt<KVC_DTYPE_F16>(cpr, nt);
-        default: return pick_tma_nt<KVC_DTYPE_BF16>(cpr, nt);
-    }
+    return dtype == KVC_DTYPE_BF16 ? pick_tma_bf16(cpr, nt) : pick_tma_other(dtype, cpr, nt);
 }
-#endif  // KVC_HAS_CORE
+#endif
+#if KVC_HAS_FUSED_OTHER
+FusedFn pick_tma_other(int dtype, int cpr, int nt) {
+    return dtype == KVC_DTYPE_F32 ? pick_tma_nt<KVC_DTYPE_F32>(cpr, nt) : pick_tma_nt<KVC_DTYPE_F16>(cpr, nt);
+}
+#endif
 
-static bool tma_supported_cpr(int cpr) {  // 128/160/192/256/320/512-byte rows
-    return cpr == 8 || cpr == 10 || cpr == 12 || cpr == 16 || cpr == 20 || cpr == 32;
-}
+// Rows of 16 B .. 2 KB: 128/160/192/256/320/512-byte rows have kernels with compile-time widths, the rest run the
+// generic-width instantiation of the same kernels.
+static bool row_width_ok(int cpr) { return cpr >= 1 && cpr <= 128; }
 
 static int ensure_tma_attrs(const void* fn, int device) {
     // Function attributes are sticky per (function, device): set them once, not on every decode step.
@@ -497,10 +325,16 @@ static int ensure_tma_attrs(const void* fn, int device) {
 
 
 // ------------------------------------------------------------------ slab kernels: variant tables
-#if KVC_HAS_SLAB
 using SlabFn = void (*)(const SlabBatchDev);
 using AppendFn = void (*)(const AppendBatchDev);
+using AppendOneFn = void (*)(const AppendOneDev);
+SlabFn pick_slab_bf16(int cpr, int nt);
+SlabFn pick_slab_other(int dtype, int cpr, int nt);
+AppendFn pick_append(int dtype, int cpr);          // thread-per-row form, all layers
+AppendOneFn pick_append_one(int dtype, int cpr);   // thread-per-row form, one layer (small parameter block)
+AppendFn pick_append_tma(int dtype, int cpr);      // bulk-copy form (prefill-sized appends)
 
+#if KVC_HAS_SLAB || KVC_HAS_SLAB_OTHER
 template <int DT, int NT, int MINB>
 static SlabFn pick_slab_cpr(int cpr) {
     switch (cpr) {
@@ -510,50 +344,37 @@ static SlabFn pick_slab_cpr(int cpr) {
         case 16: return kvc_slab_compress_kernel<DT, 16, NT, MINB>;
         case 20: return kvc_slab_compress_kernel<DT, 20, NT, MINB>;
         case 32: return kvc_slab_compress_kernel<DT, 32, NT, MINB>;
-        default: return nullptr;
+        default: return kvc_slab_compress_kernel<DT, 0, NT, MINB>;
     }
 }
 template <int DT>
 static SlabFn pick_slab_nt(int cpr, int nt) {
     return nt == 512 ? pick_slab_cpr<DT, 512, 1>(cpr) : pick_slab_cpr<DT, 256, 3>(cpr);
 }
+#endif
+#if KVC_HAS_SLAB
+SlabFn pick_slab_bf16(int cpr, int nt) { return pick_slab_nt<KVC_DTYPE_BF16>(cpr, nt); }
 static SlabFn pick_slab(int dtype, int cpr, int nt) {
-    switch (dtype) {
-        case KVC_DTYPE_F32: return pick_slab_nt<KVC_DTYPE_F32>(cpr, nt);
-        case KVC_DTYPE_F16: return pick_slab_nt<KVC_DTYPE_F16>(cpr, nt);
-        default: return pick_slab_nt<KVC_DTYPE_BF16>(cpr, nt);
-    }
+    return dtype == KVC_DTYPE_BF16 ? pick_slab_bf16(cpr, nt) : pick_slab_other(dtype, cpr, nt);
 }
-template <int DT>
-static AppendFn pick_append_cpr(int cpr) {
+#endif
+#if KVC_HAS_SLAB_OTHER
+SlabFn pick_slab_other(int dtype, int cpr, int nt) {
+    return dtype == KVC_DTYPE_F32 ? pick_slab_nt<KVC_DTYPE_F32>(cpr, nt) : pick_slab_nt<KVC_DTYPE_F16>(cpr, nt);
+}
+#endif
+
+#if KVC_HAS_APPEND
+template <int DT, typename Params>
+static void (*pick_append_row_cpr(int cpr))(const Params) {
     switch (cpr) {
-        case 8: return kvc_slab_append_kernel<DT, 8, AppendBatchDev>;
-        case 10: return kvc_slab_append_kernel<DT, 10, AppendBatchDev>;
-        case 12: return kvc_slab_append_kernel<DT, 12, AppendBatchDev>;
-        case 16: return kvc_slab_append_kernel<DT, 16, AppendBatchDev>;
-        case 20: return kvc_slab_append_kernel<DT, 20, AppendBatchDev>;
-        case 32: return kvc_slab_append_kernel<DT, 32, AppendBatchDev>;
-        default: return nullptr;
-    }
-}
-using AppendOneFn = void (*)(const AppendOneDev);
-template <int DT>
-static AppendOneFn pick_append_one_cpr(int cpr) {
-    switch (cpr) {
-        case 8: return kvc_slab_append_kernel<DT, 8, AppendOneDev>;
-        case 10: return kvc_slab_append_kernel<DT, 10, AppendOneDev>;
-        case 12: return kvc_slab_append_kernel<DT, 12, AppendOneDev>;
-        case 16: return kvc_slab_append_kernel<DT, 16, AppendOneDev>;
-        case 20: return kvc_slab_append_kernel<DT, 20, AppendOneDev>;
-        case 32: return kvc_slab_append_kernel<DT, 32, AppendOneDev>;
-        default: return nullptr;
-    }
-}
-static AppendOneFn pick_append_one(int dtype, int cpr) {
-    switch (dtype) {
-        case KVC_DTYPE_F32: return pick_append_one_cpr<KVC_DTYPE_F32>(cpr);
-        case KVC_DTYPE_F16: return pick_append_one_cpr<KVC_DTYPE_F16>(cpr);
-        default: return pick_append_one_cpr<KVC_DTYPE_BF16>(cpr);
+        case 8: return kvc_slab_append_kernel<DT, 8, Params>;
+        case 10: return kvc_slab_append_kernel<DT, 10, Params>;
+        case 12: return kvc_slab_append_kernel<DT, 12, Params>;
+        case 16: return kvc_slab_append_kernel<DT, 16, Params>;
+        case 20: return kvc_slab_append_kernel<DT, 20, Params>;
+        case 32: return kvc_slab_append_kernel<DT, 32, Params>;
+        default: return kvc_slab_append_kernel<DT, 0, Params>;
     }
 }
 template <int DT>
@@ -565,25 +386,31 @@ static AppendFn pick_append_tma_cpr(int cpr) {
         case 16: return kvc_slab_append_tma_kernel<DT, 16>;
         case 20: return kvc_slab_append_tma_kernel<DT, 20>;
         case 32: return kvc_slab_append_tma_kernel<DT, 32>;
-        default: return nullptr;
+        default: return kvc_slab_append_tma_kernel<DT, 0>;
     }
 }
-static AppendFn pick_append_tma(int dtype, int cpr) {
+AppendOneFn pick_append_one(int dtype, int cpr) {
+    switch (dtype) {
+        case KVC_DTYPE_F32: return pick_append_row_cpr<KVC_DTYPE_F32, AppendOneDev>(cpr);
+        case KVC_DTYPE_F16: return pick_append_row_cpr<KVC_DTYPE_F16, AppendOneDev>(cpr);
+        default: return pick_append_row_cpr<KVC_DTYPE_BF16, AppendOneDev>(cpr);
+    }
+}
+AppendFn pick_append(int dtype, int cpr) {
+    switch (dtype) {
+        case KVC_DTYPE_F32: return pick_append_row_cpr<KVC_DTYPE_F32, AppendBatchDev>(cpr);
+        case KVC_DTYPE_F16: return pick_append_row_cpr<KVC_DTYPE_F16, AppendBatchDev>(cpr);
+        default: return pick_append_row_cpr<KVC_DTYPE_BF16, AppendBatchDev>(cpr);
+    }
+}
+AppendFn pick_append_tma(int dtype, int cpr) {
     switch (dtype) {
         case KVC_DTYPE_F32: return pick_append_tma_cpr<KVC_DTYPE_F32>(cpr);
         case KVC_DTYPE_F16: return pick_append_tma_cpr<KVC_DTYPE_F16>(cpr);
         default: return pick_append_tma_cpr<KVC_DTYPE_BF16>(cpr);
     }
 }
-static AppendFn pick_append(int dtype, int cpr) {
-    switch (dtype) {
-        case KVC_DTYPE_F32: return pick_append_cpr<KVC_DTYPE_F32>(cpr);
-        case KVC_DTYPE_F16: return pick_append_cpr<KVC_DTYPE_F16>(cpr);
-        default: return pick_append_cpr<KVC_DTYPE_BF16>(cpr);
-    }
-}
-
-#endif  // KVC_HAS_SLAB
+#endif  // KVC_HAS_APPEND
 
 static int check_shape(const kvc_shape* shape, int* cpr_out) {
     if (!shape) return KVC_ERR_INVALID_ARG;
@@ -658,7 +485,7 @@ static void chunk_stats(const kvc_layer_plan* plans, int nl, int* n_active, int*
 
 int64_t kvc_workspace_bytes(const kvc_shape* shape, int32_t n_layers, const kvc_layer_plan* plans) {
     int cpr = 0;
-    if (check_shape(shape, &cpr) != KVC_OK || n_layers <= 0 || !plans || !tma_supported_cpr(cpr)) return 0;
+    if (check_shape(shape, &cpr) != KVC_OK || n_layers <= 0 || !plans || !row_width_ok(cpr)) return 0;
     int64_t need = 0;
     for (int l0 = 0; l0 < n_layers; l0 += KVC_MAX_LAYERS_PER_LAUNCH) {
         const int nl = (n_layers - l0) < KVC_MAX_LAYERS_PER_LAUNCH ? (n_layers - l0) : KVC_MAX_LAYERS_PER_LAUNCH;
@@ -679,13 +506,12 @@ int kvc_compress_layers_ws(const kvc_shape* shape, int32_t n_layers, const kvc_l
                            const kvc_layer_io* io, void* workspace, int64_t workspace_bytes, void* stream) {
     if (!shape || n_layers < 0 || (n_layers > 0 && (!plans || !io))) return KVC_ERR_INVALID_ARG;
     if (n_layers == 0) return KVC_OK;
-    const int B = shape->batch, H = shape->heads, D = shape->head_dim, dt = shape->dtype;
-    if (B <= 0 || H <= 0 || D <= 0) return KVC_ERR_INVALID_ARG;
-    if (dt != KVC_DTYPE_F32 && dt != KVC_DTYPE_F16 && dt != KVC_DTYPE_BF16) return KVC_ERR_UNSUPPORTED;
+    int cpr = 0;
+    int st = check_shape(shape, &cpr);
+    if (st != KVC_OK) return st;
+    if (!row_width_ok(cpr)) return KVC_ERR_UNSUPPORTED;
+    const int B = shape->batch, H = shape->heads, dt = shape->dtype;
     const int e = elem_bytes(dt);
-    if (((int64_t)D * e) % 16 != 0) return KVC_ERR_UNSUPPORTED;
-    if ((int64_t)B * H > 0x7fffffffLL) return KVC_ERR_INVALID_ARG;
-    const int cpr = D * e / 16;
 
     // validate every layer before anything is enqueued
     for (int l = 0; l < n_layers; ++l) {
@@ -697,12 +523,11 @@ int kvc_compress_layers_ws(const kvc_shape* shape, int32_t n_layers, const kvc_l
         if (p.k_sel > 0) {
             if (p.sel_lo < 0 || p.sel_hi > p.seq_len || p.sel_lo > p.sel_hi) return KVC_ERR_INVALID_ARG;
             if (p.k_sel > p.sel_hi - p.sel_lo) return KVC_ERR_INVALID_ARG;
-            if (p.score == KVC_SCORE_NONE) return KVC_ERR_INVALID_ARG;
-            if (p.score < KVC_SCORE_NONE || p.score > KVC_SCORE_GIVEN_SCORE) return KVC_ERR_INVALID_ARG;
+            if (p.score <= KVC_SCORE_NONE || p.score > KVC_SCORE_GIVEN_SCORE) return KVC_ERR_INVALID_ARG;
             if (p.score == KVC_SCORE_GIVEN_INDEX && !x.idx_in) return KVC_ERR_INVALID_ARG;
-            if (p.score == KVC_SCORE_GIVEN_SCORE && (!x.score_in || !tma_supported_cpr(cpr))) return KVC_ERR_INVALID_ARG;
-            if (p.score == KVC_SCORE_GIVEN_SCORE && p.pool_kernel > 2 * kMaxPoolHalo) return KVC_ERR_UNSUPPORTED;
-            if (p.score == KVC_SCORE_SNAPKV_POOL && p.pool_kernel > 2 * kMaxPoolHalo) return KVC_ERR_UNSUPPORTED;
+            if (p.score == KVC_SCORE_GIVEN_SCORE && !x.score_in) return KVC_ERR_INVALID_ARG;
+            if ((p.score == KVC_SCORE_GIVEN_SCORE || p.score == KVC_SCORE_SNAPKV_POOL) && p.pool_kernel > 2 * kMaxPoolHalo)
+                return KVC_ERR_UNSUPPORTED;
         }
         if (C == 0) continue;
         if (!x.k_in || !x.v_in || !x.k_out || !x.v_out) return KVC_ERR_INVALID_ARG;
@@ -712,10 +537,9 @@ int kvc_compress_layers_ws(const kvc_shape* shape, int32_t n_layers, const kvc_l
         const int64_t s = (x.k_stride_b | x.k_stride_h | x.k_stride_s | x.v_stride_b | x.v_stride_h | x.v_stride_s);
         if ((s * e) & 15) return KVC_ERR_UNSUPPORTED;
     }
-    int st = set_device(shape->device);
-    if (st != KVC_OK) return st;
+    DeviceGuard guard(shape->device);
+    if (guard.status != KVC_OK) return guard.status;
 
-    const FusedVariant var = pick_fused_dt(dt, cpr);
     for (int l0 = 0; l0 < n_layers; l0 += KVC_MAX_LAYERS_PER_LAUNCH) {
         const int nl = (n_layers - l0) < KVC_MAX_LAYERS_PER_LAUNCH ? (n_layers - l0) : KVC_MAX_LAYERS_PER_LAUNCH;
         BatchDev bd;
@@ -723,10 +547,8 @@ int kvc_compress_layers_ws(const kvc_shape* shape, int32_t n_layers, const kvc_l
         bd.B = B;
         bd.H = H;
         bd.cpr = cpr;
-        bd.lpr = pow2_lanes(cpr);
-        bd.cpl = cpr / bd.lpr;
         int n_active = 0, max_region = 0, max_ksel = 0;
-        bool any_select = false;
+        bool any_select = false, any_scan = false;
         for (int l = 0; l < nl; ++l) {
             const kvc_layer_plan& p = plans[l0 + l];
             const kvc_layer_io& x = io[l0 + l];
@@ -752,8 +574,16 @@ int kvc_compress_layers_ws(const kvc_shape* shape, int32_t n_layers, const kvc_l
             d.tail = p.tail;
             d.score = p.k_sel > 0 ? p.score : KVC_SCORE_NONE;
             d.pool = p.pool_kernel;
+            const bool ranked = p.k_sel > 0 && (p.score == KVC_SCORE_L2_LOW || p.score == KVC_SCORE_L2_HIGH ||
+                                                p.score == KVC_SCORE_SNAPKV_POOL);
+            if (ranked && x.norms_in) {  // the caller holds the key norms: the scan is skipped
+                d.n_in = (const char*)x.norms_in;
+                d.nsb = x.n_stride_b * key_bytes(dt);
+                d.nsh = x.n_stride_h * key_bytes(dt);
+            }
             if (p.k_sel > 0) {
                 any_select = true;
+                any_scan |= ranked && !x.norms_in;
                 if (p.k_sel > max_ksel) max_ksel = p.k_sel;
                 if (p.score != KVC_SCORE_GIVEN_INDEX && p.sel_hi - p.sel_lo > max_region)
                     max_region = p.sel_hi - p.sel_lo;
@@ -761,49 +591,33 @@ int kvc_compress_layers_ws(const kvc_shape* shape, int32_t n_layers, const kvc_l
         }
         if (n_active == 0) continue;
         bd.idx_cap = (max_ksel + 3) & ~3;
-        dim3 grid((unsigned)((int64_t)B * H), (unsigned)n_active, 1);
-        TmaPlan tp;
-        bool given_score = false;
-        for (int l = 0; l < nl; ++l) given_score |= plans[l0 + l].k_sel > 0 && plans[l0 + l].score == KVC_SCORE_GIVEN_SCORE;
-        if (tma_supported_cpr(cpr) && (given_score || !env_int("KVC_FORCE_LDG", 0))) {
-            // caller-supplied scores: no K scan, the launch moves only the kept rows -> residency over slot depth
-            tp = plan_tma(dt, cpr, max_region, bd.idx_cap, any_select, /*light_traffic=*/given_score);
-            if (any_select && workspace != nullptr && !onchip_plan_ok(tp, cpr, false)) {
-                // keys and kept indices go to the workspace; shared memory keeps the histogram and the slots
-                const WsLayout w = ws_layout(dt, max_region, bd.idx_cap);
-                if (w.unit * B * H * n_active > workspace_bytes) return KVC_ERR_INVALID_ARG;
-                bd.ws = (char*)workspace;
-                bd.ws_unit = w.unit;
-                bd.ws_keys = w.keys;
-                tp = plan_tma(dt, cpr, 0, 0, true);
-            }
+        // no K scan in this launch (stored norms, caller-supplied scores or rows, pure slices with a select next to
+        // them): only kept rows move -> residency over slot depth
+        const bool light = any_select && !any_scan;
+        TmaPlan tp = plan_tma(dt, cpr, max_region, bd.idx_cap, any_select, light);
+        if (any_select && workspace != nullptr && !onchip_plan_ok(tp, cpr, light)) {
+            // keys and kept indices go to the workspace; shared memory keeps the histogram and the slots
+            const WsLayout w = ws_layout(dt, max_region, bd.idx_cap);
+            if (w.unit * B * H * n_active > workspace_bytes) return KVC_ERR_INVALID_ARG;
+            bd.ws = (char*)workspace;
+            bd.ws_unit = w.unit;
+            bd.ws_keys = w.keys;
+            tp = plan_tma(dt, cpr, 0, 0, true, light);
         }
-        if (given_score && !tp.ok) return KVC_ERR_TOO_LARGE;
-        if (tp.ok) {
-            // bulk-copy form: rows are staged through shared memory by the TMA unit
-            FusedFn fn = pick_tma(dt, cpr, tp.nt);
-            bd.nsw = tp.nsw;
-            bd.off_hist = tp.off_hist;
-            bd.off_idx = tp.off_idx;
-            bd.off_keys = tp.off_keys;
-            bd.off_stage = tp.off_stage;
-            bd.upc = tp.upc;
-            grid.x = (unsigned)(((int64_t)B * H + tp.upc - 1) / tp.upc);
-            st = ensure_tma_attrs((const void*)fn, shape->device);
-            if (st != KVC_OK) return st;
-            fn<<<grid, tp.nt, tp.smem, (cudaStream_t)stream>>>(bd);
-            cudaError_t err = cudaGetLastError();
-            if (err != cudaSuccess) return cuda_fail(err, "kvc_fused_tma_kernel launch");
-        } else {
-            // LDG form: head dims without a compiled row width, or key buffers that leave no room to stage
-            size_t smem = any_select ? fused_smem_bytes(dt, max_region, bd.idx_cap) : 0;
-            if (smem > (size_t)kMaxSmemOptin) return KVC_ERR_TOO_LARGE;
-            st = ensure_smem((const void*)var.fn, smem);
-            if (st != KVC_OK) return st;
-            var.fn<<<grid, var.threads, smem, (cudaStream_t)stream>>>(bd);
-            cudaError_t err = cudaGetLastError();
-            if (err != cudaSuccess) return cuda_fail(err, "kvc_fused_ldg_kernel launch");
-        }
+        if (!tp.ok) return KVC_ERR_TOO_LARGE;
+        FusedFn fn = pick_tma(dt, cpr, tp.nt);
+        bd.nsw = tp.nsw;
+        bd.off_hist = tp.off_hist;
+        bd.off_idx = tp.off_idx;
+        bd.off_keys = tp.off_keys;
+        bd.off_stage = tp.off_stage;
+        bd.upc = tp.upc;
+        dim3 grid((unsigned)(((int64_t)B * H + tp.upc - 1) / tp.upc), (unsigned)n_active, 1);
+        st = ensure_tma_attrs((const void*)fn, shape->device);
+        if (st != KVC_OK) return st;
+        fn<<<grid, tp.nt, tp.smem, (cudaStream_t)stream>>>(bd);
+        cudaError_t err = cudaGetLastError();
+        if (err != cudaSuccess) return cuda_fail(err, "kvc_fused_tma_kernel launch");
         g_launches.fetch_add(1);
     }
     return KVC_OK;
@@ -821,8 +635,8 @@ int kvc_key_norms(const kvc_shape* shape, const void* k_in, int64_t stride_b, in
     const int R = row_hi - row_lo;
     const int64_t total = (int64_t)B * H * R;
     if (total == 0) return KVC_OK;
-    int st = set_device(shape->device);
-    if (st != KVC_OK) return st;
+    DeviceGuard guard(shape->device);
+    if (guard.status != KVC_OK) return guard.status;
     const int cpr = D * e / 16;
     const int lpr = pow2_lanes(cpr), cpl = cpr / lpr;
     const int rpw = 32 / lpr;
@@ -860,8 +674,9 @@ int kvc_select(int32_t dtype, int32_t device, const void* scores, int64_t n_rows
     if (n_rows > 0x7fffffffLL) return KVC_ERR_INVALID_ARG;
     const size_t smem = fused_smem_bytes(dtype, n, (k + 3) & ~3);
     if (smem > (size_t)kMaxSmemOptin) return KVC_ERR_TOO_LARGE;
-    int st = set_device(device);
-    if (st != KVC_OK) return st;
+    DeviceGuard guard(device);
+    if (guard.status != KVC_OK) return guard.status;
+    int st = KVC_OK;
     cudaStream_t s = (cudaStream_t)stream;
     const void* fn = nullptr;
     switch (dtype) {
@@ -901,7 +716,7 @@ int kvc_slab_append(const kvc_shape* shape, int32_t n_layers, const kvc_slab_lay
     if (st != KVC_OK) return st;
     if (n_layers < 0 || (n_layers > 0 && (!slabs || !rows))) return KVC_ERR_INVALID_ARG;
     if (n_layers == 0) return KVC_OK;
-    if (!tma_supported_cpr(cpr)) return KVC_ERR_UNSUPPORTED;
+    if (!row_width_ok(cpr)) return KVC_ERR_UNSUPPORTED;
     const int B = shape->batch, H = shape->heads, dt = shape->dtype;
     const int e = elem_bytes(dt);
     for (int l = 0; l < n_layers; ++l) {
@@ -917,8 +732,8 @@ int kvc_slab_append(const kvc_shape* shape, int32_t n_layers, const kvc_slab_lay
         if ((sb * e) & 15) return KVC_ERR_UNSUPPORTED;
         if ((int64_t)B * H * r.n_new > 0x7fffffffLL) return KVC_ERR_TOO_LARGE;
     }
-    st = set_device(shape->device);
-    if (st != KVC_OK) return st;
+    DeviceGuard guard(shape->device);
+    if (guard.status != KVC_OK) return guard.status;
     auto fill = [&](AppendLayerDev& d, const kvc_slab_layer& sl, const kvc_slab_new_rows& r) {
         d.k_new = (const char*)r.k_new;
         d.v_new = (const char*)r.v_new;
@@ -946,7 +761,7 @@ int kvc_slab_append(const kvc_shape* shape, int32_t n_layers, const kvc_slab_lay
         one.B = B;
         one.H = H;
         one.max_new = rows[0].n_new;
-        one.pad = 0;
+        one.cpr = cpr;
         fill(one.layers[0], slabs[0], rows[0]);
         const int64_t threads = (int64_t)B * H * rows[0].n_new;
         pick_append_one(dt, cpr)<<<(unsigned)((threads + 127) / 128), 128, 0, (cudaStream_t)stream>>>(one);
@@ -972,6 +787,7 @@ int kvc_slab_append(const kvc_shape* shape, int32_t n_layers, const kvc_slab_lay
         }
         if (n_active == 0) continue;
         bd.max_new = max_new;
+        bd.cpr = cpr;
         cudaError_t err;
         if (max_new >= 32) {
             // prefill / chunked prefill: rows move 32 at a time through shared memory with bulk copies
@@ -1006,7 +822,7 @@ int kvc_slab_compress(const kvc_shape* shape, int32_t n_layers, const kvc_layer_
     if (st != KVC_OK) return st;
     if (n_layers < 0 || (n_layers > 0 && (!slabs || !plans))) return KVC_ERR_INVALID_ARG;
     if (n_layers == 0) return KVC_OK;
-    if (!tma_supported_cpr(cpr)) return KVC_ERR_UNSUPPORTED;
+    if (!row_width_ok(cpr)) return KVC_ERR_UNSUPPORTED;
     const int B = shape->batch, H = shape->heads, dt = shape->dtype;
     const int e = elem_bytes(dt);
     for (int l = 0; l < n_layers; ++l) {
@@ -1027,14 +843,15 @@ int kvc_slab_compress(const kvc_shape* shape, int32_t n_layers, const kvc_layer_
         if (((uintptr_t)sl.k | (uintptr_t)sl.v) & 15) return KVC_ERR_UNSUPPORTED;
         if (((sl.k_stride_b | sl.k_stride_h | sl.v_stride_b | sl.v_stride_h) * e) & 15) return KVC_ERR_UNSUPPORTED;
     }
-    st = set_device(shape->device);
-    if (st != KVC_OK) return st;
+    DeviceGuard guard(shape->device);
+    if (guard.status != KVC_OK) return guard.status;
     for (int l0 = 0; l0 < n_layers; l0 += KVC_MAX_LAYERS_PER_LAUNCH) {
         const int nl = (n_layers - l0) < KVC_MAX_LAYERS_PER_LAUNCH ? (n_layers - l0) : KVC_MAX_LAYERS_PER_LAUNCH;
         SlabBatchDev bd;
         memset(&bd, 0, sizeof(bd));
         bd.B = B;
         bd.H = H;
+        bd.cpr = cpr;
         int n_active = 0, max_region = 0, max_ksel = 0;
         bool any_select = false;
         for (int l = 0; l < nl; ++l) {
@@ -1115,10 +932,17 @@ static EncodeTiledFn tensor_map_encoder() {
     return fn;
 }
 
-// TMA-fed vote kernel (kvc_vote.cuh): returns KVC_ERR_UNSUPPORTED when a tensor map cannot describe the keys,
-// in which case the caller falls back to the cp.async-fed kernel.
+// Shared-memory bytes the fused tail needs inside the (dead) key-tile ring: histogram, kept indices, radix keys
+// of the prefix, at least one staging slot of 32 rows.
+static size_t vote_tail_bytes(int cpr, int prefix_rows, int idx_cap) {
+    const size_t keys = ((size_t)prefix_rows * 2 + 15) & ~(size_t)15;
+    return (((size_t)kHistBins * 4 + (size_t)idx_cap * 4 + keys + 127) & ~(size_t)127) + (size_t)32 * cpr * 16;
+}
+
+// TMA-fed vote kernel (kvc_vote.cuh): returns KVC_ERR_UNSUPPORTED when a tensor map cannot describe the keys.
+// plans / io non-null: the fused form — pool, select and gather behind the vote in the same launch.
 static int launch_vote_tma(const kvc_shape* shape, int32_t n_layers, const kvc_vote_layer* layers, int32_t group,
-                           int32_t window, int cpr, void* stream) {
+                           int32_t window, int cpr, const kvc_layer_plan* plans, const kvc_layer_io* io, void* stream) {
     EncodeTiledFn encode = tensor_map_encoder();
     if (!encode) return KVC_ERR_UNSUPPORTED;
     const int B = shape->batch, H = shape->heads, D = shape->head_dim, dt = shape->dtype;
@@ -1168,10 +992,30 @@ static int launch_vote_tma(const kvc_shape* shape, int32_t n_layers, const kvc_v
             }
             d.q = (const char*)v.q_obs;
             d.votes = (char*)v.votes_out;
+            d.lse = v.lse;
             d.qsb = v.q_stride_b * 2;
             d.qsh = v.q_stride_h * 2;
             d.qss = v.q_stride_s * 2;
             d.S = v.seq_len;
+            if (plans != nullptr) {
+                const kvc_layer_plan& p = plans[l0 + l];
+                const kvc_layer_io& x = io[l0 + l];
+                d.k_in = (const char*)x.k_in;
+                d.v_in = (const char*)x.v_in;
+                d.k_out = (char*)x.k_out;
+                d.v_out = (char*)x.v_out;
+                d.idx_out = x.idx_out;
+                d.ksb = x.k_stride_b * 2;
+                d.ksh = x.k_stride_h * 2;
+                d.kss = x.k_stride_s * 2;
+                d.vsb = x.v_stride_b * 2;
+                d.vsh = x.v_stride_h * 2;
+                d.vss = x.v_stride_s * 2;
+                d.ksel = p.k_sel;
+                d.tail = p.tail;
+                d.pool = p.pool_kernel;
+                d.idx_cap = (p.k_sel + 3) & ~3;
+            }
         }
         dim3 grid((unsigned)((int64_t)B * H), (unsigned)nl, 1);
         fn<<<grid, 576, smem, (cudaStream_t)stream>>>(bd);
@@ -1182,142 +1026,14 @@ static int launch_vote_tma(const kvc_shape* shape, int32_t n_layers, const kvc_v
     return KVC_OK;
 }
 
-// ---- persistent split-sequence vote (kvc_vote_split.cuh) -----------------------------------------------------
-// Slices per unit: a CTA holds ~2-3 slices between their passes, 148 CTAs at once, and all of it has to stay in L2.
-static int vote_slices(int cpr, int seq_len) {
-    const int n1 = (seq_len + kVoteTile - 1) / kVoteTile;
-    const int tile_bytes = cpr * 16 * kVoteTile;
-    int ts = env_int("KVC_VOTE_TS", 0);
-    if (ts <= 0) ts = std::max(4, (int)(((size_t)40 << 20) / 148 / tile_bytes));  // ~40 MB of fresh key tiles chip-wide
-    int ns = (n1 + ts - 1) / ts;
-    return std::min(std::max(ns, 1), 64);
-}
-struct VoteWsLayout {
-    int64_t units, tickets;
-    size_t off_final, off_part, bytes;
-};
-static VoteWsLayout vote_ws_layout(const kvc_shape* shape, int nl, const kvc_vote_layer* layers, int cpr) {
-    VoteWsLayout w{};
-    w.units = (int64_t)shape->batch * shape->heads * nl;
-    for (int l = 0; l < nl; ++l) w.tickets += (int64_t)shape->batch * shape->heads * vote_slices(cpr, layers[l].seq_len);
-    w.off_final = (size_t)((64 + 8 * w.units + 255) & ~(int64_t)255);  // ticket counter, arrivals, ready flags
-    w.off_part = w.off_final + (size_t)w.units * 1024;
-    w.bytes = w.off_part + (size_t)w.tickets * 1024;
-    return w;
-}
-
-static int launch_vote_split(const kvc_shape* shape, int32_t n_layers, const kvc_vote_layer* layers, int32_t group,
-                             int32_t window, int cpr, void* workspace, int64_t workspace_bytes, void* stream) {
-    EncodeTiledFn encode = tensor_map_encoder();
-    if (!encode) return KVC_ERR_UNSUPPORTED;
-    const int B = shape->batch, H = shape->heads, D = shape->head_dim, dt = shape->dtype;
-    using Fn = void (*)(const VoteSplitBatchDev);
-    Fn fn = nullptr;
-    if (dt == KVC_DTYPE_BF16)
-        fn = cpr == 8 ? kvc_snapkv_vote_split_kernel<KVC_DTYPE_BF16, 8>
-                      : cpr == 10 ? kvc_snapkv_vote_split_kernel<KVC_DTYPE_BF16, 10> : kvc_snapkv_vote_split_kernel<KVC_DTYPE_BF16, 16>;
-    else
-        fn = cpr == 8 ? kvc_snapkv_vote_split_kernel<KVC_DTYPE_F16, 8>
-                      : cpr == 10 ? kvc_snapkv_vote_split_kernel<KVC_DTYPE_F16, 10> : kvc_snapkv_vote_split_kernel<KVC_DTYPE_F16, 16>;
-    const size_t tile = (size_t)(cpr / 8) * kVoteTile * 128 + (size_t)(cpr % 8) * kVoteTile * 16;
-    const size_t smem = kSpHeader + (2 + kSpRing) * tile;
-    int st = ensure_tma_attrs((const void*)fn, shape->device);
-    if (st != KVC_OK) return st;
-    int sms = 0;
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, shape->device) != cudaSuccess || sms <= 0) sms = 148;
-    const CUtensorMapDataType tdt = dt == KVC_DTYPE_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-    size_t ws_used = 0;
-    for (int l0 = 0; l0 < n_layers; l0 += 32) {
-        const int nl = (n_layers - l0) < 32 ? (n_layers - l0) : 32;
-        static_assert(sizeof(VoteSplitBatchDev) < 32 * 1024, "kernel parameters are limited to 32 KB");
-        const VoteWsLayout w = vote_ws_layout(shape, nl, layers + l0, cpr);
-        if (w.tickets > 0x7fffffff) return KVC_ERR_TOO_LARGE;
-        if (ws_used + w.bytes > (size_t)workspace_bytes) return KVC_ERR_INVALID_ARG;
-        VoteSplitBatchDev bd;
-        memset(&bd, 0, sizeof(bd));
-        bd.B = B;
-        bd.H = H;
-        bd.G = group;
-        bd.W = window;
-        bd.scale_log2e = 1.4426950408889634f / sqrtf((float)D);
-        bd.n_layers = nl;
-        bd.total = (int32_t)w.tickets;
-        bd.pend_max = std::min(std::max(env_int("KVC_VOTE_PEND", 2), 1), kSpPend);
-        bd.ws = reinterpret_cast<uint32_t*>((char*)workspace + ws_used);
-        bd.off_final = (int64_t)w.off_final;
-        bd.off_part = (int64_t)w.off_part;
-        ws_used += (w.bytes + 255) & ~(size_t)255;
-        int64_t tickets = 0;
-        for (int l = 0; l < nl; ++l) {
-            const kvc_vote_layer& v = layers[l0 + l];
-            VoteSplitLayerDev& d = bd.layers[l];
-            const cuuint32_t estr[4] = {1, 1, 1, 1};
-            const cuuint64_t kdims[4] = {(cuuint64_t)D, (cuuint64_t)v.seq_len, (cuuint64_t)H, (cuuint64_t)B};
-            const cuuint64_t kstr[3] = {(cuuint64_t)v.k_stride_s * 2, (cuuint64_t)v.k_stride_h * 2, (cuuint64_t)v.k_stride_b * 2};
-            const cuuint64_t qdims[4] = {(cuuint64_t)D, (cuuint64_t)window, (cuuint64_t)H * group, (cuuint64_t)B};
-            const cuuint64_t qstr[3] = {(cuuint64_t)v.q_stride_s * 2, (cuuint64_t)v.q_stride_h * 2, (cuuint64_t)v.q_stride_b * 2};
-            const cuuint32_t kbox[4] = {64, (cuuint32_t)kVoteTile, 1, 1}, kbox_tail[4] = {16, (cuuint32_t)kVoteTile, 1, 1};
-            const cuuint32_t qbox[4] = {64, (cuuint32_t)window, (cuuint32_t)group, 1};
-            const cuuint32_t qbox_tail[4] = {16, (cuuint32_t)window, (cuuint32_t)group, 1};
-            auto enc = [&](CUtensorMap* m, const void* base, const cuuint64_t* dims, const cuuint64_t* str,
-                           const cuuint32_t* box, CUtensorMapSwizzle sw) {
-                return encode(m, tdt, 4, const_cast<void*>(base), dims, str, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
-                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-            };
-            if (!enc(&d.kmap, v.k_in, kdims, kstr, kbox, CU_TENSOR_MAP_SWIZZLE_128B)) return KVC_ERR_UNSUPPORTED;
-            if (!enc(&d.qmap, v.q_obs, qdims, qstr, qbox, CU_TENSOR_MAP_SWIZZLE_128B)) return KVC_ERR_UNSUPPORTED;
-            if (cpr % 8) {  // D = 80: the last 16 elements of every row through 32-byte-swizzled boxes
-                if (!enc(&d.kmap_tail, v.k_in, kdims, kstr, kbox_tail, CU_TENSOR_MAP_SWIZZLE_32B)) return KVC_ERR_UNSUPPORTED;
-                if (!enc(&d.qmap_tail, v.q_obs, qdims, qstr, qbox_tail, CU_TENSOR_MAP_SWIZZLE_32B)) return KVC_ERR_UNSUPPORTED;
-            }
-            d.votes = (char*)v.votes_out;
-            d.S = v.seq_len;
-            d.first = (int32_t)tickets;
-            d.ns = vote_slices(cpr, v.seq_len);
-            tickets += (int64_t)B * H * d.ns;
-            if (l == 0) bd.per_layer = (int32_t)tickets;
-            else if (d.ns != bd.layers[0].ns) bd.per_layer = 0;
-        }
-        cudaError_t err = cudaMemsetAsync(bd.ws, 0, w.off_final, (cudaStream_t)stream);  // counters and flags
-        if (err != cudaSuccess) return cuda_fail(err, "vote workspace memset");
-        const unsigned grid = (unsigned)std::min<int64_t>(tickets, sms);
-        fn<<<grid, kSpThreads, smem, (cudaStream_t)stream>>>(bd);
-        err = cudaGetLastError();
-        if (err != cudaSuccess) return cuda_fail(err, "kvc_snapkv_vote_split_kernel launch");
-        g_launches.fetch_add(1);
-    }
-    return KVC_OK;
-}
-
-int64_t kvc_vote_workspace_bytes(const kvc_shape* shape, int32_t n_layers, const kvc_vote_layer* layers) {
-    int cpr = 0;
-    if (check_shape(shape, &cpr) != KVC_OK || n_layers <= 0 || !layers) return 0;
-    if (shape->dtype == KVC_DTYPE_F32 || (cpr != 8 && cpr != 10 && cpr != 16)) return 0;
-    // Opt-in (KVC_VOTE_SPLIT=1): the split form halves the HBM traffic of the vote but, at the slice sizes L2 can
-    // hold, its cross-CTA hand-offs cost more than the second HBM read (profiles/r01_vote_split_sweep.json).
-    if (!env_int("KVC_VOTE_SPLIT", 0)) return 0;
-    size_t total = 0;
-    for (int l0 = 0; l0 < n_layers; l0 += 32) {
-        const int nl = (n_layers - l0) < 32 ? (n_layers - l0) : 32;
-        total += (vote_ws_layout(shape, nl, layers + l0, cpr).bytes + 255) & ~(size_t)255;
-    }
-    return (int64_t)total;
-}
-
 int kvc_snapkv_vote(const kvc_shape* shape, int32_t n_layers, const kvc_vote_layer* layers, int32_t group,
                     int32_t window, void* stream) {
-    return kvc_snapkv_vote_ws(shape, n_layers, layers, group, window, nullptr, 0, stream);
-}
-
-int kvc_snapkv_vote_ws(const kvc_shape* shape, int32_t n_layers, const kvc_vote_layer* layers, int32_t group,
-                       int32_t window, void* workspace, int64_t workspace_bytes, void* stream) {
     int cpr = 0;
     int st = check_shape(shape, &cpr);
     if (st != KVC_OK) return st;
     if (n_layers < 0 || (n_layers > 0 && !layers) || group <= 0 || window <= 0) return KVC_ERR_INVALID_ARG;
     if (n_layers == 0) return KVC_OK;
-    const int B = shape->batch, H = shape->heads, dt = shape->dtype;
-    if (dt == KVC_DTYPE_F32) return KVC_ERR_UNSUPPORTED;
+    if (shape->dtype == KVC_DTYPE_F32) return KVC_ERR_UNSUPPORTED;
     if (cpr != 8 && cpr != 10 && cpr != 16) return KVC_ERR_UNSUPPORTED;
     if ((int64_t)group * window > kVoteM) return KVC_ERR_UNSUPPORTED;
     for (int l = 0; l < n_layers; ++l) {
@@ -1327,63 +1043,49 @@ int kvc_snapkv_vote_ws(const kvc_shape* shape, int32_t n_layers, const kvc_vote_
         const int64_t sb = v.k_stride_b | v.k_stride_h | v.k_stride_s | v.q_stride_b | v.q_stride_h | v.q_stride_s;
         if ((sb * 2) & 15) return KVC_ERR_UNSUPPORTED;
     }
-    st = set_device(shape->device);
+    DeviceGuard guard(shape->device);
+    if (guard.status != KVC_OK) return guard.status;
+    // key tiles arrive through TMA tensor loads: layouts a tensor map cannot describe are KVC_ERR_UNSUPPORTED (the
+    // Python layer makes such keys contiguous first)
+    return launch_vote_tma(shape, n_layers, layers, group, window, cpr, nullptr, nullptr, stream);
+}
+
+int kvc_snapkv_vote_compress(const kvc_shape* shape, int32_t n_layers, const kvc_vote_layer* layers,
+                             const kvc_layer_plan* plans, const kvc_layer_io* io, int32_t group, int32_t window,
+                             void* stream) {
+    int cpr = 0;
+    int st = check_shape(shape, &cpr);
     if (st != KVC_OK) return st;
-    using VoteFn = void (*)(const VoteBatchDev);
-    VoteFn fn = nullptr;
-    if (dt == KVC_DTYPE_BF16)
-        fn = cpr == 8 ? kvc_snapkv_vote_kernel<KVC_DTYPE_BF16, 8> : cpr == 10 ? kvc_snapkv_vote_kernel<KVC_DTYPE_BF16, 10>
-                                                                             : kvc_snapkv_vote_kernel<KVC_DTYPE_BF16, 16>;
-    else
-        fn = cpr == 8 ? kvc_snapkv_vote_kernel<KVC_DTYPE_F16, 8> : cpr == 10 ? kvc_snapkv_vote_kernel<KVC_DTYPE_F16, 10>
-                                                                            : kvc_snapkv_vote_kernel<KVC_DTYPE_F16, 16>;
-    if (workspace != nullptr && workspace_bytes > 0 && env_int("KVC_VOTE_TMA", 1)) {
-        // with a workspace: persistent CTAs, every (b, h) split along S so that the second pass hits L2
-        if (((uintptr_t)workspace & 255) != 0) return KVC_ERR_INVALID_ARG;
-        st = launch_vote_split(shape, n_layers, layers, group, window, cpr, workspace, workspace_bytes, stream);
-        if (st != KVC_ERR_UNSUPPORTED) return st;
+    if (n_layers < 0 || (n_layers > 0 && (!layers || !plans || !io)) || group <= 0 || window <= 0)
+        return KVC_ERR_INVALID_ARG;
+    if (n_layers == 0) return KVC_OK;
+    if (shape->dtype == KVC_DTYPE_F32) return KVC_ERR_UNSUPPORTED;
+    if (cpr != 8 && cpr != 10 && cpr != 16) return KVC_ERR_UNSUPPORTED;
+    if ((int64_t)group * window > kVoteM) return KVC_ERR_UNSUPPORTED;
+    const size_t ring_bytes = (size_t)vote_tma_ring(cpr) * ((size_t)(cpr / 8) * kVoteTile * 128 + (size_t)(cpr % 8) * kVoteTile * 16);
+    for (int l = 0; l < n_layers; ++l) {
+        const kvc_vote_layer& v = layers[l];
+        const kvc_layer_plan& p = plans[l];
+        const kvc_layer_io& x = io[l];
+        if (!v.k_in || !v.q_obs || !v.votes_out || v.seq_len <= window) return KVC_ERR_INVALID_ARG;
+        if (((uintptr_t)v.k_in | (uintptr_t)v.q_obs) & 15) return KVC_ERR_UNSUPPORTED;
+        const int64_t sb = v.k_stride_b | v.k_stride_h | v.k_stride_s | v.q_stride_b | v.q_stride_h | v.q_stride_s;
+        if ((sb * 2) & 15) return KVC_ERR_UNSUPPORTED;
+        // the plan of snapkv_lite in vote mode: no sinks, the prefix [0, S - W) ranked by pooled votes, the window kept
+        if (p.seq_len != v.seq_len || p.sink != 0 || p.sel_lo != 0 || p.sel_hi != v.seq_len - window || p.k_sel <= 0 ||
+            p.k_sel > p.sel_hi || p.tail < 0 || p.tail > window || p.score != KVC_SCORE_GIVEN_SCORE)
+            return KVC_ERR_INVALID_ARG;
+        if (p.pool_kernel > 2 * kMaxPoolHalo) return KVC_ERR_UNSUPPORTED;
+        if (!x.k_in || !x.v_in || !x.k_out || !x.v_out || x.k_in != v.k_in) return KVC_ERR_INVALID_ARG;
+        if (((uintptr_t)x.v_in | (uintptr_t)x.k_out | (uintptr_t)x.v_out) & 15) return KVC_ERR_UNSUPPORTED;
+        if (((x.v_stride_b | x.v_stride_h | x.v_stride_s) * 2) & 15) return KVC_ERR_UNSUPPORTED;
+        if (x.k_stride_b != v.k_stride_b || x.k_stride_h != v.k_stride_h || x.k_stride_s != v.k_stride_s)
+            return KVC_ERR_INVALID_ARG;
+        if (vote_tail_bytes(cpr, p.sel_hi, (p.k_sel + 3) & ~3) > ring_bytes) return KVC_ERR_TOO_LARGE;
     }
-    if (env_int("KVC_VOTE_TMA", 1)) {
-        // head_dim 64 / 80 / 128: key tiles arrive through TMA tensor loads; strided layouts a tensor map cannot
-        // describe fall through to the cp.async-fed kernel below
-        st = launch_vote_tma(shape, n_layers, layers, group, window, cpr, stream);
-        if (st != KVC_ERR_UNSUPPORTED) return st;
-    }
-    size_t smem = 2304 + 3 * (size_t)(kVoteTile / 8) * cpr * kVoteLBO;
-    int threads = 256;
-    st = ensure_tma_attrs((const void*)fn, shape->device);
-    if (st != KVC_OK) return st;
-    for (int l0 = 0; l0 < n_layers; l0 += KVC_MAX_LAYERS_PER_LAUNCH) {
-        const int nl = (n_layers - l0) < KVC_MAX_LAYERS_PER_LAUNCH ? (n_layers - l0) : KVC_MAX_LAYERS_PER_LAUNCH;
-        VoteBatchDev bd;
-        memset(&bd, 0, sizeof(bd));
-        bd.B = B;
-        bd.H = H;
-        bd.G = group;
-        bd.W = window;
-        bd.scale_log2e = 1.4426950408889634f / sqrtf((float)shape->head_dim);
-        bd.pad[0] = vote_debug_mode();  // stage isolation for profiling: 1 = no math, 2 = no math, no MMA
-        for (int l = 0; l < nl; ++l) {
-            const kvc_vote_layer& v = layers[l0 + l];
-            VoteLayerDev& d = bd.layers[l];
-            d.k = (const char*)v.k_in;
-            d.q = (const char*)v.q_obs;
-            d.votes = (char*)v.votes_out;
-            d.ksb = v.k_stride_b * 2;
-            d.ksh = v.k_stride_h * 2;
-            d.kss = v.k_stride_s * 2;
-            d.qsb = v.q_stride_b * 2;
-            d.qsh = v.q_stride_h * 2;
-            d.qss = v.q_stride_s * 2;
-            d.S = v.seq_len;
-        }
-        dim3 grid((unsigned)((int64_t)B * H), (unsigned)nl, 1);
-        fn<<<grid, threads, smem, (cudaStream_t)stream>>>(bd);
-        cudaError_t err = cudaGetLastError();
-        if (err != cudaSuccess) return cuda_fail(err, "kvc_snapkv_vote_kernel launch");
-        g_launches.fetch_add(1);
-    }
-    return KVC_OK;
+    DeviceGuard guard(shape->device);
+    if (guard.status != KVC_OK) return guard.status;
+    return launch_vote_tma(shape, n_layers, layers, group, window, cpr, plans, io, stream);
 }
 
 #endif  // KVC_HAS_VOTE

@@ -8,19 +8,27 @@
 //     vote[b, hkv, j] = sum over the G query heads of the group and the W window queries i of
 //                       softmax_j( q_i . k_j / sqrt(D)  [causal inside the window] )         for j < P = S - W
 //
-// One CTA (256 threads) owns one (layer, batch, kv head).  Queries of the group are stacked into a
-// 128-row operand (G*W <= 128, zero rows beyond).  Keys stream in tiles of 128 rows, twice:
+// One CTA (576 threads, one per SM) owns one (layer, batch, kv head).  Queries of the group are stacked into a
+// 128-row operand (G*W <= 128; fewer rows are replicated, see below).  Keys stream in tiles of 128 rows, twice:
 //
 //   pass 1  S   = Q . Ktile^T  (M = query rows, N = keys): TMEM lane = query row, so each thread keeps the
 //           online softmax statistics (running max m_i, sum l_i) of ITS row — no cross-thread traffic;
 //   pass 2  S^T = Ktile . Q^T  (M = keys, N = query rows): TMEM lane = key, so each thread sums
-//           exp2(s*c - m_i) / l_i over the 128 columns of ITS key — the vote — and stores it.
+//           exp2(s*c - m_i) / l_i over the columns of ITS key — the vote — and stores it.
 //
-// Operands are staged in shared memory in the canonical K-major no-swizzle UMMA layout (8x16-byte core
-// matrices) by the CTA's own threads (`cp.async` 16-byte copies straight into the layout, in flight under
-// the math of the previous tile), the accumulator lives in TMEM (2 x 128 columns, one per 128-thread
-// pipeline), `tcgen05.mma` is issued by one thread per pipeline,
-// completion arrives on an mbarrier through `tcgen05.commit`, and `tcgen05.ld` brings scores to registers.
+// Pass 1 exists only to produce the softmax denominators.  An attention kernel that has just run those W
+// queries already holds them (the log-sum-exp per query row every flash-attention forward returns): with
+// kvc_vote_layer.lse the kernel runs pass 2 alone and K crosses HBM once instead of twice.
+//
+// Key tiles arrive through TMA tensor loads (128-byte-swizzled boxes = the K-major SW128 UMMA layout), the
+// accumulators live in TMEM (4 x 128 columns), `tcgen05.mma` is issued by one thread, completion arrives on
+// mbarriers through `tcgen05.commit`, and `tcgen05.ld` brings scores to registers.
+//
+// Fused tail (kvc_snapkv_vote_compress): once a unit's votes exist the SAME CTA pools them, radix-selects the
+// kept rows and gathers K and V into the compacted output — snapkv_lite.py:104-150 behind the vote in ONE launch.
+// The votes go through a [B,H,P] scratch array in the cache dtype (the rounding point of the two-launch form) that
+// the CTA reads straight back out of L2; the key-tile ring, dead by then, becomes the select's key buffer and the
+// gather's staging slots.
 // Intensity is ~2*128 flop per key byte at most: the kernel stays HBM/MUFU-bound, not tensor-bound
 // (SURVEY.md §7 "SnapKV vote spec gap") — the tensor pipe is reported, not chased.
 #pragma once
@@ -28,26 +36,10 @@
 #include <type_traits>
 
 #include "kvc_device.cuh"
+#include "kvc_fused_tma.cuh"
 #include "kvc_tma.cuh"
 
 namespace kvc {
-
-struct VoteLayerDev {
-    const char* k;    // [B,H,S,D] keys
-    const char* q;    // [B,Hq,W,D] observation-window queries, Hq = G*H
-    char* votes;      // [B,H,P] in the cache dtype
-    int64_t ksb, ksh, kss;  // BYTE strides of K
-    int64_t qsb, qsh, qss;  // BYTE strides of Q (batch, query head, row)
-    int32_t S, pad;
-};
-static_assert(sizeof(VoteLayerDev) == 80, "VoteLayerDev is passed by value in kernel params");
-
-struct VoteBatchDev {
-    int32_t B, H, G, W;
-    float scale_log2e;  // log2(e) / sqrt(D)
-    int32_t pad[3];
-    VoteLayerDev layers[KVC_MAX_LAYERS_PER_LAUNCH];
-};
 
 constexpr int kVoteM = 128;     // rows of both MMA shapes
 constexpr int kVoteTile = 128;  // keys per tile
@@ -138,234 +130,14 @@ __device__ __forceinline__ void tile_item(int q, int& r, int& c) {
     r = rg * 8 + (rem & 7);
 }
 
-__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src, bool valid) {
-    const uint32_t n = valid ? 16u : 0u;  // src-size 0: the 16 destination bytes are zero-filled
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(n) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-}
-__device__ __forceinline__ void group_barrier(int grp) {  // immediate ids: ptxas reserves only the barriers named
-    if (grp == 0)
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-    else
-        asm volatile("bar.sync 2, 128;" ::: "memory");
-}
-
-// 256 threads = two independent 128-thread pipelines ("groups").  Group g owns key tiles t = g, g+2, ...,
-// one operand buffer, one 128-column accumulator in TMEM, one mbarrier and one named barrier; both share the
-// Q operand and the row statistics.  Per tile a group: waits for its MMA, starts the cp.async of its next
-// tile straight into the canonical layout (no registers), does the softmax math on the accumulator while
-// those copies fly, then hands the staged tile to the tensor core.  The other group (and the second resident
-// CTA) keep the SM busy meanwhile.
-template <int DT, int CPR>
-__global__ void __launch_bounds__(256, 2) kvc_snapkv_vote_kernel(const __grid_constant__ VoteBatchDev bd) {
-    using Tr = Traits<DT>;
-    using Key = typename Tr::Key;
-    static_assert(DT != KVC_DTYPE_F32, "the vote runs on 16-bit caches (kind::f16)");
-    constexpr int TILE_BYTES = (kVoteTile / 8) * CPR * kVoteLBO;
-    constexpr int CH = kVoteTile * CPR / 128;                     // 16-byte chunks per thread per tile
-    constexpr uint32_t IDESC = umma_idesc_f16(DT == KVC_DTYPE_BF16 ? 1 : 0, kVoteM, kVoteTile);
-
-    const VoteLayerDev& L = bd.layers[blockIdx.y];
-    const int bh = blockIdx.x;
-    const int b = bh / bd.H, h = bh - b * bd.H;
-    const int tid = threadIdx.x, warp = tid >> 5;
-    const int grp = tid >> 7, gt = tid & 127;  // group and thread-in-group (= TMEM lane)
-    const int S = L.S, W = bd.W, G = bd.G;
-    const int P = S - W;
-    const int rows_q = G * W;
-
-    extern __shared__ __align__(128) unsigned char smem[];
-    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(smem);
-    const uint32_t bar = smem_u32(smem + 16) + grp * 8;
-    float* s_m = reinterpret_cast<float*>(smem + 256);            // [128] row max (log2 domain)
-    float* s_invl = reinterpret_cast<float*>(smem + 256 + 512);   // [128] 1 / row sum (0 for padding rows)
-    float* s_part = reinterpret_cast<float*>(smem + 256 + 1024);  // [2][128] group 1's partial (m, l)
-    unsigned char* s_q = smem + 2304;
-    unsigned char* s_k = s_q + TILE_BYTES + grp * TILE_BYTES;     // this group's operand buffer
-
-    if (warp == 0) tmem_alloc(smem_u32(s_tmem), 256);
-    if (gt == 0) {
-        mbar_init(bar, 1);
-        mbar_init_fence();
-    }
-    // ---------------------------------------------------------------- Q operand (once per unit)
-    const char* kbase = L.k + (int64_t)b * L.ksb + (int64_t)h * L.ksh;
-    for (int q = tid; q < kVoteM * CPR; q += 256) {
-        int r, c;
-        tile_item<CPR>(q, r, c);
-        int4 v = make_int4(0, 0, 0, 0);
-        if (r < rows_q) {
-            const int g = r / W, w = r - g * W;
-            v = ldg128_stream(L.q + (int64_t)b * L.qsb + (int64_t)(h * G + g) * L.qsh + (int64_t)w * L.qss + c * 16);
-        }
-        *reinterpret_cast<int4*>(s_q + umma_off<CPR>(r, c)) = v;
-    }
-    const uint32_t k_addr = smem_u32(s_k), q_addr = smem_u32(s_q);
-    // stage key tile t into this group's buffer (cp.async, 16 bytes per copy, CPR copies per thread).
-    // The row stride is pinned in a register: re-reading it from the parameter bank inside the loop put a
-    // long-scoreboard stall on every address (profiles/r01_vote_*).
-    int64_t kss = L.kss;
-    asm volatile("" : "+l"(kss));
-    auto stage_tile = [&](int t) {
-        const int r0 = t * kVoteTile;
-        const char* tile = kbase + (int64_t)r0 * kss;
-#pragma unroll
-        for (int i = 0; i < CH; ++i) {
-            int r, c;
-            tile_item<CPR>(i * 128 + gt, r, c);
-            const bool ok = r0 + r < S;
-            cp_async16(k_addr + umma_off<CPR>(r, c), ok ? tile + r * kss + c * 16 : kbase, ok);
-        }
-    };
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem = *s_tmem + grp * kVoteTile;                 // this group's accumulator columns
-    const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);  // this warp's 32 TMEM lanes
-
-    // the CPR/2 K-steps of one 128x128xD product: pass 1 (A = Q, B = K tile) or pass 2 (A = K tile, B = Q)
-    auto issue = [&](bool keys_are_rows) {
-        const uint32_t a0 = keys_are_rows ? k_addr : q_addr;
-        const uint32_t b0 = keys_are_rows ? q_addr : k_addr;
-#pragma unroll
-        for (int ks = 0; ks < CPR / 2; ++ks) {
-            const uint64_t ad = umma_smem_desc(a0 + ks * 2 * kVoteLBO, kVoteLBO, CPR * kVoteLBO);
-            const uint64_t bdsc = umma_smem_desc(b0 + ks * 2 * kVoteLBO, kVoteLBO, CPR * kVoteLBO);
-            umma_f16(tmem, ad, bdsc, IDESC, ks > 0 ? 1u : 0u);
-        }
-        umma_commit(bar);
-    };
-
-    const float c2 = bd.scale_log2e;
-    uint32_t phase = 0;
-    for (int pass = 0; pass < 2; ++pass) {
-        const bool keys_are_rows = pass == 1;
-        const int n_tiles = keys_are_rows ? (P + kVoteTile - 1) / kVoteTile : (S + kVoteTile - 1) / kVoteTile;
-        float m_run = -INFINITY, l_run = 0.f;  // pass 1: this group's share of query row `gt`
-        if (grp < n_tiles) {
-            stage_tile(grp);
-            cp_async_wait_all();
-            fence_proxy_async_smem();
-        }
-        group_barrier(grp);
-        if (gt == 0 && grp < n_tiles) {
-            tc_fence_after();
-            issue(keys_are_rows);
-        }
-        for (int t = grp; t < n_tiles; t += 2) {
-            const bool more = t + 2 < n_tiles;
-            mbar_wait(bar, phase);
-            phase ^= 1;
-            tc_fence_after();
-            if (more) stage_tile(t + 2);  // the operand buffer is free: copies fly under the math below
-            const int key0 = t * kVoteTile;
-            uint32_t v[32];
-            if (!keys_are_rows && (warp & 3) * 32 >= rows_q) {
-                // this warp's 32 TMEM lanes are padding query rows (G*W < 128, e.g. MHA with W = 32): nothing to reduce
-            } else if (!keys_are_rows) {
-                // ---------------- pass 1: lane = query row, columns = keys of this tile (online softmax statistics)
-                const int limit = P + ((gt < rows_q) ? (gt % W) : 0);  // causal inside the window
-                const bool masked = key0 + kVoteTile > P;               // only the last tiles meet the mask / S
-#pragma unroll 1
-                for (int cb = 0; cb < kVoteTile; cb += 32) {
-                    tmem_ld32(t_lane + cb, v);
-                    float cmax = -INFINITY;
-                    if (masked) {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int key = key0 + cb + j;
-                            if (key > limit || key >= S) v[j] = 0xff800000u;  // -inf
-                            cmax = fmaxf(cmax, __uint_as_float(v[j]));
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) cmax = fmaxf(cmax, __uint_as_float(v[j]));
-                    }
-                    const float m_new = fmaxf(m_run, cmax * c2);
-                    if (m_new > -INFINITY) {
-                        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-#pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            acc0 += ex2(fmaf(__uint_as_float(v[j]), c2, -m_new));
-                            acc1 += ex2(fmaf(__uint_as_float(v[j + 1]), c2, -m_new));
-                            acc2 += ex2(fmaf(__uint_as_float(v[j + 2]), c2, -m_new));
-                            acc3 += ex2(fmaf(__uint_as_float(v[j + 3]), c2, -m_new));
-                        }
-                        l_run = fmaf(l_run, ex2(m_run - m_new), (acc0 + acc1) + (acc2 + acc3));
-                        m_run = m_new;
-                    }
-                }
-            } else {
-                // ---------------- pass 2: lane = key, columns = query rows
-                float vote0 = 0.f, vote1 = 0.f, vote2 = 0.f, vote3 = 0.f;
-#pragma unroll 1
-                for (int cb = 0; cb < rows_q; cb += 32) {  // padding query rows (columns >= G*W) never vote
-                    tmem_ld32(t_lane + cb, v);
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        const float4 mm = *reinterpret_cast<const float4*>(s_m + cb + j);
-                        const float4 il = *reinterpret_cast<const float4*>(s_invl + cb + j);
-                        vote0 = fmaf(ex2(fmaf(__uint_as_float(v[j + 0]), c2, -mm.x)), il.x, vote0);
-                        vote1 = fmaf(ex2(fmaf(__uint_as_float(v[j + 1]), c2, -mm.y)), il.y, vote1);
-                        vote2 = fmaf(ex2(fmaf(__uint_as_float(v[j + 2]), c2, -mm.z)), il.z, vote2);
-                        vote3 = fmaf(ex2(fmaf(__uint_as_float(v[j + 3]), c2, -mm.w)), il.w, vote3);
-                    }
-                }
-                const int key = key0 + gt;
-                if (key < P) {
-                    Key* out = reinterpret_cast<Key*>(L.votes) + (int64_t)bh * P;
-                    out[key] = (Key)Tr::to_raw((vote0 + vote1) + (vote2 + vote3));
-                }
-            }
-            // accumulator read out, next tile staged: hand it to the tensor core
-            tc_fence_before();
-            if (more) {
-                cp_async_wait_all();
-                fence_proxy_async_smem();
-            }
-            group_barrier(grp);
-            if (more && gt == 0) {
-                tc_fence_after();
-                issue(keys_are_rows);
-            }
-        }
-        if (!keys_are_rows) {
-            // merge the two groups' partial statistics of each query row; padding rows (>= G*W) never vote
-            if (grp == 1) {
-                s_part[gt] = m_run;
-                s_part[128 + gt] = l_run;
-            }
-            __syncthreads();
-            if (grp == 0) {
-                const float m1 = s_part[gt], l1 = s_part[128 + gt];
-                const float m = fmaxf(m_run, m1);
-                float l = 0.f;
-                if (m > -INFINITY) l = l_run * ex2(m_run - m) + l1 * ex2(m1 - m);
-                const bool live = gt < rows_q && l > 0.f;
-                s_m[gt] = live ? m : 0.f;
-                s_invl[gt] = live ? 1.f / l : 0.f;
-            }
-            __syncthreads();
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) tmem_dealloc(*s_tmem, 256);
-}
-
 // ---------------------------------------------------------------------------------------------
-// Warp-specialised forms below: ONE CTA per SM; warps 0-15 are four math groups (128 threads = the 128 TMEM lanes;
+// Warp-specialised: ONE CTA per SM; warps 0-15 are four math groups (128 threads = the 128 TMEM lanes;
 // group g owns accumulator g, 128 of the 512 TMEM columns, and reduces work items g, g+4, g+8, ...), one thread feeds
 // a shared-memory ring of key tiles, one thread issues every tcgen05.mma (waits: slot full, accumulator drained) and
 // commits to the accumulator-full and slot-empty mbarriers.  Work items are the tiles of pass 1 (all S keys, A = Q)
 // followed by the tiles of pass 2 (P keys, A = keys); the copy and MMA threads run ahead across the pass boundary,
 // only the math groups meet there to merge the row statistics.  (A cp.async-fed variant of this layout, four copy
 // warps, was measured at 21.6 ms on c4_vote against 15.6 ms for the TMA-fed one and removed.)
-constexpr int kWsRing = 5;
-
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -382,8 +154,17 @@ struct VoteTmaLayerDev {
     alignas(64) CUtensorMap map_tail;  // D % 64 == 16 (D = 80): box (16, 128, 1, 1), SWIZZLE_32B, for the last 16 elements
     const char* q;
     char* votes;
+    const float* lse;  // optional [B, H*G, W] natural-log softmax denominators of the window queries: pass 2 only
     int64_t qsb, qsh, qss;
     int32_t S, pad;
+    // fused tail (k_out != nullptr): pool the votes, keep the ksel highest of [0, S - W) + the last `tail` rows
+    const char* k_in;
+    const char* v_in;
+    char* k_out;
+    char* v_out;
+    int32_t* idx_out;
+    int64_t ksb, ksh, kss, vsb, vsh, vss;  // BYTE strides of K and V
+    int32_t ksel, tail, pool, idx_cap;
 };
 struct VoteTmaBatchDev {
     int32_t B, H, G, W;
@@ -456,7 +237,8 @@ __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __gri
     const bool one_k = bd.pad[0] == 4;              // profiling: no math, ONE K step per tile
     const int dbg = no_tail ? 0 : (one_k ? 1 : bd.pad[0]);  // profiling: 1 = no math, 2 = no math, no MMA
     const int RB = rows_q <= 32 ? 32 : (rows_q <= 64 ? 64 : 128);  // rows per replica block, F = 128 / RB replicas
-    const int n1 = (S + kVoteTile - 1) / kVoteTile, n2 = (P + kVoteTile - 1) / kVoteTile;
+    const bool have_lse = L.lse != nullptr;  // the caller holds the softmax denominators: no pass 1
+    const int n1 = have_lse ? 0 : (S + kVoteTile - 1) / kVoteTile, n2 = (P + kVoteTile - 1) / kVoteTile;
     const int n_items = n1 + n2;
 
     extern __shared__ __align__(1024) unsigned char smem_tma[];  // swizzle atoms need 1024-byte alignment
@@ -469,6 +251,7 @@ __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __gri
     float* s_m = reinterpret_cast<float*>(smem + 512);
     float* s_invl = reinterpret_cast<float*>(smem + 1024);
     float* s_part = reinterpret_cast<float*>(smem + 1536);  // [4 groups][2][128]
+    const uint32_t bar_tail = smem_u32(smem + 5632);        // [18]  count = 1: the fused tail's staging slots
     unsigned char* s_q = smem + 6144;
     unsigned char* s_ring = s_q + Q_BYTES;  // 1024-byte aligned: swizzle atoms are 8 rows x 128 B
 
@@ -481,6 +264,7 @@ __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __gri
             mbar_init(bar_tfull + 8 * i, 1);
             mbar_init(bar_tempty + 8 * i, 128);
         }
+        for (int i = 0; i < 18; ++i) mbar_init(bar_tail + 8 * i, 1);
         mbar_init_fence();
     }
     if (warp == 17) tmem_alloc(smem_u32(s_tmem), 512);
@@ -571,7 +355,16 @@ __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __gri
         s_part[(grp * 2 + 0) * 128 + gt] = m_run;
         s_part[(grp * 2 + 1) * 128 + gt] = l_run;
         asm volatile("bar.sync 1, 512;" ::: "memory");
-        if (tid < 128) {
+        if (have_lse) {
+            // exp(s - lse) is the normalised probability: m = lse in the log2 domain, 1 / l = 1
+            if (tid < 128) {
+                const bool live = tid < rows_q;
+                float lse = 0.f;
+                if (live) lse = L.lse[((int64_t)b * bd.H * G + (int64_t)h * G + tid / W) * W + tid % W];
+                s_m[tid] = lse * 1.4426950408889634f;
+                s_invl[tid] = live ? 1.f : 0.f;
+            }
+        } else if (tid < 128) {
             // query row `tid`: four groups x F replicas, always in the same order
             float m = -INFINITY;
             if (tid < RB) {
@@ -695,6 +488,46 @@ __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __gri
     tc_fence_before();
     __syncthreads();
     if (warp == 17) tmem_dealloc(tmem, 512);
+    if (L.k_out == nullptr) return;  // votes only (CTA-uniform)
+
+    // ==================================================================== fused tail: pool -> select -> gather
+    // Every MMA has completed (the math groups drained every accumulator), so the key-tile ring is dead: it becomes
+    // histogram | kept indices | radix keys | staging slots.  The unit's votes were written by this CTA's own
+    // threads before the barrier above: they are read back with plain loads (L2 hits), in the cache dtype — the
+    // same rounding point as the two-launch form, so both keep the same rows.
+    {
+        constexpr int NT = 576;
+        constexpr int RBYTES = CPR * 16;
+        int32_t* misc = reinterpret_cast<int32_t*>(s_part);  // 512 B of scalars; the row statistics are dead
+        uint32_t* hist = reinterpret_cast<uint32_t*>(s_ring);
+        int32_t* sidx = reinterpret_cast<int32_t*>(s_ring + kHistBins * 4);
+        Key* keys = reinterpret_cast<Key*>(s_ring + kHistBins * 4 + L.idx_cap * 4);
+        const int keys_bytes = (P * (int)sizeof(Key) + 15) & ~15;
+        const int off_stage = (kHistBins * 4 + L.idx_cap * 4 + keys_bytes + 127) & ~127;
+        const int nstage = min(18, (RING * TILE_BYTES - off_stage) / (32 * RBYTES));  // >= 1: checked by the host
+        const int ksel = L.ksel;
+        fence_proxy_async_smem();
+        for (int i = tid; i < kHistBins; i += NT) hist[i] = 0;
+        const Key* src = reinterpret_cast<const Key*>(L.votes) + (int64_t)bh * P;
+        load_keys_vectorised<DT, NT, /*NC=*/false>(src, P, keys, [&](int i, uint32_t raw) { keys[i] = (Key)raw; });
+        __syncthreads();
+        snapkv_transform<DT, NT>(keys, P, L.pool, hist, misc, /*invert=*/false);
+        block_radix_select<Key, NT>(keys, P, ksel, hist, misc, sidx, 0);
+        const int C = ksel + L.tail;
+        const KeepMap src_row{sidx, 0, ksel, S - L.tail - ksel};
+        if (L.idx_out != nullptr) {
+            int32_t* io = L.idx_out + (int64_t)bh * C;
+            for (int j = tid; j < C; j += NT) io[j] = src_row(j);
+        }
+        if (warp < nstage) {
+            uint32_t parity = 0;
+            gather_unit(src_row, C, L.k_in + (int64_t)b * L.ksb + (int64_t)h * L.ksh,
+                        L.v_in + (int64_t)b * L.vsb + (int64_t)h * L.vsh, L.kss, L.vss,
+                        L.k_out + (int64_t)bh * C * RBYTES, L.v_out + (int64_t)bh * C * RBYTES, RBYTES,
+                        smem_u32(s_ring + off_stage) + (uint32_t)(warp * 32 * RBYTES), bar_tail + 8 * warp, parity, warp,
+                        nstage, lane);
+        }
+    }
 }
 
 }  // namespace kvc

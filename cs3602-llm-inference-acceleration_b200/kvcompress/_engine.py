@@ -23,19 +23,20 @@ from . import _planner as P
 
 _LIB_NAME = "libkvc_sm100a.so"
 _CSRC_DIR = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "csrc"))
-_LIB_PATH = os.environ.get("KVC_LIBRARY") or os.path.join(_CSRC_DIR, _LIB_NAME)  # KVC_LIBRARY: A/B builds of the kernels
+_LIB_PATH = os.path.join(_CSRC_DIR, _LIB_NAME)
 
 # struct layouts of include/kvc.h
 _PLAN = struct.Struct("8i")        # kvc_layer_plan: seq_len sink sel_lo sel_hi k_sel tail score pool_kernel
-_IO = struct.Struct("4P6q3P")      # kvc_layer_io: k_in v_in k_out v_out | 6 strides | idx_out idx_in score_in
+_IO = struct.Struct("4P6q4P2q")    # kvc_layer_io: k_in v_in k_out v_out | 6 strides | idx_out idx_in score_in norms_in | 2 strides
 _SHAPE = struct.Struct("5i")       # kvc_shape: batch heads head_dim dtype device
-assert _PLAN.size == 32 and _IO.size == 104 and _SHAPE.size == 20
-KVC_ABI_VERSION = 4
+assert _PLAN.size == 32 and _IO.size == 128 and _SHAPE.size == 20
+KVC_ABI_VERSION = 5
 
 KVC_DTYPE = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
 KVC_OK = 0
 _STATUS_EXC = {1: ValueError, 2: ValueError, 3: ValueError, 4: RuntimeError}
 
+_RANKED = (P.SCORE_L2_LOW, P.SCORE_L2_HIGH, P.SCORE_SNAPKV_POOL)  # scores derived from key norms
 _lib = None
 _WS_NEED = {}  # (plan set, group) -> workspace bytes the launch needs (0: everything fits on chip)
 
@@ -86,11 +87,9 @@ def load_library():
     lib.kvc_snapkv_vote.restype = ctypes.c_int
     lib.kvc_snapkv_vote.argtypes = [ctypes.c_char_p, ctypes.c_int32, ctypes.c_char_p, ctypes.c_int32, ctypes.c_int32,
                                     ctypes.c_void_p]
-    lib.kvc_vote_workspace_bytes.restype = ctypes.c_int64
-    lib.kvc_vote_workspace_bytes.argtypes = [ctypes.c_char_p, ctypes.c_int32, ctypes.c_char_p]
-    lib.kvc_snapkv_vote_ws.restype = ctypes.c_int
-    lib.kvc_snapkv_vote_ws.argtypes = [ctypes.c_char_p, ctypes.c_int32, ctypes.c_char_p, ctypes.c_int32, ctypes.c_int32,
-                                       ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]
+    lib.kvc_snapkv_vote_compress.restype = ctypes.c_int
+    lib.kvc_snapkv_vote_compress.argtypes = [ctypes.c_char_p, ctypes.c_int32, ctypes.c_char_p, ctypes.c_char_p,
+                                             ctypes.c_char_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p]
     if lib.kvc_abi_version() != KVC_ABI_VERSION:
         raise RuntimeError(f"{_LIB_NAME}: ABI version {lib.kvc_abi_version()} != {KVC_ABI_VERSION} — rebuild the library")
     _lib = lib
@@ -170,7 +169,7 @@ class PlanSet:
 
 
 def run_plans(kv: Sequence[Tuple[torch.Tensor, torch.Tensor]], plans, given_indices: Optional[dict] = None,
-              return_indices: bool = False, given_scores: Optional[dict] = None):
+              return_indices: bool = False, given_scores: Optional[dict] = None, norms: Optional[Sequence] = None):
     """Apply per-layer plans (a list of ``LayerPlan`` or a cached :class:`PlanSet`) to a list of (K, V) pairs.
 
     KEEP layers keep their tensor objects, VIEW layers become ``x[:, :, -n:, :]`` views (both
@@ -181,6 +180,9 @@ def run_plans(kv: Sequence[Tuple[torch.Tensor, torch.Tensor]], plans, given_indi
     given_indices: {layer_idx: int32 tensor [B, H, k_sel]} for SCORE_GIVEN_INDEX plans.
     given_scores: {layer_idx: cache-dtype tensor [B, H, sel_hi - sel_lo]} for SCORE_GIVEN_SCORE plans.
     return_indices: also return {layer_idx: int32 tensor [B, H, C]} of kept absolute rows.
+    norms: per-layer stored key norms (``[B, H, >= S]``, cache dtype, last dim dense; ``None`` entries allowed) — what
+        ``torch.norm(K, p=2, dim=-1)`` returns for the rows.  Layers that have them are ranked from 2-4 bytes per row
+        instead of reading the K rows of the selection region (a :class:`KVSlabCache` records them at append time).
     """
     ps = plans if isinstance(plans, PlanSet) else PlanSet(plans)
     out: List[Tuple[torch.Tensor, torch.Tensor]] = list(kv)
@@ -277,10 +279,22 @@ def run_plans(kv: Sequence[Tuple[torch.Tensor, torch.Tensor]], plans, given_indi
                     raise ValueError(f"layer {li}: scores must be a contiguous {dtype} [B, H, region] tensor on {device}")
                 score_in_ptr = gs.data_ptr()
                 keepalive.append(gs)
+            norms_ptr, nsb, nsh = 0, 0, 0
+            nt = None if norms is None else norms[li]
+            if nt is not None and plan.k_sel > 0 and plan.score in _RANKED:
+                if nt.dtype != dtype or nt.dim() != 3 or nt.size(0) != B or nt.size(1) != H or nt.size(2) < plan.seq_len \
+                        or nt.stride(2) != 1 or nt.device != device:
+                    raise ValueError(f"layer {li}: stored norms must be a {dtype} [B, H, >= S] tensor on {device} "
+                                     "with a dense last dimension")
+                if on_host and not nt.is_pinned():
+                    raise RuntimeError(f"layer {li}: stored norms of a host-resident cache must be pinned")
+                norms_ptr, nsb, nsh = nt.data_ptr(), nt.stride(0), nt.stride(1)
+                keepalive.append(nt)
             plan_buf[m * _PLAN.size:(m + 1) * _PLAN.size] = ps.packed[li]
             ks, vs = keys.stride(), values.stride()
             _IO.pack_into(io_buf, m * _IO.size, keys.data_ptr(), values.data_ptr(), k_out_ptr, v_out_ptr,
-                          ks[0], ks[1], ks[2], vs[0], vs[1], vs[2], idx_out_ptr, idx_in_ptr, score_in_ptr)
+                          ks[0], ks[1], ks[2], vs[0], vs[1], vs[2], idx_out_ptr, idx_in_ptr, score_in_ptr,
+                          norms_ptr, nsb, nsh)
         dev_index = run_device.index if run_device.index is not None else torch.cuda.current_device()
         shape_rec = _SHAPE.pack(B, H, D, KVC_DTYPE[dtype], dev_index)
         plan_bytes = bytes(plan_buf)
@@ -339,18 +353,13 @@ def select(scores: torch.Tensor, k: int, largest: bool = False) -> torch.Tensor:
     return out
 
 
-_VOTE = struct.Struct("3P6q2i")  # kvc_vote_layer: k_in q_obs votes_out | 6 strides | seq_len reserved
-assert _VOTE.size == 80
+_VOTE = struct.Struct("3P6q2iP")  # kvc_vote_layer: k_in q_obs votes_out | 6 strides | seq_len reserved | lse
+assert _VOTE.size == 88
 
 
-def snapkv_votes(layers: Sequence[Tuple[torch.Tensor, torch.Tensor]], window: int) -> List[torch.Tensor]:
-    """Observation-window votes on the tensor cores (tcgen05), one launch for every (keys, obs_queries) pair.
-
-    layers: [(keys [B,H,S,D], obs_queries [B,H*G,W,D]), ...] 16-bit CUDA tensors of one shape.
-    Returns votes [B,H,S-W] per layer (cache dtype):
-    ``softmax(Q K^T / sqrt(D), causal inside the window)[..., :S-W].sum over the window queries and the group``."""
-    if not layers:
-        return []
+def _vote_records(layers: Sequence[Tuple[torch.Tensor, torch.Tensor]], window: int, lse: Optional[Sequence]):
+    """Validate (keys, obs_queries[, lse]) per layer and pack the ``kvc_vote_layer`` records.
+    Returns (shape record, packed records, votes tensors, group size, keep-alive list, prepared keys)."""
     k0, q0 = layers[0]
     _require_cuda(k0, "keys")
     B, H, _, D = k0.shape
@@ -363,7 +372,9 @@ def snapkv_votes(layers: Sequence[Tuple[torch.Tensor, torch.Tensor]], window: in
         raise ValueError(f"head_dim {D}: the vote kernel covers head_dim 64, 80 and 128")
     if G * window > 128:
         raise ValueError(f"group size x observation_window = {G * window} exceeds the 128 query rows of one MMA")
-    out, keep = [], []
+    if lse is not None and len(lse) != len(layers):
+        raise ValueError(f"obs_lse: {len(lse)} entries for {len(layers)} layers")
+    out, keep, prepared = [], [], []
     buf = bytearray(_VOTE.size * len(layers))
     for m, (keys, q) in enumerate(layers):
         _require_cuda(keys, f"layer {m} keys")
@@ -377,19 +388,106 @@ def snapkv_votes(layers: Sequence[Tuple[torch.Tensor, torch.Tensor]], window: in
             keys = keys.contiguous()
         if not _rows_ok(q):
             q = q.contiguous()
+        lse_ptr = 0
+        if lse is not None and lse[m] is not None:
+            t = lse[m]
+            if t.dtype != torch.float32 or tuple(t.shape) != (B, H * G, window) or t.device != k0.device:
+                raise ValueError(f"layer {m}: obs_lse must be a float32 [B={B}, H*G={H * G}, W={window}] tensor on {k0.device}")
+            t = t.contiguous()
+            keep.append(t)
+            lse_ptr = t.data_ptr()
         keep.append((keys, q))
+        prepared.append(keys)
         votes = torch.empty((B, H, keys.size(2) - window), dtype=keys.dtype, device=keys.device)
         out.append(votes)
         ks, qs = keys.stride(), q.stride()
         _VOTE.pack_into(buf, m * _VOTE.size, keys.data_ptr(), q.data_ptr(), votes.data_ptr(), ks[0], ks[1], ks[2],
-                        qs[0], qs[1], qs[2], keys.size(2), 0)
+                        qs[0], qs[1], qs[2], keys.size(2), 0, lse_ptr)
     shape = _SHAPE.pack(B, H, D, KVC_DTYPE[k0.dtype], k0.device.index)
-    lib, desc = load_library(), bytes(buf)
-    # long sequences: every (b, h) is split along S over several CTAs that meet through this scratch buffer
-    need = int(lib.kvc_vote_workspace_bytes(shape, len(layers), desc))
-    ws = torch.empty(need, dtype=torch.uint8, device=k0.device) if need else None
-    status = lib.kvc_snapkv_vote_ws(shape, len(layers), desc, G, window,
-                                    ctypes.c_void_p(ws.data_ptr() if need else 0), need,
-                                    ctypes.c_void_p(_stream_ptr(k0.device)))
+    return shape, bytes(buf), out, G, keep, prepared
+
+
+def snapkv_votes(layers: Sequence[Tuple[torch.Tensor, torch.Tensor]], window: int,
+                 lse: Optional[Sequence[Optional[torch.Tensor]]] = None) -> List[torch.Tensor]:
+    """Observation-window votes on the tensor cores (tcgen05), one launch for every (keys, obs_queries) pair.
+
+    layers: [(keys [B,H,S,D], obs_queries [B,H*G,W,D]), ...] 16-bit CUDA tensors of one shape.
+    lse: optional per-layer ``[B, H*G, W]`` float32 log-sum-exp of the window queries' attention rows (what a
+        flash-attention forward returns): the kernel then reads K once instead of twice.
+    Returns votes [B,H,S-W] per layer (cache dtype):
+    ``softmax(Q K^T / sqrt(D), causal inside the window)[..., :S-W].sum over the window queries and the group``."""
+    if not layers:
+        return []
+    shape, recs, out, G, keep, _ = _vote_records(layers, window, lse)
+    k0 = layers[0][0]
+    status = load_library().kvc_snapkv_vote(shape, len(layers), recs, G, window, ctypes.c_void_p(_stream_ptr(k0.device)))
     _check(status, "kvc_snapkv_vote")
     return out
+
+
+def snapkv_vote_compress(kv: Sequence[Tuple[torch.Tensor, torch.Tensor]], plans, obs_queries: Sequence, window: int,
+                         lse: Optional[Sequence] = None, return_indices: bool = False, return_votes: bool = False):
+    """snapkv_lite in vote mode, ONE launch: per (layer, b, h) the vote, ``avg_pool1d``, top-k, sort and the K/V gather
+    (reference snapkv_lite.py:104-150 behind the q.K^T vote).  ``plans``: the snapkv plans with
+    ``SCORE_GIVEN_SCORE`` on the layers that vote; other layers follow their plan as in :func:`run_plans`.
+    Prefixes too long for the kernel's shared memory run as vote launch + select/gather launch instead."""
+    ps = plans if isinstance(plans, PlanSet) else PlanSet(plans)
+    voted = [li for li in ps.gather if ps.plans[li].score == P.SCORE_GIVEN_SCORE and ps.plans[li].k_sel > 0]
+    rest = [li for li in ps.gather if li not in voted]
+    out: List[Tuple[torch.Tensor, torch.Tensor]] = list(kv)
+    indices, votes_by_layer = {}, {}
+    if rest or ps.views:  # layers that do not vote (tail-only budgets): the ordinary path
+        other = [p if li not in voted else P.LayerPlan(P.KEEP, p.seq_len) for li, p in enumerate(ps.plans)]
+        res = run_plans(kv, other, return_indices=return_indices)
+        out, idx = res if return_indices else (res, {})
+        indices.update(idx)
+    if voted:
+        shape, recs, votes, G, keep, keys_used = _vote_records([(kv[li][0], obs_queries[li]) for li in voted], window,
+                                                               None if lse is None else [lse[li] for li in voted])
+        k0 = kv[voted[0]][0]
+        B, H, _, D = k0.shape
+        plan_buf = bytearray(_PLAN.size * len(voted))
+        io_buf = bytearray(_IO.size * len(voted))
+        lens = [ps.out_lens[li] for li in voted]
+        sizes = [B * H * c * D for c in lens for _ in (0, 1)]
+        flat = torch.empty((sum(sizes),), dtype=k0.dtype, device=k0.device)
+        chunks = flat.split_with_sizes(sizes)
+        for m, li in enumerate(voted):
+            keys, values = keys_used[m], kv[li][1]
+            _require_cuda(values, f"layer {li} values")
+            if values.shape != kv[li][0].shape or values.dtype != keys.dtype or values.device != keys.device:
+                raise ValueError(f"layer {li}: keys/values must be matching [B, H, S, D] tensors")
+            if not _rows_ok(values):
+                values = values.contiguous()
+                keep.append(values)
+            k_out, v_out = chunks[2 * m].view(B, H, lens[m], D), chunks[2 * m + 1].view(B, H, lens[m], D)
+            out[li] = (k_out, v_out)
+            idx_ptr = 0
+            if return_indices:
+                indices[li] = torch.empty((B, H, lens[m]), dtype=torch.int32, device=keys.device)
+                idx_ptr = indices[li].data_ptr()
+            plan_buf[m * _PLAN.size:(m + 1) * _PLAN.size] = ps.packed[li]
+            ks, vs = keys.stride(), values.stride()
+            _IO.pack_into(io_buf, m * _IO.size, keys.data_ptr(), values.data_ptr(), k_out.data_ptr(), v_out.data_ptr(),
+                          ks[0], ks[1], ks[2], vs[0], vs[1], vs[2], idx_ptr, 0, 0, 0, 0, 0)
+            votes_by_layer[li] = votes[m]
+        lib = load_library()
+        status = lib.kvc_snapkv_vote_compress(shape, len(voted), recs, bytes(plan_buf), bytes(io_buf), G, window,
+                                              ctypes.c_void_p(_stream_ptr(k0.device)))
+        if status == 3:  # prefix too long for the fused tail: votes, then select + gather with a workspace
+            status = lib.kvc_snapkv_vote(shape, len(voted), recs, G, window, ctypes.c_void_p(_stream_ptr(k0.device)))
+            _check(status, "kvc_snapkv_vote")
+            two = [p if li in voted else P.LayerPlan(P.KEEP, p.seq_len) for li, p in enumerate(ps.plans)]
+            res = run_plans(kv, two, given_scores=votes_by_layer, return_indices=return_indices)
+            res, idx = res if return_indices else (res, {})
+            for li in voted:
+                out[li] = res[li]
+            indices.update(idx)
+        else:
+            _check(status, "kvc_snapkv_vote_compress")
+    ret = [out]
+    if return_indices:
+        ret.append(indices)
+    if return_votes:
+        ret.append(votes_by_layer)
+    return ret[0] if len(ret) == 1 else tuple(ret)

@@ -39,5 +39,13 @@ def cached_plans(plan_fn: Callable, lens: Sequence[int], *args, skip_layers=()) 
     return hit
 
 
-def execute(layers, plans, given_indices=None):
-    return _engine.run_plans(layers, plans, given_indices=given_indices)
+def stored_norms(past_key_values):
+    """Per-layer key norms kept by the cache container (``KVSlabCache.key_norm_layers``), or ``None`` for plain
+    ``(K, V)`` lists and HF caches: with them a method ranks rows without reading K (reference e.g.
+    fix_size_l2.py:104-113 recomputes ``torch.norm`` on every call)."""
+    fn = getattr(past_key_values, "key_norm_layers", None)
+    return fn() if callable(fn) else None
+
+
+def execute(layers, plans, given_indices=None, norms=None):
+    return _engine.run_plans(layers, plans, given_indices=given_indices, norms=norms)

@@ -5,7 +5,7 @@ from typing import List, Tuple
 import torch
 
 from .. import _planner
-from ._common import as_layer_list, cached_plans, execute, seq_lens
+from ._common import as_layer_list, cached_plans, execute, seq_lens, stored_norms
 
 
 def adaptive_l2_compress(past_key_values, target_size: int = 512, soft_limit: int = 256, hard_limit: int = 1024,
@@ -19,7 +19,7 @@ def adaptive_l2_compress(past_key_values, target_size: int = 512, soft_limit: in
         return layers
     plans = cached_plans(_planner.plan_adaptive, seq_lens(layers), target_size, soft_limit, hard_limit, keep_ratio_min,
                          keep_ratio_max, skip_layers=skip_layers)
-    return execute(layers, plans)
+    return execute(layers, plans, norms=stored_norms(past_key_values))
 
 
 __all__ = ["adaptive_l2_compress"]

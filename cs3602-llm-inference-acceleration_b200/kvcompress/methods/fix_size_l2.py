@@ -5,7 +5,7 @@ from typing import List, Tuple
 import torch
 
 from .. import _planner
-from ._common import as_layer_list, cached_plans, execute, seq_lens
+from ._common import as_layer_list, cached_plans, execute, seq_lens, stored_norms
 
 
 def _random_indices(keys: torch.Tensor, zone_end: int, count: int) -> torch.Tensor:
@@ -34,7 +34,7 @@ def fix_size_l2_compress(past_key_values, fix_kv_size: int = 1024, keep_ratio: f
     if strategy == "random":
         given = {li: _random_indices(layers[li][0], p.sel_hi, p.k_sel)
                  for li, p in enumerate(plans) if p.score == _planner.SCORE_GIVEN_INDEX}
-    return execute(layers, plans, given_indices=given)
+    return execute(layers, plans, given_indices=given, norms=stored_norms(past_key_values))
 
 
 __all__ = ["fix_size_l2_compress"]

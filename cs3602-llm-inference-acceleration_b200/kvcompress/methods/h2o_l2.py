@@ -5,7 +5,7 @@ from typing import List, Tuple
 import torch
 
 from .. import _planner
-from ._common import as_layer_list, cached_plans, execute, seq_lens
+from ._common import as_layer_list, cached_plans, execute, seq_lens, stored_norms
 
 
 def h2o_l2_compress(past_key_values, start_size: int = 4, heavy_hitter_size: int = 64, recent_size: int = 444,
@@ -17,7 +17,7 @@ def h2o_l2_compress(past_key_values, start_size: int = 4, heavy_hitter_size: int
         return layers
     plans = cached_plans(_planner.plan_h2o, seq_lens(layers), start_size, heavy_hitter_size, recent_size,
                          skip_layers=skip_layers)
-    return execute(layers, plans)
+    return execute(layers, plans, norms=stored_norms(past_key_values))
 
 
 __all__ = ["h2o_l2_compress"]

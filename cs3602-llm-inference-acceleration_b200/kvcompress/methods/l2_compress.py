@@ -5,7 +5,7 @@ from typing import List, Tuple
 import torch
 
 from .. import _planner
-from ._common import as_layer_list, cached_plans, execute, seq_lens
+from ._common import as_layer_list, cached_plans, execute, seq_lens, stored_norms
 
 
 def l2_compress(past_key_values, keep_ratio: float = 1.0, prune_after: int = 1000,
@@ -17,7 +17,7 @@ def l2_compress(past_key_values, keep_ratio: float = 1.0, prune_after: int = 100
     """
     layers = as_layer_list(past_key_values)
     plans = cached_plans(_planner.plan_l2, seq_lens(layers), keep_ratio, prune_after, skip_layers=skip_layers)
-    return execute(layers, plans)
+    return execute(layers, plans, norms=stored_norms(past_key_values))
 
 
 __all__ = ["l2_compress"]

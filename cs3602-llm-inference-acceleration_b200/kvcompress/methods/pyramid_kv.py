@@ -5,7 +5,7 @@ from typing import List, Tuple
 import torch
 
 from .. import _planner
-from ._common import as_layer_list, cached_plans, execute, seq_lens
+from ._common import as_layer_list, cached_plans, execute, seq_lens, stored_norms
 
 
 def pyramid_kv_compress(past_key_values, base_size: int = 512, layer_decay: float = 0.9, min_size: int = 64,
@@ -18,7 +18,7 @@ def pyramid_kv_compress(past_key_values, base_size: int = 512, layer_decay: floa
         return layers
     plans = cached_plans(_planner.plan_pyramid, seq_lens(layers), base_size, layer_decay, min_size, profile,
                          skip_layers=skip_layers)
-    return execute(layers, plans)
+    return execute(layers, plans, norms=stored_norms(past_key_values))
 
 
 __all__ = ["pyramid_kv_compress"]

@@ -6,7 +6,7 @@ from typing import List, Optional, Sequence, Tuple
 import torch
 
 from .. import _engine, _planner
-from ._common import as_layer_list, cached_plans, execute, seq_lens
+from ._common import as_layer_list, cached_plans, execute, seq_lens, stored_norms
 
 
 def snapkv_lite_compress(past_key_values, observation_window: int = 32, keep_size: int = 512,
@@ -19,7 +19,9 @@ def snapkv_lite_compress(past_key_values, observation_window: int = 32, keep_siz
     default — the reference has no queries): one ``[B, H*G, W, D]`` tensor per
     layer holding the query states of the last ``W = observation_window`` positions.  The prefix score then
     becomes the SnapKV vote ``softmax(q.K^T / sqrt(D)).sum(window queries, group heads)`` computed on the tensor
-    cores (``_engine.snapkv_votes``), pooled and selected exactly as above."""
+    cores, pooled, selected and gathered exactly as above — all in ONE launch (``_engine.snapkv_vote_compress``).
+    ``obs_lse=`` (optional, with ``obs_queries``): per layer the ``[B, H*G, W]`` float32 log-sum-exp of those queries'
+    attention rows, as returned by a flash-attention forward; the kernel then reads K once instead of twice."""
     obs_queries: Optional[Sequence[Optional[torch.Tensor]]] = kwargs.get("obs_queries")
     layers = as_layer_list(past_key_values)
     if not layers:
@@ -27,16 +29,15 @@ def snapkv_lite_compress(past_key_values, observation_window: int = 32, keep_siz
     plans = cached_plans(_planner.plan_snapkv, seq_lens(layers), observation_window, keep_size, pooling_kernel,
                          skip_layers=skip_layers)
     if obs_queries is None:
-        return execute(layers, plans)
+        return execute(layers, plans, norms=stored_norms(past_key_values))
     if len(obs_queries) != len(layers):
         raise ValueError(f"obs_queries: {len(obs_queries)} entries for {len(layers)} layers")
     voted = [li for li, p in enumerate(plans) if p.kind == _planner.GATHER and p.k_sel > 0]
     for li in voted:
         if obs_queries[li] is None:
             raise ValueError(f"obs_queries[{li}] is missing for a layer that is compressed")
-    votes = _engine.snapkv_votes([(layers[li][0], obs_queries[li]) for li in voted], observation_window)
     plans = [replace(p, score=_planner.SCORE_GIVEN_SCORE) if li in voted else p for li, p in enumerate(plans)]
-    return _engine.run_plans(layers, plans, given_scores=dict(zip(voted, votes)))
+    return _engine.snapkv_vote_compress(layers, plans, obs_queries, observation_window, lse=kwargs.get("obs_lse"))
 
 
 __all__ = ["snapkv_lite_compress"]

@@ -17,7 +17,12 @@ Here every layer's K and V live in pre-allocated ``[B, H, capacity, D]`` slabs o
 
 ``compress_`` keeps exactly the rows the function of the same name keeps (same planner, same select,
 bit-identical norms) — ``tests/test_gpu_slab.py`` walks both loops side by side.  Any registered
-compress function also accepts a slab cache directly (``to_legacy_cache`` hands out views).
+compress function also accepts a slab cache directly (``to_legacy_cache`` hands out views) and then ranks
+rows from the stored norms (``key_norm_layers``) instead of re-reading K.
+
+``pinned=True`` keeps the slabs — K, V **and the norms** — in page-locked HOST memory (an offloaded cache),
+mapped into the GPU's address space: ``update`` writes new rows and their norms over PCIe, ``compress_`` and
+the compress functions read 2-4 bytes per row for scoring and pull only the rows that are kept.
 """
 
 from __future__ import annotations
@@ -75,23 +80,25 @@ class KVSlabCache:
     """Pre-allocated per-layer K/V slabs with in-place ``update`` (append) and ``compress_``."""
 
     def __init__(self, num_layers: int, batch: int, heads: int, head_dim: int, capacity: int,
-                 dtype: torch.dtype = torch.bfloat16, device="cuda"):
+                 dtype: torch.dtype = torch.bfloat16, device="cuda", pinned: bool = False):
         device = torch.device(device)
         if device.type != "cuda":
-            raise RuntimeError("KVSlabCache lives on a CUDA device (sm_100a): there is no CPU path")
+            raise RuntimeError("KVSlabCache runs on a CUDA device (sm_100a): there is no CPU path "
+                               "(pinned=True keeps the slabs in host memory, the kernels still run on `device`)")
         if dtype not in _engine.KVC_DTYPE:
             raise ValueError(f"dtype {dtype} is not supported (float32, float16, bfloat16)")
         row_bytes = head_dim * torch.empty((), dtype=dtype).element_size()
-        if row_bytes % 16 or row_bytes // 16 not in (8, 10, 12, 16, 20, 32):
-            raise ValueError(f"head_dim*itemsize = {row_bytes} B: the slab kernels cover rows of 128, 160, 192, 256, "
-                             "320 and 512 bytes")
+        if row_bytes % 16 or not 16 <= row_bytes <= 2048:
+            raise ValueError(f"head_dim*itemsize = {row_bytes} B: rows must be a multiple of 16 bytes, at most 2 KB")
         if device.index is None:
             device = torch.device("cuda", torch.cuda.current_device())
         self.num_layers, self.batch, self.heads, self.head_dim = num_layers, batch, heads, head_dim
-        self.capacity, self.dtype, self.device = capacity, dtype, device
-        self.k = torch.empty((num_layers, batch, heads, capacity, head_dim), dtype=dtype, device=device)
-        self.v = torch.empty((num_layers, batch, heads, capacity, head_dim), dtype=dtype, device=device)
-        self.n = torch.zeros((num_layers, batch, heads, capacity), dtype=dtype, device=device)
+        self.capacity, self.dtype, self.device, self.pinned = capacity, dtype, device, bool(pinned)
+        # `device` is where the kernels run; pinned slabs live in page-locked host memory mapped into its address space
+        alloc = dict(dtype=dtype, pin_memory=True) if pinned else dict(dtype=dtype, device=device)
+        self.k = torch.empty((num_layers, batch, heads, capacity, head_dim), **alloc)
+        self.v = torch.empty((num_layers, batch, heads, capacity, head_dim), **alloc)
+        self.n = torch.zeros((num_layers, batch, heads, capacity), **alloc)
         self.lengths: List[int] = [0] * num_layers
         self._shape = _engine._SHAPE.pack(batch, heads, head_dim, _engine.KVC_DTYPE[dtype], device.index)
         self._recs = [_SLAB.pack(self.k[l].data_ptr(), self.v[l].data_ptr(), self.n[l].data_ptr(),
@@ -106,9 +113,10 @@ class KVSlabCache:
 
     # ------------------------------------------------------------------ construction / views
     @classmethod
-    def from_legacy_cache(cls, past_key_values, capacity: Optional[int] = None) -> "KVSlabCache":
+    def from_legacy_cache(cls, past_key_values, capacity: Optional[int] = None, pinned: Optional[bool] = None,
+                          device=None) -> "KVSlabCache":
         """Build a slab cache holding a list of ``(K, V)`` pairs (``capacity`` rows per layer, default: twice the
-        longest layer)."""
+        longest layer).  ``pinned`` defaults to where the pairs live: host tensors give a pinned-host slab."""
         from .utils import normalize_kv_cache
 
         layers = list(normalize_kv_cache(past_key_values))
@@ -117,7 +125,11 @@ class KVSlabCache:
         k0 = layers[0][0]
         B, H, _, D = k0.shape
         longest = max(k.size(2) for k, _ in layers)
-        cache = cls(len(layers), B, H, D, capacity or max(2 * longest, 16), k0.dtype, k0.device)
+        if pinned is None:
+            pinned = k0.device.type == "cpu"
+        if device is None:
+            device = k0.device if k0.is_cuda else torch.device("cuda", torch.cuda.current_device())
+        cache = cls(len(layers), B, H, D, capacity or max(2 * longest, 16), k0.dtype, device, pinned=pinned)
         cache.append(layers)
         return cache
 
@@ -141,6 +153,16 @@ class KVSlabCache:
     def key_norms(self, layer_idx: int) -> torch.Tensor:
         """Stored ``||K||_2`` of the valid rows of one layer, ``[B, H, S]`` in the cache dtype."""
         return self.n[layer_idx, :, :, :self.lengths[layer_idx]]
+
+    def key_norm_layers(self) -> List[torch.Tensor]:
+        """Per-layer stored norms for the compress functions (``methods/_common.stored_norms``)."""
+        return [self.n[l, :, :, :self.lengths[l]] for l in range(self.num_layers)]
+
+    def _finish(self) -> None:
+        """Pinned slabs are read by the host with plain loads: finish the device work before returning, as the
+        reference's (synchronous) CPU path does."""
+        if self.pinned and not torch.cuda.is_current_stream_capturing():
+            torch.cuda.current_stream(self.device).synchronize()
 
     def as_hf_cache(self):
         """This slab as a ``transformers.Cache``: the model's attention layers call ``update`` (in-place append)
@@ -186,8 +208,10 @@ class KVSlabCache:
 
     # ------------------------------------------------------------------ append
     def _check_new(self, keys: torch.Tensor, values: torch.Tensor, layer_idx: int) -> None:
-        if not keys.is_cuda or keys.device != self.device or values.device != self.device:
-            raise RuntimeError(f"layer {layer_idx}: new rows must live on {self.device}")
+        for t in (keys, values):
+            if not (t.device == self.device or (t.device.type == "cpu" and t.is_pinned())):
+                raise RuntimeError(f"layer {layer_idx}: new rows must live on {self.device} or in pinned host memory "
+                                   f"(got {t.device}); there is no CPU path")
         if keys.dtype != self.dtype or values.dtype != self.dtype:
             raise ValueError(f"layer {layer_idx}: new rows must be {self.dtype}")
         if keys.dim() != 4 or keys.shape != values.shape or keys.size(0) != self.batch or keys.size(1) != self.heads \
@@ -214,9 +238,9 @@ class KVSlabCache:
                 self._check_new(keys, values, l)
                 want = None
             if not _engine._rows_ok(keys):
-                keys = keys.contiguous()
+                keys = keys.contiguous() if keys.is_cuda else keys.contiguous().pin_memory()
             if not _engine._rows_ok(values):
-                values = values.contiguous()
+                values = values.contiguous() if values.is_cuda else values.contiguous().pin_memory()
             keep.append((keys, values))
             ks, vs = keys.stride(), values.stride()
             slab_buf[m * _SLAB.size:(m + 1) * _SLAB.size] = self._recs[l]
@@ -227,6 +251,7 @@ class KVSlabCache:
         _engine._check(status, "kvc_slab_append")
         for l, keys, _ in items:
             self.lengths[l] += keys.size(2)
+        self._finish()
 
     def update(self, key_states: torch.Tensor, value_states: torch.Tensor, layer_idx: int, cache_kwargs=None):
         """HF ``Cache.update`` contract: append ``[B, H, T, D]`` rows to one layer, return that layer's full
@@ -254,6 +279,8 @@ class KVSlabCache:
         if status:
             _engine._check(status, "kvc_slab_append")
         self.lengths[layer_idx] = n + T
+        if self.pinned:
+            self._finish()
         return self._k_layers[layer_idx].narrow(2, 0, n + T), self._v_layers[layer_idx].narrow(2, 0, n + T)
 
     def append(self, new_rows) -> "KVSlabCache":
@@ -284,6 +311,7 @@ class KVSlabCache:
                                                         ctypes.c_void_p(_engine._stream_ptr(self.device)))
         _engine._check(status, "kvc_slab_append")
         self.lengths = [n + T for n in self.lengths]
+        self._finish()
         return self
 
     # ------------------------------------------------------------------ in-place compression
@@ -355,7 +383,9 @@ class KVSlabCache:
             for m, i in enumerate(ids):
                 gi = given_indices.get(i)
                 if gi is not None:
-                    if gi.dtype != torch.int32 or not gi.is_contiguous() or gi.device != self.device:
+                    if gi.device.type == "cpu" and self.pinned:
+                        gi = gi.contiguous().pin_memory()  # drawn on the host for a host-resident slab
+                    if gi.dtype != torch.int32 or not gi.is_contiguous() or (gi.device != self.device and not gi.is_pinned()):
                         raise ValueError(f"layer {i}: indices must be a contiguous int32 tensor on {self.device}")
                     keep.append(gi)
                     ptrs[m] = gi.data_ptr()
@@ -371,6 +401,7 @@ class KVSlabCache:
         _engine._check(status, "kvc_slab_compress")
         for i, c in zip(ids, out_lens):
             self.lengths[i] = c
+        self._finish()
         return (self, indices) if return_indices else self
 
 

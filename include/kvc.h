@@ -32,6 +32,8 @@
  * "Device pointer" includes page-locked host memory mapped into the device's address
  * space (cudaHostAlloc / cudaHostRegister under UVA): an offloaded cache is then read
  * and written in place over PCIe, each needed row crossing the link once per read.
+ * Every entry point runs on shape->device and restores the calling thread's current CUDA
+ * device before it returns.  The library reads no environment variable.
  */
 #ifndef KVC_H_
 #define KVC_H_
@@ -42,7 +44,7 @@
 extern "C" {
 #endif
 
-#define KVC_ABI_VERSION 4
+#define KVC_ABI_VERSION 5
 
 typedef enum kvc_status {
     KVC_OK = 0,
@@ -90,8 +92,15 @@ typedef struct kvc_layer_io {
     int64_t k_stride_b, k_stride_h, k_stride_s; /* elements      */
     int64_t v_stride_b, v_stride_h, v_stride_s; /* elements      */
     int32_t* idx_out;      /* optional [B,H,C] kept absolute row indices, ascending; may be NULL */
-    const int32_t* idx_in; /* GIVEN_INDEX only: [B,H,k_sel] ascending absolute rows inside the region */
+    const int32_t* idx_in; /* GIVEN_INDEX only: [B,H,k_sel] ascending absolute rows inside the region (rows outside
+                              [0, seq_len) are clamped into the layer, never dereferenced) */
     const void* score_in;  /* GIVEN_SCORE only: [B,H,sel_hi-sel_lo] scores of the region's rows, cache dtype, dense */
+    /* Optional stored key norms (L2_LOW / L2_HIGH / SNAPKV_POOL): norms_in[b,h,s] = what torch.norm(K, p=2, dim=-1)
+     * returns for row s, cache dtype, rows [0, seq_len) valid.  When given, the K rows of the selection region are NOT
+     * read for scoring (2-4 bytes per row instead of head_dim*e): a slab cache records the norms at append time
+     * (kvc_slab_append).  The kept set is the one the scan would have produced from the same norms.  NULL: scan K. */
+    const void* norms_in;
+    int64_t n_stride_b, n_stride_h; /* elements */
 } kvc_layer_io;
 
 typedef struct kvc_shape {
@@ -153,16 +162,22 @@ typedef struct kvc_vote_layer {
     int64_t q_stride_b, q_stride_h, q_stride_s; /* elements */
     int32_t seq_len;    /* S */
     int32_t reserved;
+    /* Optional [B, H*G, W] fp32, dense: lse[b,hq,i] = log(sum_j exp(q_i . k_j / sqrt(D))) over the keys query i sees
+     * (all S keys, causal inside the window) — the log-sum-exp an attention forward over these queries returns.  With
+     * it the kernel skips its first pass (the softmax denominators) and reads K once instead of twice.  NULL: two passes. */
+    const float* lse;
 } kvc_vote_layer;
 int kvc_snapkv_vote(const kvc_shape* shape, int32_t n_layers, const kvc_vote_layer* layers, int32_t group,
                     int32_t window, void* stream);
-/* With a device workspace of kvc_vote_workspace_bytes(...) bytes (256-byte aligned) the vote runs as persistent CTAs
- * that split every (b,h) along S and exchange their softmax row statistics through the workspace, so that the second
- * read of a key tile hits L2 instead of HBM.  Same votes up to fp32 summation order, reproducible run to run; without
- * a workspace (kvc_snapkv_vote) one CTA walks a whole sequence.  The workspace is scratch: nothing survives the call. */
-int64_t kvc_vote_workspace_bytes(const kvc_shape* shape, int32_t n_layers, const kvc_vote_layer* layers);
-int kvc_snapkv_vote_ws(const kvc_shape* shape, int32_t n_layers, const kvc_vote_layer* layers, int32_t group,
-                       int32_t window, void* workspace, int64_t workspace_bytes, void* stream);
+/* The vote, then snapkv_lite.py:104-150 in the SAME launch: the CTA that produced a (b,h)'s votes pools them
+ * (avg_pool1d(plans[l].pool_kernel)), keeps the plans[l].k_sel highest of the prefix [0, S - W) plus the last
+ * plans[l].tail rows, and gathers K and V into io[l].k_out / v_out.  plans[l]: sink 0, sel [0, S - W), score
+ * KVC_SCORE_GIVEN_SCORE; io[l].k_in / strides must be layers[l]'s keys; layers[l].votes_out is still written (the votes
+ * pass through it in the cache dtype).  KVC_ERR_TOO_LARGE when the prefix keys + kept indices exceed the shared
+ * memory of the key ring (~80K rows): run kvc_snapkv_vote + kvc_compress_layers_ws instead. */
+int kvc_snapkv_vote_compress(const kvc_shape* shape, int32_t n_layers, const kvc_vote_layer* layers,
+                             const kvc_layer_plan* plans, const kvc_layer_io* io, int32_t group, int32_t window,
+                             void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Slab cache: the container step on both sides of the compress call.
@@ -199,12 +214,14 @@ typedef struct kvc_slab_new_rows {
     int32_t n_new;     /* rows to append */
 } kvc_slab_new_rows;
 
-/* Append rows to n_layers slabs in one launch.  head_dim * sizeof(dtype) / 16 must be one of 8, 10, 16, 20, 32. */
+/* Append rows to n_layers slabs in one launch (any row width that is a multiple of 16 bytes, up to 2 KB). */
 int kvc_slab_append(const kvc_shape* shape, int32_t n_layers, const kvc_slab_layer* slabs,
                     const kvc_slab_new_rows* rows, void* stream);
 
 /* Compact n_layers slabs in place in one launch.  plans[l].seq_len = rows currently valid.
- * idx_out[l] (optional, may be NULL / hold NULLs): [B,H,C] kept absolute rows; idx_in[l]: GIVEN_INDEX rows. */
+ * idx_out[l] (optional, may be NULL / hold NULLs): [B,H,C] kept absolute rows; idx_in[l]: GIVEN_INDEX rows, which
+ * must be STRICTLY ASCENDING inside [sel_lo, sel_hi) per (b,h): kept rows only ever move towards row 0, which is what
+ * makes the compaction safe in place (values outside [0, seq_len) are clamped, never dereferenced). */
 int kvc_slab_compress(const kvc_shape* shape, int32_t n_layers, const kvc_layer_plan* plans,
                       const kvc_slab_layer* slabs, int32_t* const* idx_out, const int32_t* const* idx_in,
                       void* workspace, int64_t workspace_bytes, void* stream);

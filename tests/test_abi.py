@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_library_metadata_and_argument_checks():
     lib = _engine.load_library()
-    assert lib.kvc_abi_version() == 4
+    assert lib.kvc_abi_version() == 5
     assert b"sm_100a" in lib.kvc_build_info()
     assert lib.kvc_status_string(0) == b"ok"
     assert lib.kvc_launch_count() >= 0
@@ -38,7 +38,7 @@ def test_library_metadata_and_argument_checks():
     assert lib.kvc_compress_layers(None, 1, None, None, None) == 1
     shape = _engine._SHAPE.pack(1, 1, 12, 2, 0)  # D=12 bf16 -> 24-byte rows: not 16-byte aligned
     plan = _engine._PLAN.pack(10, 1, 0, 0, 0, 1, 0, 1)
-    io = _engine._IO.pack(16, 16, 16, 16, 120, 120, 12, 120, 120, 12, 0, 0, 0)
+    io = _engine._IO.pack(16, 16, 16, 16, 120, 120, 12, 120, 120, 12, 0, 0, 0, 0, 0, 0)
     assert lib.kvc_compress_layers(shape, 1, plan, io, None) == 2
     shape = _engine._SHAPE.pack(1, 1, 16, 2, 0)
     bad_plan = _engine._PLAN.pack(10, 1, 0, 20, 3, 1, 1, 1)  # sel_hi > seq_len
@@ -46,28 +46,30 @@ def test_library_metadata_and_argument_checks():
 
 
 def test_structs_match_header_sizes():
-    assert _engine._PLAN.size == 32 and _engine._IO.size == 104 and _engine._SHAPE.size == 20
+    assert _engine._PLAN.size == 32 and _engine._IO.size == 128 and _engine._SHAPE.size == 20
 
 
-def test_vote_workspace_sizing_is_opt_in_and_grows_with_the_sequence(monkeypatch):
-    """kvc_vote_workspace_bytes is pure host arithmetic: 0 unless the split-sequence form is asked for, then one
-    1 KB row-statistics record per (unit, slice) plus per-unit counters and final rows."""
+def test_library_ignores_the_environment(monkeypatch):
+    """The product build reads no environment variable (launch-shape overrides and stage isolation exist only in a
+    -DKVC_LAB build): the planner's answers do not move when the old knobs are set."""
     lib = _engine.load_library()
+    shape = _engine._SHAPE.pack(2, 8, 128, 2, 0)
+    plan = _engine._PLAN.pack(200000, 4, 4, 199000, 64, 444, 1, 1)
+    before = int(lib.kvc_workspace_bytes(shape, 1, plan))
+    for name in ("KVC_TMA_NT", "KVC_TMA_CTAS", "KVC_TMA_NSW", "KVC_TMA_UPC", "KVC_VOTE_DEBUG", "KVC_FORCE_LDG"):
+        monkeypatch.setenv(name, "1")
+    assert int(lib.kvc_workspace_bytes(shape, 1, plan)) == before > 0
+    text = open(_engine.library_path(), "rb").read()
+    assert b"KVC_VOTE_DEBUG" not in text and b"KVC_TMA_NT" not in text
 
-    def need(B, H, D, S, n_layers=2):
-        shape = _engine._SHAPE.pack(B, H, D, 2, 0)
-        layer = _engine._VOTE.pack(16, 16, 16, H * S * D, S * D, D, 4 * H * 32 * D, 32 * D, D, S, 0)
-        return int(lib.kvc_vote_workspace_bytes(shape, n_layers, layer * n_layers))
 
-    monkeypatch.delenv("KVC_VOTE_SPLIT", raising=False)
-    assert need(2, 8, 128, 32768) == 0
-    monkeypatch.setenv("KVC_VOTE_SPLIT", "1")
-    monkeypatch.setenv("KVC_VOTE_TS", "8")
-    small, big = need(2, 8, 128, 4096), need(2, 8, 128, 32768)
-    units = 2 * 8 * 2
-    assert small >= units * (4096 // 128 // 8) * 1024 and big >= units * (32768 // 128 // 8) * 1024
-    assert small < big and big % 256 == 0
-    assert need(2, 8, 96, 4096) == 0                       # head_dim 96: no vote kernel for that row width
+def test_vote_argument_checks():
+    lib = _engine.load_library()
     shape32 = _engine._SHAPE.pack(2, 8, 128, 0, 0)        # fp32 caches: the vote runs on 16-bit data only
-    layer = _engine._VOTE.pack(16, 16, 16, 1, 1, 128, 1, 1, 128, 4096, 0)
-    assert lib.kvc_vote_workspace_bytes(shape32, 1, layer) == 0
+    layer = _engine._VOTE.pack(16, 16, 16, 1, 1, 128, 1, 1, 128, 4096, 0, 0)
+    assert lib.kvc_snapkv_vote(shape32, 1, layer, 4, 32, None) == 2
+    shape96 = _engine._SHAPE.pack(2, 8, 96, 2, 0)         # head_dim 96: no vote kernel for that row width
+    assert lib.kvc_snapkv_vote(shape96, 1, layer, 4, 32, None) == 2
+    shape = _engine._SHAPE.pack(2, 8, 128, 2, 0)
+    assert lib.kvc_snapkv_vote(shape, 1, layer, 8, 32, None) == 2   # 256 query rows > one MMA
+    assert lib.kvc_snapkv_vote(shape, 1, None, 4, 32, None) == 1

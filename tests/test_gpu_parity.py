@@ -206,10 +206,20 @@ def test_errors():
     kv = [(torch.randn(1, 2, 2000, 16, device="cuda"), torch.randn(1, 2, 2000, 16, device="cuda"))]
     with pytest.raises(ValueError, match="Unknown strategy: nope"):
         kvcompress.fix_size_l2_compress(kv, fix_kv_size=512, strategy="nope", skip_layers=[])
-    # fp32 region beyond the on-chip score buffer is reported, not silently mis-handled
-    big = [(torch.zeros(1, 1, 70000, 16, device="cuda"), torch.zeros(1, 1, 70000, 16, device="cuda"))]
-    with pytest.raises(ValueError, match="too large"):
-        kvcompress.h2o_l2_compress(big)
+
+
+def test_any_row_width_takes_the_workspace_beyond_shared_memory():
+    """Row widths without a compiled kernel run the generic-width instantiation of the SAME kernel, so they get
+    the workspace path too: an fp32 region beyond the on-chip key buffer at head_dim 16 (round 1: an error)."""
+    S = 70000
+    k = torch.zeros(1, 1, S, 16, device="cuda")
+    k[0, 0, 1000:1064] = -1e-3      # 64 rows with the only non-zero norms: never kept by keep-lowest
+    v = torch.arange(S, device="cuda", dtype=torch.float32).view(1, 1, S, 1).expand(1, 1, S, 16).contiguous()
+    out = kvcompress.h2o_l2_compress([(k, v)])
+    kept = out[0][1][0, 0, :, 0].long()
+    # all-zero norms tie: lowest indices win -> sinks 0..3, heavy hitters 4..67, the last 444 rows
+    want = torch.cat([torch.arange(0, 68, device="cuda"), torch.arange(S - 444, S, device="cuda")])
+    assert torch.equal(kept, want)
 
 
 # ----------------------------------------------------------------------------------------------
@@ -355,10 +365,11 @@ def test_pinned_host_cache_matches_device_cache(method, kwargs):
 
 
 # ----------------------------------------------------------------------------------------------
-# The golden cases use small head dims (rows of 32-64 B -> the LDG form).  The same presets at the
-# PRODUCT row widths (the TMA form: 128/160/192/256/320/512-byte rows) against the golden-pinned oracle.
+# The golden cases use small head dims (rows of 32-64 B -> the generic-width kernel).  The same presets at the
+# PRODUCT row widths (compile-time widths: 128/160/192/256/320/512-byte rows) and at a few odd ones (bf16 D=72 / 40,
+# fp32 D=100: 144 / 80 / 400-byte rows, generic width) against the golden-pinned oracle.
 WIDTHS = [("bf16", 64), ("bf16", 80), ("bf16", 96), ("bf16", 128), ("bf16", 256), ("f16", 80), ("f32", 32),
-          ("f32", 48), ("f32", 80), ("f32", 128)]
+          ("f32", 48), ("f32", 80), ("f32", 128), ("bf16", 72), ("bf16", 40), ("f32", 100)]
 WIDE_PRESETS = [
     ("streaming", "streaming_llm", dict(start_size=4, recent_size=508)),
     ("h2o", "h2o_l2", dict(start_size=4, heavy_hitter_size=64, recent_size=444, skip_layers=[1])),
@@ -402,7 +413,9 @@ def test_oracle_parity_at_product_row_widths(name, method, kwargs, dtype, D, sty
         if dtype == "f32":
             assert info["identical_heads"] == info["heads"], (case["name"], li, info)
         else:
-            assert info["identical_heads"] >= 0.5 * info["heads"], (case["name"], li, info)  # validity is the rule; rounding-boundary flips are rare
+            # validity is the rule; a head differs from the oracle only when a norm sits on a rounding boundary of
+            # the 16-bit dtype (the oracle sums in a different order): rare, never systematic
+            assert info["identical_heads"] >= 0.9 * info["heads"], (case["name"], li, info)
 
 
 # ----------------------------------------------------------------------------------------------

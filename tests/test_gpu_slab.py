@@ -172,3 +172,89 @@ def test_captured_decode_step_replays_append_and_compress():
     with pytest.raises(ValueError, match="steady"):
         KVSlabCache.from_legacy_cache([(k[:, :, :40], v[:, :, :40]) for k, v in prefill], capacity=cap + 8) \
             .capture_step("h2o_l2", skip_layers=[], **kw)
+
+
+# ----------------------------------------------------------------------------------------------
+# Stored norms: functions called on a slab cache rank rows from the norms recorded at append time, and a slab in
+# pinned HOST memory (offloaded cache) gives the same bytes as the device slab and as the plain (K, V) functions.
+STORED = [
+    ("fix_size_l2", dict(fix_kv_size=128, keep_ratio=0.2, skip_layers=[0]), "bf16", 80),
+    ("fix_size_l2", dict(fix_kv_size=128, keep_ratio=0.3, strategy="keep_high", skip_layers=[]), "f32", 128),
+    ("h2o_l2", dict(start_size=4, heavy_hitter_size=32, recent_size=92), "bf16", 128),
+    ("snapkv_lite", dict(observation_window=16, keep_size=128, pooling_kernel=5), "bf16", 80),
+    ("snapkv_lite", dict(observation_window=16, keep_size=128, pooling_kernel=4), "f16", 72),
+    ("pyramid_kv", dict(base_size=128, layer_decay=0.8, min_size=32), "bf16", 128),
+    ("adaptive_l2", dict(target_size=128, soft_limit=64, hard_limit=300), "bf16", 80),
+    ("l2_compress", dict(keep_ratio=0.7, prune_after=100, skip_layers=[1]), "f32", 80),
+    ("streaming_llm", dict(start_size=4, recent_size=124), "bf16", 80),
+    ("fix_size_l2", dict(fix_kv_size=128, keep_ratio=0.25, strategy="random", skip_layers=[]), "bf16", 80),
+]
+
+
+@pytest.mark.parametrize("method,kwargs,dtype,D", STORED, ids=[f"{m}-{i}" for i, (m, *_r) in enumerate(STORED)])
+def test_pinned_slab_equals_device_slab_equals_functions(method, kwargs, dtype, D):
+    L, B, H, S = 3, 2, 3, 700
+    dt = DT[dtype]
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    kv = [rand_rows(B, H, S, D, dt, gen) for _ in range(L)]
+    fn = kvcompress.get_compress_fn(method)
+
+    def run(x):
+        torch.manual_seed(77)  # strategy="random" draws from the default generators
+        return fn(x, **kwargs)
+
+    want = run(kv)                                              # plain (K, V) list: the K scan
+    dev = KVSlabCache.from_legacy_cache(kv, capacity=S + 3)
+    host = KVSlabCache.from_legacy_cache(kv, capacity=S + 3, pinned=True)
+    assert host.pinned and host.k.is_pinned() and not host.k.is_cuda and host.n.is_pinned()
+    for l in range(L):
+        assert torch.equal(host.key_norms(l).cuda(), dev.key_norms(l))
+        assert torch.equal(host[l][0].cuda(), kv[l][0]) and torch.equal(host[l][1].cuda(), kv[l][1])
+    random = kwargs.get("strategy") == "random"
+    # out of place, scores from the stored norms (device slab, then the host-resident one: outputs land in pinned memory)
+    n0 = _engine.launch_count()
+    got_dev = run(dev)
+    assert _engine.launch_count() - n0 <= 1
+    got_host = run(host)
+    for li in range(L):
+        assert torch.equal(got_dev[li][0], want[li][0]) and torch.equal(got_dev[li][1], want[li][1]), (method, li)
+        if want[li][0] is not kv[li][0]:
+            assert not got_host[li][0].is_cuda and got_host[li][0].is_pinned()
+        if not random:   # the host slab draws its random rows from the CPU generator, like the reference on CPU tensors
+            assert torch.equal(got_host[li][0].cuda(), want[li][0]) and torch.equal(got_host[li][1].cuda(), want[li][1])
+        assert got_host[li][0].shape == want[li][0].shape
+    # in place
+    torch.manual_seed(77)
+    dev.compress_(method, **kwargs)
+    torch.manual_seed(77)
+    host.compress_(method, **kwargs)
+    assert dev.lengths == host.lengths == [k.size(2) for k, _ in want]
+    for li in range(L):
+        assert torch.equal(dev[li][0], want[li][0]) and torch.equal(dev[li][1], want[li][1])
+        if not random:
+            assert torch.equal(host[li][0].cuda(), want[li][0]) and torch.equal(host[li][1].cuda(), want[li][1])
+            assert torch.equal(host.key_norms(li).cuda(), dev.key_norms(li))
+    # the host slab keeps decoding: append a token from the device, compress again
+    new = [rand_rows(B, H, 1, D, dt, gen) for _ in range(L)]
+    dev.append(new)
+    host.append(new)
+    if not random:
+        for li in range(L):
+            assert torch.equal(host[li][0].cuda(), dev[li][0]) and torch.equal(host.key_norms(li).cuda(), dev.key_norms(li))
+
+
+def test_stored_norms_replace_the_scan_bytes():
+    """With stored norms no K row of the selection region is read for scoring: poison every K row that is NOT kept
+    after recording the norms — the function must still return the rows the scan would have kept."""
+    L, B, H, S, D = 2, 2, 2, 900, 80
+    gen = torch.Generator(device="cuda").manual_seed(9)
+    kv = [rand_rows(B, H, S, D, torch.bfloat16, gen) for _ in range(L)]
+    want, idx = _engine.run_plans(kv, plan_for("h2o_l2", [S] * L, dict(start_size=4, heavy_hitter_size=32, recent_size=92)),
+                                  return_indices=True)
+    slab = KVSlabCache.from_legacy_cache(kv, capacity=S)
+    for li in range(L):
+        kept = torch.zeros(B, H, S, dtype=torch.bool, device="cuda").scatter_(2, idx[li].long(), True)
+        slab.k[li][~kept] = float("nan")                       # the norms were recorded at append time
+    got = kvcompress.h2o_l2_compress(slab, start_size=4, heavy_hitter_size=32, recent_size=92)
+    for li in range(L):
+        assert torch.equal(got[li][0], want[li][0]) and torch.equal(got[li][1], want[li][1])

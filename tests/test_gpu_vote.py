@@ -58,43 +58,48 @@ def test_votes_match_torch_reference(B, H, G, W, S, D, dtype):
         assert torch.all(want.sum(-1) <= G * W + 1e-3)
 
 
-SPLIT_CASES = [
-    # B, H, G, W, S, D, dtype, key tiles per slice (0: the library's choice)
-    (2, 2, 4, 32, 1040, 128, torch.bfloat16, 1),   # 9 one-tile slices per unit; the last holds window keys only
-    (2, 3, 1, 32, 1500, 80, torch.bfloat16, 4),    # 12 tiles -> 3 slices, 32 live query rows
-    (1, 2, 2, 16, 2100, 64, torch.float16, 8),     # 17 tiles -> 3 slices of 6, 6, 5
-    (1, 1, 4, 32, 20000, 128, torch.bfloat16, 0),
-    (4, 8, 4, 32, 3000, 128, torch.bfloat16, 2),   # more slices than SMs: CTAs loop over tickets
-]
+def lse_reference(keys, queries, window):
+    """fp32 log-sum-exp of every window query's attention row (what a flash-attention forward returns)."""
+    B, H, S, D = keys.shape
+    G = queries.size(1) // H
+    P = S - window
+    k = keys.float().repeat_interleave(G, dim=1)
+    s = torch.matmul(queries.float(), k.transpose(-1, -2)) / math.sqrt(D)
+    pos_q = P + torch.arange(window, device=keys.device).view(1, 1, window, 1)
+    pos_k = torch.arange(S, device=keys.device).view(1, 1, 1, S)
+    return torch.logsumexp(s.masked_fill(pos_k > pos_q, float("-inf")), dim=-1)   # [B, H*G, W]
 
 
-@pytest.mark.parametrize("pend", [1, 2, 3])
-@pytest.mark.parametrize("B,H,G,W,S,D,dtype,ts", SPLIT_CASES, ids=[f"S{c[4]}D{c[5]}ts{c[7]}" for c in SPLIT_CASES])
-def test_split_sequence_votes_match_torch_reference(B, H, G, W, S, D, dtype, ts, pend, monkeypatch):
-    """Opt-in form (KVC_VOTE_SPLIT=1): persistent CTAs, every (b, h) split along S, softmax row statistics merged
-    through the workspace.  Votes match the fp32 reference, are reproducible run to run, and agree with the shipped
-    one-CTA-per-unit kernel (no workspace) within one spacing of the cache dtype."""
-    monkeypatch.setenv("KVC_VOTE_SPLIT", "1")
-    if ts:
-        monkeypatch.setenv("KVC_VOTE_TS", str(ts))
-    monkeypatch.setenv("KVC_VOTE_PEND", str(pend))
-    gen = torch.Generator(device="cuda").manual_seed(S)
-    keys = [torch.randn(B, H, S, D, generator=gen, device="cuda").to(dtype) for _ in range(3)]
-    qs = [(1.5 * torch.randn(B, H * G, W, D, generator=gen, device="cuda")).to(dtype) for _ in range(3)]
-    n0 = _engine.launch_count()
-    votes = _engine.snapkv_votes(list(zip(keys, qs)), W)
-    assert _engine.launch_count() - n0 == 1
-    again = _engine.snapkv_votes(list(zip(keys, qs)), W)
+@pytest.mark.parametrize("B,H,G,W,S,D,dtype", CASES[:4] + CASES[5:], ids=[f"B{c[0]}H{c[1]}G{c[2]}W{c[3]}S{c[4]}D{c[5]}" for c in CASES[:4] + CASES[5:]])
+def test_single_pass_votes_with_caller_lse(B, H, G, W, S, D, dtype):
+    """obs_lse: the kernel skips its first pass (the softmax denominators) and reads K once."""
+    gen = torch.Generator(device="cuda").manual_seed(7 * S + D)
+    keys = [torch.randn(B, H, S, D, generator=gen, device="cuda").to(dtype) for _ in range(2)]
+    qs = [(1.5 * torch.randn(B, H * G, W, D, generator=gen, device="cuda")).to(dtype) for _ in range(2)]
+    lse = [lse_reference(k, q, W) for k, q in zip(keys, qs)]
+    votes = _engine.snapkv_votes(list(zip(keys, qs)), W, lse=lse)
+    two_pass = _engine.snapkv_votes(list(zip(keys, qs)), W)
     ulp = 2.0 ** -8 if dtype == torch.bfloat16 else 2.0 ** -11
-    for k, q, v, v2 in zip(keys, qs, votes, again):
+    for k, q, v, u in zip(keys, qs, votes, two_pass):
         want = vote_reference(k, q, W)
         got = v.float()
         assert torch.all((got - want).abs() <= 2.5 * ulp * want + 1e-7), float(((got - want).abs() / (want + 1e-12)).max())
-        assert torch.equal(v, v2)
-    monkeypatch.setenv("KVC_VOTE_SPLIT", "0")
-    whole = _engine.snapkv_votes(list(zip(keys, qs)), W)
-    for v, u in zip(votes, whole):
-        assert torch.all((v.float() - u.float()).abs() <= 2.02 * ulp * u.float() + 1e-7)  # at most one spacing of the dtype
+        assert torch.all((got - u.float()).abs() <= 2.02 * ulp * u.float() + 1e-7)
+
+
+def test_votes_at_the_c4_shape():
+    """BASELINE configs[3] shape, one layer, one stream: S = 32768, 8 KV heads, 4 query heads per group, W = 32."""
+    B, H, G, W, S, D = 1, 8, 4, 32, 32768, 128
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    k = torch.randn(B, H, S, D, generator=gen, device="cuda").bfloat16()
+    q = (1.5 * torch.randn(B, H * G, W, D, generator=gen, device="cuda")).bfloat16()
+    v = _engine.snapkv_votes([(k, q)], W)[0]
+    want = vote_reference(k, q, W)
+    got = v.float()
+    ulp = 2.0 ** -8
+    assert torch.all((got - want).abs() <= 2.5 * ulp * want + 1e-7), float(((got - want).abs() / (want + 1e-12)).max())
+    one = _engine.snapkv_votes([(k, q)], W, lse=[lse_reference(k, q, W)])[0]
+    assert torch.all((one.float() - want).abs() <= 2.5 * ulp * want + 1e-7)
 
 
 def test_strided_keys_and_queries():
@@ -115,7 +120,7 @@ def test_snapkv_vote_mode_selects_the_highest_pooled_votes():
     n0 = _engine.launch_count()
     out = kvcompress.snapkv_lite_compress(kv, observation_window=W, keep_size=keep, pooling_kernel=pk,
                                           skip_layers=[0], obs_queries=qs)
-    assert _engine.launch_count() - n0 == 2  # one vote launch + one pool/select/gather launch for all layers
+    assert _engine.launch_count() - n0 == 1  # vote, pool, select and gather of every layer in ONE launch
     assert out[0][0] is kv[0][0]
     for li in (1, 2):
         k_in, v_in = kv[li]
@@ -131,12 +136,56 @@ def test_snapkv_vote_mode_selects_the_highest_pooled_votes():
         rows_ref = torch.gather(v_in, 2, want_idx.unsqueeze(-1).expand(-1, -1, -1, D))
         # identical up to ties at the threshold: compare the multiset of pooled scores of the kept rows
         got_rows = v_out[:, :, :keep - W]
-        match = (got_rows.unsqueeze(3) == v_in[:, :, :S - W].unsqueeze(2)[..., :1, :]).all(-1) if False else None
         same = (got_rows == rows_ref).all(-1).float().mean()
         assert same > 0.97, float(same)
         # out-of-place K rows correspond to the same positions as V rows
         k_ref = torch.gather(k_in, 2, want_idx.unsqueeze(-1).expand(-1, -1, -1, D))
         assert ((k_out[:, :, :keep - W] == k_ref).all(-1) == (got_rows == rows_ref).all(-1)).all()
+
+
+@pytest.mark.parametrize("B,H,G,W,S,D,keep,pk,dtype", [
+    (2, 2, 4, 32, 1500, 128, 256, 5, torch.bfloat16),
+    (1, 3, 1, 32, 5000, 80, 512, 5, torch.bfloat16),
+    (2, 2, 2, 16, 700, 64, 300, 3, torch.float16),
+    (1, 2, 4, 32, 300, 128, 512, 5, torch.bfloat16),     # keep_size > S: untouched
+    (1, 2, 4, 32, 600, 128, 512, 7, torch.bfloat16),
+    (1, 2, 4, 32, 560, 128, 512, 1, torch.bfloat16),     # no pooling
+    (1, 8, 4, 32, 32768, 128, 512, 5, torch.bfloat16),   # BASELINE configs[3] shape, one stream
+])
+def test_fused_vote_compress_equals_the_two_launch_form(B, H, G, W, S, D, keep, pk, dtype):
+    """kvc_snapkv_vote_compress == kvc_snapkv_vote followed by kvc_compress_layers(GIVEN_SCORE): same votes (bit for
+    bit), same kept rows, same K/V bytes; and the kept rows are the top-k of the pooled torch fp32 reference votes up
+    to ties at the threshold."""
+    from dataclasses import replace
+
+    from kvcompress import _planner
+
+    L = 2
+    gen = torch.Generator(device="cuda").manual_seed(S + keep)
+    kv = [(torch.randn(B, H, S, D, generator=gen, device="cuda").to(dtype),
+           torch.randn(B, H, S, D, generator=gen, device="cuda").to(dtype)) for _ in range(L)]
+    qs = [(2.0 * torch.randn(B, H * G, W, D, generator=gen, device="cuda")).to(dtype) for _ in range(L)]
+    plans = _planner.plan_snapkv([S] * L, W, keep, pk, [])
+    if plans[0].kind != _planner.GATHER:
+        out = kvcompress.snapkv_lite_compress(kv, observation_window=W, keep_size=keep, pooling_kernel=pk, obs_queries=qs)
+        assert all(a[0] is b[0] and a[1] is b[1] for a, b in zip(out, kv))
+        return
+    plans = [replace(p, score=_planner.SCORE_GIVEN_SCORE) for p in plans]
+    n0 = _engine.launch_count()
+    out, idx, votes = _engine.snapkv_vote_compress(kv, plans, qs, W, return_indices=True, return_votes=True)
+    assert _engine.launch_count() - n0 == 1
+    votes2 = _engine.snapkv_votes([(k, q) for (k, _), q in zip(kv, qs)], W)
+    out2, idx2 = _engine.run_plans(kv, plans, given_scores=dict(enumerate(votes2)), return_indices=True)
+    for li in range(L):
+        assert torch.equal(votes[li], votes2[li])
+        assert torch.equal(idx[li], idx2[li])
+        assert torch.equal(out[li][0], out2[li][0]) and torch.equal(out[li][1], out2[li][1])
+        ii = idx[li].long()
+        assert torch.equal(out[li][0], torch.gather(kv[li][0], 2, ii.unsqueeze(-1).expand(-1, -1, -1, D)))
+        assert torch.equal(out[li][1], torch.gather(kv[li][1], 2, ii.unsqueeze(-1).expand(-1, -1, -1, D)))
+        assert torch.all(ii[..., 1:] > ii[..., :-1]) and torch.equal(ii[..., -W:], torch.arange(S - W, S, device="cuda").expand(B, H, W))
+    api = kvcompress.snapkv_lite_compress(kv, observation_window=W, keep_size=keep, pooling_kernel=pk, obs_queries=qs)
+    assert all(torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) for a, b in zip(api, out))
 
 
 def test_vote_errors():
