@@ -28,6 +28,8 @@ from .methods import (
     COMPRESS_METHODS,
 )
 from .slab_cache import KVSlabCache
+from .evaluate import evaluate_with_compression, evaluate_baseline, compare_methods
+from .benchmark import benchmark, measure_generation_metrics, run_benchmark_suite, print_benchmark_summary
 from .utils import (
     to_dynamic_cache,
     normalize_kv_cache,
@@ -42,6 +44,8 @@ __all__ = [
     "snapkv_lite_compress", "pyramid_kv_compress", "adaptive_l2_compress",
     "get_compress_fn", "list_methods", "register_method", "COMPRESS_METHODS",
     "to_dynamic_cache", "normalize_kv_cache", "get_cache_size_mb", "get_cache_info", "get_seq_len",
+    "evaluate_with_compression", "evaluate_baseline", "compare_methods",
+    "benchmark", "measure_generation_metrics", "run_benchmark_suite", "print_benchmark_summary",
     "KVSlabCache",
 ]
 

@@ -97,9 +97,35 @@ def run_benchmark_suite(model, tokenizer=None, text: str = "", methods_config: L
         res = benchmark(model, tokenizer, text, compress_fn=config.get("compress_fn"), compress_kwargs=config.get("kwargs", {}),
                         max_new_tokens=max_new_tokens, eval_tokens=eval_tokens, skip_layers=skip_layers, device=device,
                         **extra)
-        res["name"] = config.get("name", "unknown")
+        res["name"] = res["method"] = config.get("name", "unknown")
         results.append(res)
     return results
 
 
-__all__ = ["measure_generation_metrics", "benchmark", "run_benchmark_suite"]
+def print_benchmark_summary(results: List[Dict[str, float]]) -> None:
+    """Table of ``run_benchmark_suite`` results and each method's change against the baseline row (the entry named
+    "baseline", else the first) — reference benchmark.py:293-350."""
+    cols = (("ttft", "TTFT(s)", "{:>10.4f}"), ("tpot", "TPOT(s)", "{:>10.4f}"), ("throughput", "Thruput", "{:>10.2f}"),
+            ("perplexity", "PPL", "{:>10.2f}"), ("accuracy", "Acc", "{:>10.2%}"), ("final_cache_size", "Cache", "{:>8}"))
+    rule = "=" * 90
+    print("\n" + rule + "\nBENCHMARK SUMMARY\n" + rule)
+    print(f"{'Method':<20} " + " ".join(f"{title:>{8 if key == 'final_cache_size' else 10}}" for key, title, _ in cols))
+    print("-" * 90)
+    label = lambda r: str(r.get("method", r.get("name", "unknown")))
+    for r in results:
+        print(f"{label(r)[:20]:<20} " + " ".join(fmt.format(r[key]) for key, _, fmt in cols))
+    print(rule)
+    base = next((r for r in results if label(r) == "baseline"), results[0] if results else None)
+    if base is None or len(results) < 2:
+        return
+    print("\nAgainst " + label(base) + " (throughput: higher is better; TPOT, PPL: lower is better):")
+    for r in results:
+        if r is base:
+            continue
+        thr = (r["throughput"] / base["throughput"] - 1) * 100 if base["throughput"] > 0 else 0.0
+        tpot = (1 - r["tpot"] / base["tpot"]) * 100 if base["tpot"] > 0 else 0.0
+        ppl = (r["perplexity"] / base["perplexity"] - 1) * 100 if base["perplexity"] > 0 else 0.0
+        print(f"  {label(r)[:20]:<20} throughput {thr:+.1f}%   TPOT {tpot:+.1f}% faster   PPL {ppl:+.1f}%")
+
+
+__all__ = ["measure_generation_metrics", "benchmark", "run_benchmark_suite", "print_benchmark_summary"]

@@ -147,4 +147,28 @@ def evaluate_with_compression(model, tokenizer=None, text: str = "", compress_fn
     return result
 
 
-__all__ = ["evaluate_with_compression", "new_slab_for_model", "method_name_of"]
+def evaluate_baseline(model, tokenizer=None, text: str = "", max_tokens: int = 3000,
+                      device: Optional[torch.device] = None, show_progress: bool = False, **extra) -> Dict[str, float]:
+    """The same loop with no compression (reference evaluate.py:229-259)."""
+    return evaluate_with_compression(model=model, tokenizer=tokenizer, text=text, compress_fn=None, max_tokens=max_tokens,
+                                     device=device, show_progress=show_progress, **extra)
+
+
+def compare_methods(model, tokenizer=None, text: str = "", methods_config: List[Dict] = (), max_tokens: int = 3000,
+                    skip_layers: List[int] = [0, 1], device: Optional[torch.device] = None, **extra) -> List[Dict[str, float]]:
+    """One evaluation per ``{"name", "compress_fn", "kwargs"}`` entry; every result carries ``method`` and ``config``
+    (reference evaluate.py:262-323)."""
+    results = []
+    for entry in methods_config:
+        label, kwargs = entry.get("name", "unknown"), entry.get("kwargs", {})
+        print(f"\nEvaluating {label}...")
+        res = evaluate_with_compression(model=model, tokenizer=tokenizer, text=text, compress_fn=entry.get("compress_fn"),
+                                        compress_kwargs=kwargs, max_tokens=max_tokens, skip_layers=skip_layers,
+                                        device=device, show_progress=extra.pop("show_progress", True), **extra)
+        res["method"], res["config"] = label, kwargs
+        results.append(res)
+        print(f"  PPL: {res['perplexity']:.2f}\n  Accuracy: {res['accuracy']:.2%}\n  Final cache size: {res['final_cache_size']}")
+    return results
+
+
+__all__ = ["evaluate_with_compression", "evaluate_baseline", "compare_methods", "new_slab_for_model", "method_name_of"]

@@ -155,3 +155,46 @@ def test_slab_cache_planner_table_matches_function_signatures():
     assert (moved[2].kind, moved[2].tail) == (P.GATHER, 10)  # x[:, :, -0:] is the whole tensor
     with pytest.raises(RuntimeError, match="no CPU path"):
         slab_cache.KVSlabCache(1, 1, 1, 80, 16, device="cpu")
+
+
+def test_integration_route2_snippet_registers_into_a_reference_style_registry(monkeypatch):
+    """INTEGRATION.md route 2, executed as written: the fenced block a maintainer pastes into the reference's
+    methods/__init__.py must import the package under a private name (relative imports included) and register the
+    eight functions; with a bad KVCOMPRESS_B200 it must fall through silently."""
+    import os
+    import re
+    import sys
+
+    root = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    block = re.search(r"```python\n(try:\s+# B200 fast path.*?)```", text, flags=re.S).group(1)
+    registry = {}
+    scope = {"register_method": lambda name, fn: registry.__setitem__(name, fn)}
+    monkeypatch.setenv("KVCOMPRESS_B200", os.path.join(root, "cs3602-llm-inference-acceleration_b200"))
+    monkeypatch.delitem(sys.modules, "kvcompress_b200", raising=False)
+    exec(block, scope)
+    assert sorted(registry) == sorted(["l2_compress", "fix_size_l2", "streaming_llm", "h2o_l2", "snapkv_lite",
+                                       "pyramid_kv", "adaptive_l2", "recent_only"])
+    assert registry["h2o_l2"].__module__.startswith("kvcompress_b200.")
+    sys.modules.pop("kvcompress_b200", None)
+    for name in [m for m in sys.modules if m.startswith("kvcompress_b200.")]:
+        sys.modules.pop(name, None)
+    registry.clear()
+    monkeypatch.setenv("KVCOMPRESS_B200", "/nonexistent")
+    exec(block, scope)            # FileNotFoundError is an OSError: swallowed, registry untouched
+    assert registry == {}
+    monkeypatch.delenv("KVCOMPRESS_B200")
+    exec(block, scope)            # KeyError: swallowed
+    assert registry == {}
+
+
+def test_route1_exports_the_reference_top_level_surface():
+    """Everything `from kvcompress import ...` offers in the reference (kvcompress/__init__.py:33-97)."""
+    import kvcompress
+
+    for name in ("l2_compress", "fix_size_l2_compress", "streaming_llm_compress", "get_compress_fn", "list_methods",
+                 "register_method", "COMPRESS_METHODS", "evaluate_with_compression", "evaluate_baseline",
+                 "compare_methods", "benchmark", "measure_generation_metrics", "run_benchmark_suite",
+                 "print_benchmark_summary", "to_dynamic_cache", "normalize_kv_cache", "get_cache_size_mb",
+                 "get_cache_info", "get_seq_len"):
+        assert hasattr(kvcompress, name) and name in kvcompress.__all__, name

@@ -142,8 +142,8 @@ def test_slab_errors():
         slab.update(k[:, :, :4].cpu(), k[:, :, :4].cpu(), 0)
     with pytest.raises(ValueError, match="Unknown method"):
         slab.compress_("nope")
-    with pytest.raises(ValueError, match="cover rows of"):
-        KVSlabCache(1, 1, 2, 24, 32, torch.bfloat16)
+    with pytest.raises(ValueError, match="multiple of 16 bytes"):
+        KVSlabCache(1, 1, 2, 12, 32, torch.bfloat16)       # 24-byte rows
     with pytest.raises(RuntimeError, match="no CPU path"):
         KVSlabCache(1, 1, 2, 80, 32, torch.bfloat16, device="cpu")
 
