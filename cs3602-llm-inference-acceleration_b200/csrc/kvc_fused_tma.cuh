@@ -162,7 +162,18 @@ __global__ void __launch_bounds__(NT, MINB) kvc_fused_tma_kernel(const __grid_co
     const int cpr = CPR > 0 ? CPR : bd.cpr;
     const int RB = cpr * 16;  // row bytes
 
-    const LayerDev& L = bd.layers[blockIdx.y];
+    // Which unit this CTA owns.  CTAs start in blockIdx order (x fastest), so the mapping decides which addresses
+    // are in flight together: order 1 spreads concurrently resident CTAs over the layers (separate allocations),
+    // order 2 strides over the (batch, head) units of one layer.
+    int bx = blockIdx.x, by = blockIdx.y;
+    if (bd.order == 1) {
+        const unsigned lin = blockIdx.y * gridDim.x + blockIdx.x;
+        by = (int)(lin % gridDim.y);
+        bx = (int)(lin / gridDim.y);
+    } else if (bd.order == 2) {
+        bx = (int)(((unsigned long long)blockIdx.x * 389ull) % gridDim.x);  // 389 is prime: a permutation unless 389 | grid
+    }
+    const LayerDev& L = bd.layers[by];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     extern __shared__ __align__(128) unsigned char smem[];
@@ -192,11 +203,11 @@ __global__ void __launch_bounds__(NT, MINB) kvc_fused_tma_kernel(const __grid_co
     }
     // A CTA walks `upc` consecutive (batch, head) units (upc = 1 unless the lab build overrides it).
     const int n_units = bd.B * bd.H;
-    const int bh_end = min(n_units, ((int)blockIdx.x + 1) * bd.upc);
-    for (int bh = (int)blockIdx.x * bd.upc; bh < bh_end; ++bh) {
+    const int bh_end = min(n_units, (bx + 1) * bd.upc);
+    for (int bh = bx * bd.upc; bh < bh_end; ++bh) {
     const int b = bh / bd.H, h = bh - b * bd.H;
     if (bd.ws != nullptr) {  // selection too large for shared memory: keys / kept indices live in the workspace
-        char* unit = bd.ws + ((int64_t)blockIdx.y * n_units + bh) * bd.ws_unit;
+        char* unit = bd.ws + ((int64_t)by * n_units + bh) * bd.ws_unit;
         keys = reinterpret_cast<Key*>(unit);
         sidx = reinterpret_cast<int32_t*>(unit + bd.ws_keys);
     }
