@@ -249,7 +249,6 @@ __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __gri
     const uint32_t bar_tfull = bar_empty + 8 * RING;   // [4]        count = 1 (tcgen05.commit)
     const uint32_t bar_tempty = bar_tfull + 8 * 4;        // [4]        count = 128 (math threads)
     float* s_m = reinterpret_cast<float*>(smem + 512);
-    float* s_invl = reinterpret_cast<float*>(smem + 1024);
     float* s_part = reinterpret_cast<float*>(smem + 1536);  // [4 groups][2][128]
     const uint32_t bar_tail = smem_u32(smem + 5632);        // [18]  count = 1: the fused tail's staging slots
     unsigned char* s_q = smem + 6144;
@@ -361,8 +360,7 @@ __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __gri
                 const bool live = tid < rows_q;
                 float lse = 0.f;
                 if (live) lse = L.lse[((int64_t)b * bd.H * G + (int64_t)h * G + tid / W) * W + tid % W];
-                s_m[tid] = lse * 1.4426950408889634f;
-                s_invl[tid] = live ? 1.f : 0.f;
+                s_m[tid] = live ? lse * 1.4426950408889634f : INFINITY;
             }
         } else if (tid < 128) {
             // query row `tid`: four groups x F replicas, always in the same order
@@ -383,9 +381,10 @@ __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __gri
                     }
                 }
             }
+            // p / l = exp2(s*c - (m + log2 l)): the division folds into the exponent; rows that never vote (padding,
+            // or an empty softmax row) get +inf, i.e. exp2(-inf) = 0
             const bool live = tid < rows_q && l > 0.f;
-            s_m[tid] = live ? m : 0.f;
-            s_invl[tid] = live ? 1.f / l : 0.f;
+            s_m[tid] = live ? m + log2f(l) : INFINITY;
         }
         asm volatile("bar.sync 1, 512;" ::: "memory");
         // ---------------- pass 2: lane = key, columns = query rows
@@ -403,11 +402,10 @@ __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __gri
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) {
                         const float4 mm = *reinterpret_cast<const float4*>(s_m + cb + j);
-                        const float4 il = *reinterpret_cast<const float4*>(s_invl + cb + j);
-                        vote0 = fmaf(ex2(fmaf(__uint_as_float(v[j + 0]), c2, -mm.x)), il.x, vote0);
-                        vote1 = fmaf(ex2(fmaf(__uint_as_float(v[j + 1]), c2, -mm.y)), il.y, vote1);
-                        vote2 = fmaf(ex2(fmaf(__uint_as_float(v[j + 2]), c2, -mm.z)), il.z, vote2);
-                        vote3 = fmaf(ex2(fmaf(__uint_as_float(v[j + 3]), c2, -mm.w)), il.w, vote3);
+                        vote0 += ex2(fmaf(__uint_as_float(v[j + 0]), c2, -mm.x));
+                        vote1 += ex2(fmaf(__uint_as_float(v[j + 1]), c2, -mm.y));
+                        vote2 += ex2(fmaf(__uint_as_float(v[j + 2]), c2, -mm.z));
+                        vote3 += ex2(fmaf(__uint_as_float(v[j + 3]), c2, -mm.w));
                     }
                 }
             }

@@ -96,6 +96,27 @@ def load_library():
     return lib
 
 
+_fast = None
+_fast_tried = False
+_KIND_CODE = {P.KEEP: 0, P.VIEW: 1, P.GATHER: 2}
+
+
+def fast_binding():
+    """The compiled per-call binding (csrc/kvc_fast_binding.cpp -> kvcompress/_kvc_fast*.so) or None when it has not
+    been built.  It only replaces the per-layer pointer walk below with C++; the device library, the planner and
+    every error message stay where they are, so without it the same calls simply cost more host time."""
+    global _fast, _fast_tried
+    if not _fast_tried:
+        _fast_tried = True
+        try:
+            from . import _kvc_fast as mod
+
+            _fast = mod if mod.KVC_ABI_VERSION == KVC_ABI_VERSION else None
+        except ImportError:
+            _fast = None
+    return _fast
+
+
 def launch_count() -> int:
     """Kernels launched by the library so far in this process."""
     return int(load_library().kvc_launch_count())
@@ -148,7 +169,7 @@ class PlanSet:
     (method arguments, sequence lengths) and cached by the method wrappers: a decode loop calls the
     same plan every step, so the per-step host work is pointers and one allocation."""
 
-    __slots__ = ("plans", "gather", "views", "packed", "out_lens")
+    __slots__ = ("plans", "gather", "views", "packed", "out_lens", "_fast")
 
     def __init__(self, plans: Sequence[P.LayerPlan]):
         self.plans = list(plans)
@@ -157,6 +178,21 @@ class PlanSet:
         self.packed = {i: _PLAN.pack(p.seq_len, p.sink, p.sel_lo, p.sel_hi, p.k_sel, p.tail, p.score, p.pool_kernel)
                        for i, p in ((i, self.plans[i]) for i in self.gather)}
         self.out_lens = {i: self.plans[i].out_len for i in self.gather}
+        self._fast = None
+
+    def fast(self):
+        """This plan set inside the compiled binding (built on first use), or None."""
+        if self._fast is None:
+            mod = fast_binding()
+            if mod is None or not self.gather:
+                self._fast = False
+            else:
+                lib = load_library()
+                recs = [[_KIND_CODE[p.kind], p.seq_len, p.sink, p.sel_lo, p.sel_hi, p.k_sel, p.tail, p.score, p.pool_kernel]
+                        for p in self.plans]
+                self._fast = mod.FastPlans(recs, ctypes.cast(lib.kvc_compress_layers_ws, ctypes.c_void_p).value,
+                                           ctypes.cast(lib.kvc_workspace_bytes, ctypes.c_void_p).value)
+        return self._fast or None
 
     def __len__(self):
         return len(self.plans)
@@ -185,6 +221,14 @@ def run_plans(kv: Sequence[Tuple[torch.Tensor, torch.Tensor]], plans, given_indi
         instead of reading the K rows of the selection region (a :class:`KVSlabCache` records them at append time).
     """
     ps = plans if isinstance(plans, PlanSet) else PlanSet(plans)
+    if given_indices is None and given_scores is None and not return_indices and ps.gather and not ps.views:
+        # the common per-step call: the compiled binding walks the layers (None: not built, or a case it leaves to us)
+        fp = ps.fast()
+        first = kv[ps.gather[0]][0] if len(kv) == len(ps.plans) else None
+        if fp is not None and isinstance(first, torch.Tensor) and first.is_cuda:
+            done = fp.run(kv if type(kv) is list else list(kv), norms)   # launches on torch's current stream
+            if done is not None:
+                return done
     out: List[Tuple[torch.Tensor, torch.Tensor]] = list(kv)
     for li, n in ps.views:
         keys, values = kv[li][0], kv[li][1]

@@ -18,6 +18,12 @@ def as_layer_list(past_key_values) -> List[Tuple[torch.Tensor, torch.Tensor]]:
 
 
 def seq_lens(layers: Sequence[Tuple[torch.Tensor, torch.Tensor]]) -> List[int]:
+    fast = _engine.fast_binding()
+    if fast is not None and type(layers) is list:
+        try:
+            return fast.seq_lens(layers)
+        except (TypeError, IndexError):
+            pass
     return [layer[0].size(2) for layer in layers]
 
 

@@ -108,6 +108,13 @@ class KVSlabCache:
         self._k_layers = list(self.k.unbind(0))
         self._v_layers = list(self.v.unbind(0))
         self._lib = None
+        self._fast_update = None   # compiled per-layer update (csrc/kvc_fast_binding.cpp), device slabs only
+        if not pinned:
+            mod = _engine.fast_binding()
+            if mod is not None:
+                lib = _engine.load_library()
+                self._fast_update = mod.SlabFast(self._k_layers, self._v_layers, list(self.n.unbind(0)),
+                                                 ctypes.cast(lib.kvc_slab_append, ctypes.c_void_p).value).update
         self._ws = None
         self._launch_cache: Dict[int, tuple] = {}
 
@@ -256,7 +263,14 @@ class KVSlabCache:
     def update(self, key_states: torch.Tensor, value_states: torch.Tensor, layer_idx: int, cache_kwargs=None):
         """HF ``Cache.update`` contract: append ``[B, H, T, D]`` rows to one layer, return that layer's full
         ``(K, V)`` (views of the slab) — replaces the ``torch.cat`` of transformers ``cache_utils.py:119-120``."""
-        # hot path of the decode loop (called once per layer per token): checks and packing inlined
+        # hot path of the decode loop (called once per layer per token): the compiled binding validates, launches and
+        # returns the views; None means "a case for the checks below" (wrong shape, capacity, host rows, ...)
+        if self._fast_update is not None:
+            n = self.lengths[layer_idx]
+            done = self._fast_update(key_states, value_states, layer_idx, n)
+            if done is not None:
+                self.lengths[layer_idx] = n + key_states.shape[2]
+                return done
         if not (key_states.is_cuda and key_states.dtype is self.dtype and value_states.dtype is self.dtype
                 and key_states.device == self.device and value_states.device == self.device):
             self._check_new(key_states, value_states, layer_idx)

@@ -621,3 +621,55 @@ def test_evict_for_space_and_h2o_attention_manager_match_reference():
                                                 recent_size=c["recent_size"], skip_layers=c["skip_layers"])
         assert [k.size(2) for k, _ in out] == ref["lengths"], step
         assert [rows_of(v) for _, v in out] == ref["rows"], step
+
+
+# ----------------------------------------------------------------------------------------------
+# The compiled per-call binding (csrc/kvc_fast_binding.cpp) against the ctypes walk it replaces.
+def test_compiled_binding_takes_the_common_call_and_matches_the_python_walk():
+    assert _engine.fast_binding() is not None, "kvcompress/_kvc_fast*.so has not been built (g.build())"
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    kv = [(torch.randn(2, 4, 900, 80, generator=gen, device="cuda").bfloat16(),
+           torch.randn(2, 4, 900, 80, generator=gen, device="cuda").bfloat16()) for _ in range(5)]
+    for method, kwargs in [("h2o_l2", dict(start_size=4, heavy_hitter_size=64, recent_size=444, skip_layers=[1])),
+                           ("pyramid_kv", dict(base_size=512, layer_decay=0.7, min_size=64)),
+                           ("streaming_llm", dict(start_size=4, recent_size=508)),
+                           ("fix_size_l2", dict(fix_kv_size=512, keep_ratio=0.2, skip_layers=[0]))]:
+        plans = _engine.PlanSet(plan_for(method, [900] * 5, kwargs))
+        assert plans.fast() is not None
+        n0 = _engine.launch_count()
+        fast = plans.fast().run(kv, None)
+        assert fast is not None and _engine.launch_count() - n0 == 1
+        slow, _ = _engine.run_plans(kv, plans, return_indices=True)     # index output: the Python walk
+        api = kvcompress.get_compress_fn(method)(kv, **kwargs)
+        for li in range(5):
+            if plans[li].kind == P.KEEP:
+                assert fast[li] is kv[li] and api[li][0] is kv[li][0]
+            else:
+                assert torch.equal(fast[li][0], slow[li][0]) and torch.equal(fast[li][1], slow[li][1])
+                assert torch.equal(api[li][0], slow[li][0]) and torch.equal(api[li][1], slow[li][1])
+    # cases it leaves to the Python path: strided rows it cannot read in place, host tensors, wrong lengths
+    odd = [(k[..., :72], v[..., :72]) for k, v in kv]                  # row stride 160 B, rows 144 B: fine in place
+    plans = _engine.PlanSet(plan_for("streaming_llm", [900] * 5, dict(start_size=4, recent_size=508)))
+    got = plans.fast().run(odd, None)
+    assert got is not None and torch.equal(got[0][0], torch.cat([odd[0][0][:, :, :4], odd[0][0][:, :, -508:]], 2))
+    misaligned = [(k[..., 4:76], v[..., 4:76]) for k, v in kv]         # rows start 8 bytes into a 16-byte chunk
+    assert plans.fast().run(misaligned, None) is None
+    want = torch.cat([misaligned[0][0][:, :, :4], misaligned[0][0][:, :, -508:]], 2)
+    assert torch.equal(kvcompress.streaming_llm_compress(misaligned)[0][0], want)   # the Python path copies first
+    assert plans.fast().run([(k[:, :, :800], v[:, :, :800]) for k, v in kv], None) is None
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_calls_on_another_gpu_leave_the_current_device_alone():
+    """the library used to cudaSetDevice(shape->device) and leave it there."""
+    assert torch.cuda.current_device() == 0
+    kv = [(torch.randn(1, 2, 700, 80, device="cuda:1").bfloat16(), torch.randn(1, 2, 700, 80, device="cuda:1").bfloat16())]
+    out = kvcompress.h2o_l2_compress(kv)
+    idx_path, _ = _engine.run_plans(kv, plan_for("h2o_l2", [700], {}), return_indices=True)   # the ctypes walk
+    torch.cuda.synchronize(1)
+    assert torch.cuda.current_device() == 0
+    assert out[0][0].device == torch.device("cuda", 1) and torch.equal(out[0][0], idx_path[0][0])
+    assert torch.empty(1, device="cuda").device.index == 0
+    slab = kvcompress.KVSlabCache.from_legacy_cache(kv, capacity=800)
+    slab.compress_("h2o_l2")
+    assert torch.cuda.current_device() == 0 and slab.device.index == 1
