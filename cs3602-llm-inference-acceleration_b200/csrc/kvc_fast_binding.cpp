@@ -83,7 +83,8 @@ public:
     py::object run(py::list kv, py::object norms) {
         const size_t L = kinds_.size();
         if (!simple_ || (size_t)py::len(kv) != L) return py::none();
-        py::list out(kv);  // shallow copy: untouched layers stay the caller's own objects
+        // a real shallow copy (py::list(kv) would alias the caller's list): untouched layers stay the caller's own objects
+        py::list out = py::reinterpret_steal<py::list>(PyList_GetSlice(kv.ptr(), 0, (Py_ssize_t)L));
         const size_t n = gather_.size();
         if (n == 0) return std::move(out);
 

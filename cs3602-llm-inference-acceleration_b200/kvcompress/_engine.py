@@ -205,7 +205,8 @@ class PlanSet:
 
 
 def run_plans(kv: Sequence[Tuple[torch.Tensor, torch.Tensor]], plans, given_indices: Optional[dict] = None,
-              return_indices: bool = False, given_scores: Optional[dict] = None, norms: Optional[Sequence] = None):
+              return_indices: bool = False, given_scores: Optional[dict] = None, norms: Optional[Sequence] = None,
+              non_blocking: bool = False):
     """Apply per-layer plans (a list of ``LayerPlan`` or a cached :class:`PlanSet`) to a list of (K, V) pairs.
 
     KEEP layers keep their tensor objects, VIEW layers become ``x[:, :, -n:, :]`` views (both
@@ -219,6 +220,8 @@ def run_plans(kv: Sequence[Tuple[torch.Tensor, torch.Tensor]], plans, given_indi
     norms: per-layer stored key norms (``[B, H, >= S]``, cache dtype, last dim dense; ``None`` entries allowed) — what
         ``torch.norm(K, p=2, dim=-1)`` returns for the rows.  Layers that have them are ranked from 2-4 bytes per row
         instead of reading the K rows of the selection region (a :class:`KVSlabCache` records them at append time).
+    non_blocking: host-resident (pinned) caches only — do not synchronise before returning; the pinned outputs are
+        complete once the current stream has been synchronised.
     """
     ps = plans if isinstance(plans, PlanSet) else PlanSet(plans)
     if given_indices is None and given_scores is None and not return_indices and ps.gather and not ps.views:
@@ -357,9 +360,9 @@ def run_plans(kv: Sequence[Tuple[torch.Tensor, torch.Tensor]], plans, given_indi
         status = lib.kvc_compress_layers_ws(shape_rec, n, plan_bytes, bytes(io_buf), ws_ptr, ws_bytes,
                                             ctypes.c_void_p(_stream_ptr(run_device)))
         _check(status, "kvc_compress_layers")
-        if on_host:
-            # host tensors are read by the caller with plain loads: finish before returning,
-            # as the reference's (synchronous) CPU path does
+        if on_host and not non_blocking:
+            # host tensors are read by the caller with plain loads: finish before returning, as the reference's
+            # (synchronous) CPU path does; non_blocking=True leaves that to the caller (tensor.to(..., non_blocking=True))
             torch.cuda.current_stream(run_device).synchronize()
     if return_indices:
         return out, indices

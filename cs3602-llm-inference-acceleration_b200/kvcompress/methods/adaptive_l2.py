@@ -19,7 +19,8 @@ def adaptive_l2_compress(past_key_values, target_size: int = 512, soft_limit: in
         return layers
     plans = cached_plans(_planner.plan_adaptive, seq_lens(layers), target_size, soft_limit, hard_limit, keep_ratio_min,
                          keep_ratio_max, skip_layers=skip_layers)
-    return execute(layers, plans, norms=stored_norms(past_key_values))
+    return execute(layers, plans, norms=stored_norms(past_key_values),
+                   non_blocking=kwargs.get("non_blocking", False))
 
 
 __all__ = ["adaptive_l2_compress"]

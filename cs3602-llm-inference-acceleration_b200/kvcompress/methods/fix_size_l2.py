@@ -34,7 +34,8 @@ def fix_size_l2_compress(past_key_values, fix_kv_size: int = 1024, keep_ratio: f
     if strategy == "random":
         given = {li: _random_indices(layers[li][0], p.sel_hi, p.k_sel)
                  for li, p in enumerate(plans) if p.score == _planner.SCORE_GIVEN_INDEX}
-    return execute(layers, plans, given_indices=given, norms=stored_norms(past_key_values))
+    return execute(layers, plans, given_indices=given, norms=stored_norms(past_key_values),
+                   non_blocking=kwargs.get("non_blocking", False))
 
 
 __all__ = ["fix_size_l2_compress"]

@@ -17,7 +17,8 @@ def h2o_l2_compress(past_key_values, start_size: int = 4, heavy_hitter_size: int
         return layers
     plans = cached_plans(_planner.plan_h2o, seq_lens(layers), start_size, heavy_hitter_size, recent_size,
                          skip_layers=skip_layers)
-    return execute(layers, plans, norms=stored_norms(past_key_values))
+    return execute(layers, plans, norms=stored_norms(past_key_values),
+                   non_blocking=kwargs.get("non_blocking", False))
 
 
 __all__ = ["h2o_l2_compress"]

@@ -18,7 +18,8 @@ def pyramid_kv_compress(past_key_values, base_size: int = 512, layer_decay: floa
         return layers
     plans = cached_plans(_planner.plan_pyramid, seq_lens(layers), base_size, layer_decay, min_size, profile,
                          skip_layers=skip_layers)
-    return execute(layers, plans, norms=stored_norms(past_key_values))
+    return execute(layers, plans, norms=stored_norms(past_key_values),
+                   non_blocking=kwargs.get("non_blocking", False))
 
 
 __all__ = ["pyramid_kv_compress"]

@@ -11,12 +11,16 @@ from ._common import as_layer_list, cached_plans, execute, seq_lens
 def streaming_llm_compress(past_key_values, start_size: int = 4, recent_size: int = 508,
                            skip_layers: List[int] = [], **kwargs) -> List[Tuple[torch.Tensor, torch.Tensor]]:
     """Keep tokens ``[0, start_size)`` and the last ``recent_size`` tokens of every layer longer than
-    ``start_size + recent_size``; one gather-compaction launch for the whole call."""
+    ``start_size + recent_size``; one gather-compaction launch for the whole call.
+
+    ``non_blocking=True`` (keyword extension of every compress function, host-resident caches only): return as soon as
+    the launch is queued instead of synchronising; the pinned output tensors are complete once the current CUDA stream
+    has been synchronised — the contract of ``tensor.to("cpu", non_blocking=True)``."""
     layers = as_layer_list(past_key_values)
     if not layers:
         return layers
     plans = cached_plans(_planner.plan_streaming, seq_lens(layers), start_size, recent_size, skip_layers=skip_layers)
-    return execute(layers, plans)
+    return execute(layers, plans, non_blocking=kwargs.get("non_blocking", False))
 
 
 def evict_for_space(past_key_values, num_coming: int, start_size: int = 4, recent_size: int = 508,

@@ -36,6 +36,25 @@ def shard_layers(n_layers: int, world: int, rank: int) -> List[int]:
     return list(range(lo, hi))
 
 
+def job_units(how: str, n_layers: int, n_blocks: int, world: int, rank: int, layer_group: int = 4):
+    """This rank's share of a GLOBAL compress job as a list of slabs ``(layer_ids, block_ids)``, a slab being what is
+    resident at one time.  The job is ``n_layers`` layers x ``n_blocks`` blocks of decode streams; every
+    (layer, block) pair is owned by exactly one rank, whichever way the job is cut:
+
+    ``how="batch"``  rank owns a contiguous range of stream blocks, all layers; one slab per block
+                     (reference: units are independent per (batch, head), h2o_l2.py:77,122-141);
+    ``how="layer"``  rank owns a contiguous range of layers (``shard_layers``), every block; one slab per
+                     ``layer_group`` layers.  Per-layer budgets (pyramid_kv.py:84-97) are a function of the GLOBAL
+                     layer index, so plans are built for all layers on every rank and indexed by ``layer_ids``."""
+    if how == "batch":
+        lo, hi = shard_range(n_blocks, world, rank)
+        return [(list(range(n_layers)), [blk]) for blk in range(lo, hi)]
+    if how == "layer":
+        mine = shard_layers(n_layers, world, rank)
+        return [(mine[i:i + layer_group], list(range(n_blocks))) for i in range(0, len(mine), layer_group)]
+    raise ValueError(f"unknown sharding {how!r}: 'batch' or 'layer'")
+
+
 def combine_stats(local: Dict[str, float]) -> Dict[str, float]:
     """After the timed region: MAX of times, SUM of bytes / checksums across ranks.
 

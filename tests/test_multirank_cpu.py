@@ -26,6 +26,23 @@ def test_shard_range_partitions_exactly():
         sharding.shard_range(4, 2, 2)
 
 
+def test_job_units_cover_every_layer_block_pair_once():
+    """bench.py's strong-scaling section: a global job of L layers x n_blocks stream blocks, cut by batch or by layer."""
+    L, n_blocks = 32, 8
+    for how in ("batch", "layer"):
+        for world in (1, 2, 4, 8):
+            seen = []
+            for rank in range(world):
+                units = sharding.job_units(how, L, n_blocks, world, rank)
+                assert len(units) == 8 // world          # slabs per rank: 8 / 4 / 2 / 1
+                for layer_ids, block_ids in units:
+                    assert (len(layer_ids), len(block_ids)) == ((L, 1) if how == "batch" else (4, n_blocks))
+                    seen += [(l, b) for l in layer_ids for b in block_ids]
+            assert sorted(seen) == [(l, b) for l in range(L) for b in range(n_blocks)]
+    with pytest.raises(ValueError):
+        sharding.job_units("heads", L, n_blocks, 2, 0)
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
@@ -51,6 +68,12 @@ def _worker(rank, world, port, q):
         out = kvcompress.recent_only_compress(mine, window_size=512, skip_layers=[0])
         full = kvcompress.recent_only_compress(kv, window_size=512, skip_layers=[0])
         assert all(torch.equal(o[0], f[0][3 * rank:3 * rank + 3]) for o, f in zip(out, full))
+        # a global job cut by batch and by layer: per-(layer, block) terms add up to the same total on any cut
+        term = lambda l, b: (l + 1) * 1000 + 7 * b
+        for how in ("batch", "layer"):
+            mine_sum = sum(term(l, b) for ls, bs in sharding.job_units(how, 8, 4, world, rank, layer_group=2) for l in ls for b in bs)
+            total = sharding.combine_stats({"checksum": float(mine_sum)})["checksum"]
+            assert total == float(sum(term(l, b) for l in range(8) for b in range(4)))
         local_bytes = P.algorithmic_bytes(plans, mine[0][0].size(0), 2, 16, 4)
         stats = sharding.combine_stats({"step_ms": 10.0 + rank, "bytes": float(local_bytes), "streams": 3.0})
         q.put((rank, stats, P.algorithmic_bytes(plans, 6, 2, 16, 4)))
