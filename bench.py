@@ -663,7 +663,9 @@ def strong_section(args, device, world, rank, barrier):
                 for (k, v) in buf[:len(units[0][0])]:
                     k.zero_(), v.zero_()
                 for plans in plans_all:
-                    _engine.run_plans(buf[:len(units[0][0])], [plans[l] for l in units[0][0]], return_indices=True)
+                    warm = _engine.PlanSet([plans[l] for l in units[0][0]])
+                    _engine.run_plans(buf[:len(units[0][0])], warm)
+                    _engine.run_plans(buf[:len(units[0][0])], warm, return_indices=True)
                 torch.cuda.synchronize()
             for layer_ids, block_ids in units:
                 kv = buf[:len(layer_ids)]
@@ -673,14 +675,16 @@ def strong_section(args, device, world, rank, barrier):
                                    7_000_000 + 1000 * l + bb, dt)
                 torch.cuda.synchronize()
                 a, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                results = []
+                sub = [_engine.PlanSet([plans[l] for l in layer_ids]) for plans in plans_all]
                 a.record()
-                for plans in plans_all:
-                    results.append(_engine.run_plans(kv, [plans[l] for l in layer_ids], return_indices=True))
+                for ps in sub:      # timed: exactly what the public functions launch (no index output)
+                    out_kv = _engine.run_plans(kv, ps)
+                    del out_kv
                 b2.record()
                 torch.cuda.synchronize()
                 my_ms += a.elapsed_time(b2)
                 slabs += 1
+                results = [_engine.run_plans(kv, ps, return_indices=True) for ps in sub]   # untimed: the kept rows
                 for ci, (_, idx) in enumerate(results):   # one term per (call, layer, block): independent of the cut
                     for j in range(len(block_ids)):
                         checksum += (ci + 1) * idx_checksum({layer_ids[i]: t[j * block_B:(j + 1) * block_B]
@@ -917,6 +921,14 @@ def run_e2e(cfg, B, kv, step_bytes, args, device, world, barrier):
 
     snq_s, snq_ranks = timed(snq_step)
 
+    def sndev_step():
+        # fetch-and-compress: the compressed cache lands on the GPU (decode continues there); nothing goes back
+        outs = [[fn(host_slab, output_device=device, **kw) for fn, kw in fns] for _ in range(n_slabs)]
+        torch.cuda.current_stream().synchronize()
+        return outs
+
+    sndev_s, sndev_ranks = timed(sndev_step)
+
     host_in = host_slab.to_legacy_cache()   # the same pinned rows as plain (K, V) views: no norms travel with them
 
     def zc_step():
@@ -949,8 +961,12 @@ def run_e2e(cfg, B, kv, step_bytes, args, device, world, barrier):
                      "(round 1's e2e)")),
     ]
     legs.sort(key=lambda x: x[0])
-    best = legs[0][1]
-    best["alternatives"] = [l[1] for l in legs[1:]]
+    best = legs[0][1]   # the headline stays host buffers in -> host buffers out
+    to_dev = entry(sndev_s, sndev_ranks, sn_h2d,
+                   "stored_norms, output_device=cuda (NOT the headline: nothing returns to the host): the pinned slab is "
+                   "compressed straight onto the GPU, the kept rows cross PCIe once, host to device")
+    to_dev["d2h_bytes_per_step"] = 0
+    best["alternatives"] = [l[1] for l in legs[1:]] + [to_dev]
     return best
 
 

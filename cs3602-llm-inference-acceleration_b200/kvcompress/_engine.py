@@ -206,7 +206,7 @@ class PlanSet:
 
 def run_plans(kv: Sequence[Tuple[torch.Tensor, torch.Tensor]], plans, given_indices: Optional[dict] = None,
               return_indices: bool = False, given_scores: Optional[dict] = None, norms: Optional[Sequence] = None,
-              non_blocking: bool = False):
+              non_blocking: bool = False, output_device=None):
     """Apply per-layer plans (a list of ``LayerPlan`` or a cached :class:`PlanSet`) to a list of (K, V) pairs.
 
     KEEP layers keep their tensor objects, VIEW layers become ``x[:, :, -n:, :]`` views (both
@@ -222,6 +222,8 @@ def run_plans(kv: Sequence[Tuple[torch.Tensor, torch.Tensor]], plans, given_indi
         instead of reading the K rows of the selection region (a :class:`KVSlabCache` records them at append time).
     non_blocking: host-resident (pinned) caches only — do not synchronise before returning; the pinned outputs are
         complete once the current stream has been synchronised.
+    output_device: host-resident (pinned) caches only — a CUDA device that receives the compressed cache instead of
+        pinned host memory (stream-ordered like any CUDA tensor: no synchronisation).
     """
     ps = plans if isinstance(plans, PlanSet) else PlanSet(plans)
     if given_indices is None and given_scores is None and not return_indices and ps.gather and not ps.views:
@@ -261,7 +263,14 @@ def run_plans(kv: Sequence[Tuple[torch.Tensor, torch.Tensor]], plans, given_indi
         if on_host and not torch.cuda.is_available():
             raise RuntimeError("pinned host tensors need a CUDA device to run on: there is no CPU path")
         run_device = torch.device("cuda", torch.cuda.current_device()) if on_host else device
-        alloc = dict(dtype=dtype, pin_memory=True) if on_host else dict(dtype=dtype, device=device)
+        to_device = on_host and output_device is not None
+        if to_device:
+            run_device = torch.device(output_device)
+            if run_device.type != "cuda":
+                raise ValueError(f"output_device must be a CUDA device, got {run_device}")
+            if run_device.index is None:
+                run_device = torch.device("cuda", torch.cuda.current_device())
+        alloc = dict(dtype=dtype, pin_memory=True) if on_host and not to_device else dict(dtype=dtype, device=run_device)
         n = len(members)
         lens = [ps.out_lens[li] for li, _, _ in members]
         C0 = lens[0]
@@ -360,7 +369,7 @@ def run_plans(kv: Sequence[Tuple[torch.Tensor, torch.Tensor]], plans, given_indi
         status = lib.kvc_compress_layers_ws(shape_rec, n, plan_bytes, bytes(io_buf), ws_ptr, ws_bytes,
                                             ctypes.c_void_p(_stream_ptr(run_device)))
         _check(status, "kvc_compress_layers")
-        if on_host and not non_blocking:
+        if on_host and not non_blocking and not to_device:
             # host tensors are read by the caller with plain loads: finish before returning, as the reference's
             # (synchronous) CPU path does; non_blocking=True leaves that to the caller (tensor.to(..., non_blocking=True))
             torch.cuda.current_stream(run_device).synchronize()

@@ -53,5 +53,6 @@ def stored_norms(past_key_values):
     return fn() if callable(fn) else None
 
 
-def execute(layers, plans, given_indices=None, norms=None, non_blocking=False):
-    return _engine.run_plans(layers, plans, given_indices=given_indices, norms=norms, non_blocking=non_blocking)
+def execute(layers, plans, given_indices=None, norms=None, non_blocking=False, output_device=None):
+    return _engine.run_plans(layers, plans, given_indices=given_indices, norms=norms, non_blocking=non_blocking,
+                             output_device=output_device)

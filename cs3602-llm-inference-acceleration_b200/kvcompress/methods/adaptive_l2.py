@@ -20,7 +20,7 @@ def adaptive_l2_compress(past_key_values, target_size: int = 512, soft_limit: in
     plans = cached_plans(_planner.plan_adaptive, seq_lens(layers), target_size, soft_limit, hard_limit, keep_ratio_min,
                          keep_ratio_max, skip_layers=skip_layers)
     return execute(layers, plans, norms=stored_norms(past_key_values),
-                   non_blocking=kwargs.get("non_blocking", False))
+                   non_blocking=kwargs.get("non_blocking", False), output_device=kwargs.get("output_device"))
 
 
 __all__ = ["adaptive_l2_compress"]

@@ -35,7 +35,7 @@ def fix_size_l2_compress(past_key_values, fix_kv_size: int = 1024, keep_ratio: f
         given = {li: _random_indices(layers[li][0], p.sel_hi, p.k_sel)
                  for li, p in enumerate(plans) if p.score == _planner.SCORE_GIVEN_INDEX}
     return execute(layers, plans, given_indices=given, norms=stored_norms(past_key_values),
-                   non_blocking=kwargs.get("non_blocking", False))
+                   non_blocking=kwargs.get("non_blocking", False), output_device=kwargs.get("output_device"))
 
 
 __all__ = ["fix_size_l2_compress"]

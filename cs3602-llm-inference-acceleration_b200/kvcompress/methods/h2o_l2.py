@@ -18,7 +18,7 @@ def h2o_l2_compress(past_key_values, start_size: int = 4, heavy_hitter_size: int
     plans = cached_plans(_planner.plan_h2o, seq_lens(layers), start_size, heavy_hitter_size, recent_size,
                          skip_layers=skip_layers)
     return execute(layers, plans, norms=stored_norms(past_key_values),
-                   non_blocking=kwargs.get("non_blocking", False))
+                   non_blocking=kwargs.get("non_blocking", False), output_device=kwargs.get("output_device"))
 
 
 __all__ = ["h2o_l2_compress"]

@@ -18,7 +18,7 @@ def l2_compress(past_key_values, keep_ratio: float = 1.0, prune_after: int = 100
     layers = as_layer_list(past_key_values)
     plans = cached_plans(_planner.plan_l2, seq_lens(layers), keep_ratio, prune_after, skip_layers=skip_layers)
     return execute(layers, plans, norms=stored_norms(past_key_values),
-                   non_blocking=kwargs.get("non_blocking", False))
+                   non_blocking=kwargs.get("non_blocking", False), output_device=kwargs.get("output_device"))
 
 
 __all__ = ["l2_compress"]

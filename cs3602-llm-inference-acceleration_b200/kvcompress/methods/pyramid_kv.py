@@ -19,7 +19,7 @@ def pyramid_kv_compress(past_key_values, base_size: int = 512, layer_decay: floa
     plans = cached_plans(_planner.plan_pyramid, seq_lens(layers), base_size, layer_decay, min_size, profile,
                          skip_layers=skip_layers)
     return execute(layers, plans, norms=stored_norms(past_key_values),
-                   non_blocking=kwargs.get("non_blocking", False))
+                   non_blocking=kwargs.get("non_blocking", False), output_device=kwargs.get("output_device"))
 
 
 __all__ = ["pyramid_kv_compress"]

@@ -30,7 +30,7 @@ def snapkv_lite_compress(past_key_values, observation_window: int = 32, keep_siz
                          skip_layers=skip_layers)
     if obs_queries is None:
         return execute(layers, plans, norms=stored_norms(past_key_values),
-                   non_blocking=kwargs.get("non_blocking", False))
+                   non_blocking=kwargs.get("non_blocking", False), output_device=kwargs.get("output_device"))
     if len(obs_queries) != len(layers):
         raise ValueError(f"obs_queries: {len(obs_queries)} entries for {len(layers)} layers")
     voted = [li for li, p in enumerate(plans) if p.kind == _planner.GATHER and p.k_sel > 0]

@@ -15,12 +15,14 @@ def streaming_llm_compress(past_key_values, start_size: int = 4, recent_size: in
 
     ``non_blocking=True`` (keyword extension of every compress function, host-resident caches only): return as soon as
     the launch is queued instead of synchronising; the pinned output tensors are complete once the current CUDA stream
-    has been synchronised — the contract of ``tensor.to("cpu", non_blocking=True)``."""
+    has been synchronised — the contract of ``tensor.to("cpu", non_blocking=True)``.
+    ``output_device="cuda"`` (same scope): write the compressed cache to that GPU instead of pinned host memory — the
+    kept rows of an offloaded cache cross PCIe once, host to device, and decoding continues on the GPU."""
     layers = as_layer_list(past_key_values)
     if not layers:
         return layers
     plans = cached_plans(_planner.plan_streaming, seq_lens(layers), start_size, recent_size, skip_layers=skip_layers)
-    return execute(layers, plans, non_blocking=kwargs.get("non_blocking", False))
+    return execute(layers, plans, non_blocking=kwargs.get("non_blocking", False), output_device=kwargs.get("output_device"))
 
 
 def evict_for_space(past_key_values, num_coming: int, start_size: int = 4, recent_size: int = 508,

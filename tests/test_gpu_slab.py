@@ -223,6 +223,15 @@ def test_pinned_slab_equals_device_slab_equals_functions(method, kwargs, dtype, 
         if not random:   # the host slab draws its random rows from the CPU generator, like the reference on CPU tensors
             assert torch.equal(got_host[li][0].cuda(), want[li][0]) and torch.equal(got_host[li][1].cuda(), want[li][1])
         assert got_host[li][0].shape == want[li][0].shape
+    if not random:
+        # the torch idioms for host destinations: queue now, synchronise later; or land the result on the GPU
+        queued = fn(host, non_blocking=True, **kwargs)
+        fetched = fn(host, output_device="cuda", **kwargs)
+        torch.cuda.synchronize()
+        for li in range(L):
+            assert torch.equal(queued[li][0].cuda(), want[li][0]) and torch.equal(queued[li][1].cuda(), want[li][1])
+            if want[li][0] is not kv[li][0]:
+                assert fetched[li][0].is_cuda and torch.equal(fetched[li][0], want[li][0]) and torch.equal(fetched[li][1], want[li][1])
     # in place
     torch.manual_seed(77)
     dev.compress_(method, **kwargs)
