@@ -31,6 +31,8 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--only", default="")
+    ap.add_argument("--pad-rows", type=int, default=0,
+                    help="allocate [B,H,S+pad,D] and work on the [:, :, :S] view: a unit pitch that is not 640 KB")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
     _engine = lab_util.use_lab_library_if_asked()
@@ -39,8 +41,9 @@ def main():
     L, B, H, S, D = 32, args.batch, 32, args.seq_len, 80
     sink, tail = 4, 508
     dev = torch.device("cuda", 0)
-    kv = [(torch.randn(B, H, S, D, device=dev, dtype=torch.bfloat16), torch.randn(B, H, S, D, device=dev, dtype=torch.bfloat16))
-          for _ in range(L)]
+    pad = args.pad_rows
+    kv = [(torch.randn(B, H, S + pad, D, device=dev, dtype=torch.bfloat16)[:, :, :S],
+           torch.randn(B, H, S + pad, D, device=dev, dtype=torch.bfloat16)[:, :, :S]) for _ in range(L)]
     outs = [(torch.empty(B, H, sink + tail, D, device=dev, dtype=torch.bfloat16),
              torch.empty(B, H, sink + tail, D, device=dev, dtype=torch.bfloat16)) for _ in range(L)]
     nbytes = 2 * L * B * H * (sink + tail) * D * 2 * 2  # read + write, K and V
@@ -62,14 +65,14 @@ def main():
         def run():
             for (k, v), (ko, vo) in zip(kv, outs):
                 for t, o in ((k, ko), (v, vo)):
-                    rc = ctl.copyctl_ldg(t.data_ptr(), o.data_ptr(), B * H, S * D * 2, D * 2, sink, tail, S, ctas, stream)
+                    rc = ctl.copyctl_ldg(t.data_ptr(), o.data_ptr(), B * H, (S + pad) * D * 2, D * 2, sink, tail, S, ctas, stream)
                     assert rc == 0, rc
         return run
 
     def memcpy2d():
         for (k, v), (ko, vo) in zip(kv, outs):
             for t, o in ((k, ko), (v, vo)):
-                rc = ctl.copyctl_memcpy2d(t.data_ptr(), o.data_ptr(), B * H, S * D * 2, D * 2, sink, tail, S, stream)
+                rc = ctl.copyctl_memcpy2d(t.data_ptr(), o.data_ptr(), B * H, (S + pad) * D * 2, D * 2, sink, tail, S, stream)
                 assert rc == 0, rc
 
     flat_src = torch.empty(nbytes // 4, device=dev, dtype=torch.bfloat16)
@@ -95,10 +98,11 @@ def main():
         b.record()
         torch.cuda.synchronize()
         ms = a.elapsed_time(b) / args.steps
+        name = name + (f"_pad{pad}" if pad else "")
         res[name] = {"ms": round(ms, 4), "gbs": round(nbytes / ms / 1e6, 1)}
         print(name, res[name], flush=True)
     # correctness of the controls against the product kernel
-    if not args.only and not os.environ.get("KVC_LAB_LIBRARY"):
+    if not args.only and not os.environ.get("KVC_LAB_LIBRARY") and not pad:
         ref = product()
         ldg(4)()
         torch.cuda.synchronize()
@@ -109,6 +113,8 @@ def main():
         torch.cuda.synchronize()
         assert all(torch.equal(r[0], o[0]) and torch.equal(r[1], o[1]) for r, o in zip(ref, outs)), "memcpy2d control differs"
         res["controls_bit_identical"] = True
+    if pad:
+        res = {k: v for k, v in res.items() if k.endswith(f"_pad{pad}")}
     res["bytes_moved"] = nbytes
     res["shape"] = f"{L} layers x (B={B}, H={H}, S={S}, D={D}) bf16, rows [0,{sink}) + [{S - tail},{S})"
     if args.out:

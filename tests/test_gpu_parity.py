@@ -544,6 +544,10 @@ FULL_SIZE = [
                  ("fix_size_l2", dict(fix_kv_size=512, keep_ratio=0.2, strategy="keep_low"))], 32, 32, 32, 4096, 80),
     # c5's per-GPU shard on 8 GPUs: 32 layers x (8,8,32768,128) bf16 = 34.4 GB
     ("c5_shard", [("pyramid_kv", dict(base_size=512)), ("adaptive_l2", dict(target_size=512))], 32, 8, 8, 32768, 128),
+    # c3's per-GPU shard on 8 GPUs (and one slab of the strong-scaled job): 32 layers x (32,32,8192,80) bf16 = 85.9 GB
+    ("c3_shard", [("h2o_l2", dict(start_size=4, heavy_hitter_size=64, recent_size=444))], 32, 32, 32, 8192, 80),
+    # c4 at its full single-GPU size: 32 layers x (16,8,32768,128) bf16 = 68.7 GB
+    ("c4_full", [("snapkv_lite", dict(observation_window=32, keep_size=512, pooling_kernel=5))], 32, 16, 8, 32768, 128),
 ]
 
 
@@ -578,8 +582,19 @@ def test_full_baseline_size_checksums(name, calls, L, B, H, S, D):
                 assert torch.equal(got, want)
                 total_in += want.sum()
                 total_out += got.sum()
-            if p.k_sel and li % 8 == 0:  # tie-aware selection rule on a sample of layers (fp64 norms are heavy)
+            if p.k_sel and li % 8 == 0 and p.score == P.SCORE_L2_LOW:
+                # tie-aware selection rule on a sample of layers (fp64 norms are heavy)
                 assert_valid_lowest(kv[li][0][:, :, p.sel_lo:p.sel_hi], idx[li][..., p.sink:p.sink + p.k_sel] - p.sel_lo)
+            if p.k_sel and li % 8 == 0 and p.score == P.SCORE_SNAPKV_POOL:
+                # snapkv_lite.py:96-134 with torch ops on this layer: the kept prefix rows are a top-k of the pooled
+                # scores (ties at the threshold may differ: every kept score >= the k-th largest)
+                norms = torch.norm(kv[li][0][:, :, :p.sel_hi], p=2, dim=-1)
+                sc = (norms.max(dim=-1, keepdim=True)[0] + 1e-6) - norms
+                pooled = torch.nn.functional.avg_pool1d(sc.reshape(B * H, 1, -1), p.pool_kernel, 1, p.pool_kernel // 2)
+                pooled = pooled.reshape(B, H, -1)[..., :p.sel_hi]
+                kth = torch.topk(pooled, p.k_sel, dim=-1)[0][..., -1:]
+                picked = torch.gather(pooled, 2, idx[li][..., :p.k_sel].long())
+                assert torch.all(picked >= kth)
         assert int(total_in) == int(total_out)  # checksum of checksums over the whole job
         again = kvcompress.get_compress_fn(method)(out, **kwargs)
         if method != "adaptive_l2":
