@@ -73,3 +73,12 @@ def test_vote_argument_checks():
     shape = _engine._SHAPE.pack(2, 8, 128, 2, 0)
     assert lib.kvc_snapkv_vote(shape, 1, layer, 8, 32, None) == 2   # 256 query rows > one MMA
     assert lib.kvc_snapkv_vote(shape, 1, None, 4, 32, None) == 1
+
+
+def test_integration_stub_uses_the_current_struct_layouts():
+    """INTEGRATION.md section 3 shows a ctypes stub a maintainer would paste: its struct formats must be the binding's."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    for fmt in (_engine._PLAN.format, _engine._IO.format, _engine._SHAPE.format):
+        assert f'struct.Struct("{fmt}")' in text, fmt
+    header = open(os.path.join(ROOT, "include", "kvc.h")).read()
+    assert f"#define KVC_ABI_VERSION {_engine.KVC_ABI_VERSION}" in header

@@ -148,6 +148,15 @@ def test_slab_errors():
         KVSlabCache(1, 1, 2, 80, 32, torch.bfloat16, device="cpu")
 
 
+def test_unit_pitch_avoids_channel_aligned_strides():
+    """A (batch, head) pitch that is a multiple of 16 KB lines the same rows of every unit up on the same HBM channels
+    (profiles/r02_stream_copy_control.json): the slab pads such capacities, the valid rows stay where they were."""
+    slab = KVSlabCache(1, 1, 2, 80, 4096, torch.bfloat16)          # 4096 x 160 B = 640 KB
+    assert slab.pitch == 4104 and slab.k.shape == (1, 1, 2, 4096, 80) and slab.k.stride(2) == 4104 * 80
+    assert KVSlabCache(1, 1, 2, 128, 32768, torch.bfloat16).pitch == 32776
+    assert KVSlabCache(1, 1, 2, 80, 4104, torch.bfloat16).pitch == 4104 and KVSlabCache(1, 1, 2, 80, 513, torch.bfloat16).pitch == 513
+
+
 def test_captured_decode_step_replays_append_and_compress():
     """CUDA-graph replay of (append one token, compress in place) == the same two calls made eagerly."""
     gen = torch.Generator(device="cuda").manual_seed(9)
