@@ -971,6 +971,7 @@ static int launch_vote_tma(const kvc_shape* shape, int32_t n_layers, const kvc_v
         bd.W = window;
         bd.scale_log2e = 1.4426950408889634f / sqrtf((float)D);
         bd.pad[0] = vote_debug_mode();
+        bd.pad[1] = env_int("KVC_VOTE_PF", kVotePrefetch);  // key tiles pulled into L2 ahead of their staging load
         for (int l = 0; l < nl; ++l) {
             const kvc_vote_layer& v = layers[l0 + l];
             VoteTmaLayerDev& d = bd.layers[l];

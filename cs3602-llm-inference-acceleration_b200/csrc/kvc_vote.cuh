@@ -43,6 +43,7 @@ namespace kvc {
 
 constexpr int kVoteM = 128;     // rows of both MMA shapes
 constexpr int kVoteTile = 128;  // keys per tile
+constexpr int kVotePrefetch = 0;  // key tiles prefetched into L2 ahead of the staging ring (0: off)
 
 // ---------------------------------------------------------------- tcgen05 wrappers
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
@@ -179,6 +180,12 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst_smem, const CUtensorMap
         "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
         ::"r"(dst_smem), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
         : "memory");
+}
+// Pull a box into L2 ahead of the load that will stage it (no destination, no completion to wait for).
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(c0), "r"(c1),
+                 "r"(c2), "r"(c3)
+                 : "memory");
 }
 // K-major, 32-byte swizzle: rows 32 B apart inside an 8-row atom, atoms 256 B apart (SBO), LBO = 16 B.
 __device__ __forceinline__ uint64_t umma_smem_desc_sw32(uint32_t smem_addr) {
@@ -420,11 +427,24 @@ __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __gri
     } else if (warp == 16) {
         // ================================================================ TMA producer (one thread)
         if (lane == 0) {
+            // A ring slot is held from the issue of its load until its MMAs have completed, so the ring depth times
+            // the slot size must cover that whole latency at full HBM rate — and at D = 128 five 32 KB slots do not
+            // quite (copies alone 10.4 ms, copies + MMAs 11.8 ms at c4).  Tiles are therefore pulled into L2 `pf` items
+            // ahead: the staging load then pays an L2 hit, not a DRAM access, and the slot turns around sooner.
+            const int pf = bd.pad[1];
+            const bool tail = REM > 0 && !no_tail;  // KVC_VOTE_DEBUG=3: timing without the 32-byte tail box
+            auto prefetch = [&](int i) {
+                const int t = i < n1 ? i : i - n1;
+#pragma unroll
+                for (int kh = 0; kh < KH; ++kh) tma_prefetch_4d(&L.map, kh * 64, t * kVoteTile, h, b);
+                if (tail) tma_prefetch_4d(&L.map_tail, KH * 64, t * kVoteTile, h, b);
+            };
+            for (int i = 0; i < min(pf, n_items); ++i) prefetch(i);
             for (int i = 0; i < n_items; ++i) {
                 const int slot = i % RING;
+                if (pf > 0 && i + pf < n_items) prefetch(i + pf);
                 mbar_wait(bar_empty + 8 * slot, (uint32_t)(((i / RING) & 1) ^ 1));  // fresh barrier: passes
                 const int t = i < n1 ? i : i - n1;
-                const bool tail = REM > 0 && !no_tail;  // KVC_VOTE_DEBUG=3: timing without the 32-byte tail box
                 mbar_arrive_expect_tx(bar_full + 8 * slot, tail || REM == 0 ? TILE_BYTES : KH * BOX_BYTES);
 #pragma unroll
                 for (int kh = 0; kh < KH; ++kh)  // rows beyond S are zero-filled by the TMA unit
