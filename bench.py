@@ -883,20 +883,26 @@ def run_e2e(cfg, B, kv, step_bytes, args, device, world, barrier):
     S = cfg["S"]
 
     def timed(step_fn):
+        """(job time per step = max over ranks of the barrier-bracketed wall clock, each rank's OWN time per step —
+        measured before the closing barrier, so a slow rank shows up as itself instead of as everybody's wait)."""
         step_fn()
         barrier()
         t0 = time.perf_counter()
+        own = 0.0
         for _ in range(steps):
-            step_fn()
+            t1 = time.perf_counter()
+            step_fn()              # ends with this rank's own stream synchronise
+            own += time.perf_counter() - t1
         barrier()
-        mine = (time.perf_counter() - t0) / steps
-        per_rank = [mine]
+        wall = (time.perf_counter() - t0) / steps
+        job, per_rank = wall, [own / steps]
         if world > 1:
-            t = torch.tensor([mine], device=device, dtype=torch.float64)
+            t = torch.tensor([wall, own / steps], device=device, dtype=torch.float64)
             parts = [torch.zeros_like(t) for _ in range(world)]
             dist.all_gather(parts, t)
-            per_rank = [float(p.item()) for p in parts]
-        return max(per_rank), per_rank
+            job = max(float(p[0].item()) for p in parts)
+            per_rank = [float(p[1].item()) for p in parts]
+        return job, per_rank
 
     # one pinned slab of `slab` streams is reused for every slab of the step (same bytes cross PCIe; content synthetic)
     dev_slice = [(k[:slab], v[:slab]) for k, v in kv]

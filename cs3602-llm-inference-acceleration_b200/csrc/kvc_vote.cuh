@@ -114,6 +114,24 @@ __device__ __forceinline__ float ex2(float x) {
     return y;
 }
 
+// 2^x on the FMA pipe (x <= ~0 here): round-to-nearest split x = n + f with the 1.5 * 2^23 trick, degree-3 minimax
+// polynomial for 2^f on [-0.5, 0.5] (relative error 1.1e-4, far inside the cache dtype's spacing), n added to the
+// exponent field.  ~9 FMA/ALU issue slots against one MUFU op that holds the quarter-rate XU pipe for 8 cycles.
+__device__ __forceinline__ float ex2_fma(float x) {
+    x = fmaxf(x, -125.f);
+    const float xr = x + 12582912.f;
+    const float f = x - (xr - 12582912.f);
+    float p = fmaf(f, 0.05550410866f, 0.24022650696f);
+    p = fmaf(p, f, 0.69314718056f);
+    p = fmaf(p, f, 1.0f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(xr) << 23));
+}
+// POLY of every 4 consecutive scores go through ex2_fma, the rest through the MUFU unit (j is a compile-time index).
+template <int POLY>
+__device__ __forceinline__ float ex2_mix(float x, int j) {
+    return (POLY > 0 && (j & 3) < POLY) ? ex2_fma(x) : ex2(x);
+}
+
 // Chunk (row r, 16-byte chunk c) of a [rows][CPR chunks] operand tile in the canonical layout: dense
 // 128-byte core matrices (8 rows x 16 B), K chunks kVoteLBO = 128 B apart, 8-row groups CPR*128 B apart.
 constexpr int kVoteLBO = 128;
@@ -218,7 +236,7 @@ __host__ __device__ constexpr int vote_tma_ring(int cpr) {
     return n > 12 ? 12 : n;
 }
 
-template <int DT, int CPR>
+template <int DT, int CPR, int POLY = 0>
 __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __grid_constant__ VoteTmaBatchDev bd) {
     using Tr = Traits<DT>;
     using Key = typename Tr::Key;
@@ -343,10 +361,10 @@ __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __gri
                         float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
 #pragma unroll
                         for (int j = 0; j < 16; j += 4) {
-                            acc0 += ex2(fmaf(__uint_as_float(v[j]), c2, -m_new));
-                            acc1 += ex2(fmaf(__uint_as_float(v[j + 1]), c2, -m_new));
-                            acc2 += ex2(fmaf(__uint_as_float(v[j + 2]), c2, -m_new));
-                            acc3 += ex2(fmaf(__uint_as_float(v[j + 3]), c2, -m_new));
+                            acc0 += ex2_mix<POLY>(fmaf(__uint_as_float(v[j]), c2, -m_new), 0);
+                            acc1 += ex2_mix<POLY>(fmaf(__uint_as_float(v[j + 1]), c2, -m_new), 1);
+                            acc2 += ex2_mix<POLY>(fmaf(__uint_as_float(v[j + 2]), c2, -m_new), 2);
+                            acc3 += ex2_mix<POLY>(fmaf(__uint_as_float(v[j + 3]), c2, -m_new), 3);
                         }
                         if (m_new != m_run) l_run *= ex2(m_run - m_new);  // the maximum settles after a few tiles
                         l_run += (acc0 + acc1) + (acc2 + acc3);
@@ -409,10 +427,10 @@ __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __gri
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) {
                         const float4 mm = *reinterpret_cast<const float4*>(s_m + cb + j);
-                        vote0 += ex2(fmaf(__uint_as_float(v[j + 0]), c2, -mm.x));
-                        vote1 += ex2(fmaf(__uint_as_float(v[j + 1]), c2, -mm.y));
-                        vote2 += ex2(fmaf(__uint_as_float(v[j + 2]), c2, -mm.z));
-                        vote3 += ex2(fmaf(__uint_as_float(v[j + 3]), c2, -mm.w));
+                        vote0 += ex2_mix<POLY>(fmaf(__uint_as_float(v[j + 0]), c2, -mm.x), 0);
+                        vote1 += ex2_mix<POLY>(fmaf(__uint_as_float(v[j + 1]), c2, -mm.y), 1);
+                        vote2 += ex2_mix<POLY>(fmaf(__uint_as_float(v[j + 2]), c2, -mm.z), 2);
+                        vote3 += ex2_mix<POLY>(fmaf(__uint_as_float(v[j + 3]), c2, -mm.w), 3);
                     }
                 }
             }

@@ -28,11 +28,12 @@ def main():
                        torch.randn(B, H, S, D, generator=g, device=dev, dtype=torch.bfloat16)))
         qs = [(1.5 * torch.randn(B, H * G, 32, D, device=dev)).bfloat16() for _ in range(L)]
         nbytes = 2 * B * H * D * L * (2 * (S - 32) + 4 * 512)
-        for dbg in ("0", "1", "2"):
-            for pf in ("0", "2", "4", "8", "16", "32"):
-                if dbg != "0" and pf not in ("0", "8"):
-                    continue
-                os.environ["KVC_VOTE_PF"], os.environ["KVC_VOTE_DEBUG"] = pf, dbg
+        combos = [("0", pf, "0") for pf in ("0", "2", "4", "8", "16", "32")]
+        combos += [(dbg, pf, "0") for dbg in ("1", "2") for pf in ("0", "8")]
+        combos += [("0", pf, poly) for poly in ("1", "2") for pf in ("0", "8")]
+        for dbg, pf, poly in combos:
+            if True:
+                os.environ["KVC_VOTE_PF"], os.environ["KVC_VOTE_DEBUG"], os.environ["KVC_VOTE_POLY"] = pf, dbg, poly
                 fn = lambda: kvcompress.snapkv_lite_compress(kv, observation_window=32, keep_size=512, obs_queries=qs)
                 for _ in range(2):
                     fn()
@@ -44,7 +45,7 @@ def main():
                 b.record()
                 torch.cuda.synchronize()
                 ms = a.elapsed_time(b) / 4
-                key = f"{name} debug={dbg} pf={pf}"
+                key = f"{name} debug={dbg} pf={pf} poly={poly}"
                 res[key] = {"ms": round(ms, 3), "gbs": round(nbytes / ms / 1e6, 1)}
                 print(key, res[key], flush=True)
         del kv, qs
