@@ -956,15 +956,6 @@ static int launch_vote_tma(const kvc_shape* shape, int32_t n_layers, const kvc_v
     else
         fn = cpr == 8 ? kvc_snapkv_vote_tma_kernel<KVC_DTYPE_F16, 8>
                       : cpr == 10 ? kvc_snapkv_vote_tma_kernel<KVC_DTYPE_F16, 10> : kvc_snapkv_vote_tma_kernel<KVC_DTYPE_F16, 16>;
-#ifdef KVC_LAB
-    // lab: a fraction of the exp2s on the FMA pipe (KVC_VOTE_POLY = 1 or 2 of every 4), bf16 only
-    if (dt == KVC_DTYPE_BF16 && env_int("KVC_VOTE_POLY", 0) == 1)
-        fn = cpr == 8 ? kvc_snapkv_vote_tma_kernel<KVC_DTYPE_BF16, 8, 1>
-                      : cpr == 10 ? kvc_snapkv_vote_tma_kernel<KVC_DTYPE_BF16, 10, 1> : kvc_snapkv_vote_tma_kernel<KVC_DTYPE_BF16, 16, 1>;
-    if (dt == KVC_DTYPE_BF16 && env_int("KVC_VOTE_POLY", 0) == 2)
-        fn = cpr == 8 ? kvc_snapkv_vote_tma_kernel<KVC_DTYPE_BF16, 8, 2>
-                      : cpr == 10 ? kvc_snapkv_vote_tma_kernel<KVC_DTYPE_BF16, 10, 2> : kvc_snapkv_vote_tma_kernel<KVC_DTYPE_BF16, 16, 2>;
-#endif
     const size_t tile = (size_t)(cpr / 8) * kVoteTile * 128 + (size_t)(cpr % 8) * kVoteTile * 16;
     const size_t smem = 6144 + (size_t)(kVoteM / 8) * cpr * kVoteLBO + (size_t)vote_tma_ring(cpr) * tile;
     int st = ensure_tma_attrs((const void*)fn, shape->device);
@@ -980,7 +971,6 @@ static int launch_vote_tma(const kvc_shape* shape, int32_t n_layers, const kvc_v
         bd.W = window;
         bd.scale_log2e = 1.4426950408889634f / sqrtf((float)D);
         bd.pad[0] = vote_debug_mode();
-        bd.pad[1] = env_int("KVC_VOTE_PF", kVotePrefetch);  // key tiles pulled into L2 ahead of their staging load
         for (int l = 0; l < nl; ++l) {
             const kvc_vote_layer& v = layers[l0 + l];
             VoteTmaLayerDev& d = bd.layers[l];

@@ -43,7 +43,6 @@ namespace kvc {
 
 constexpr int kVoteM = 128;     // rows of both MMA shapes
 constexpr int kVoteTile = 128;  // keys per tile
-constexpr int kVotePrefetch = 0;  // key tiles prefetched into L2 ahead of the staging ring (0: off)
 
 // ---------------------------------------------------------------- tcgen05 wrappers
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
@@ -114,24 +113,6 @@ __device__ __forceinline__ float ex2(float x) {
     return y;
 }
 
-// 2^x on the FMA pipe (x <= ~0 here): round-to-nearest split x = n + f with the 1.5 * 2^23 trick, degree-3 minimax
-// polynomial for 2^f on [-0.5, 0.5] (relative error 1.1e-4, far inside the cache dtype's spacing), n added to the
-// exponent field.  ~9 FMA/ALU issue slots against one MUFU op that holds the quarter-rate XU pipe for 8 cycles.
-__device__ __forceinline__ float ex2_fma(float x) {
-    x = fmaxf(x, -125.f);
-    const float xr = x + 12582912.f;
-    const float f = x - (xr - 12582912.f);
-    float p = fmaf(f, 0.05550410866f, 0.24022650696f);
-    p = fmaf(p, f, 0.69314718056f);
-    p = fmaf(p, f, 1.0f);
-    return __int_as_float(__float_as_int(p) + (__float_as_int(xr) << 23));
-}
-// POLY of every 4 consecutive scores go through ex2_fma, the rest through the MUFU unit (j is a compile-time index).
-template <int POLY>
-__device__ __forceinline__ float ex2_mix(float x, int j) {
-    return (POLY > 0 && (j & 3) < POLY) ? ex2_fma(x) : ex2(x);
-}
-
 // Chunk (row r, 16-byte chunk c) of a [rows][CPR chunks] operand tile in the canonical layout: dense
 // 128-byte core matrices (8 rows x 16 B), K chunks kVoteLBO = 128 B apart, 8-row groups CPR*128 B apart.
 constexpr int kVoteLBO = 128;
@@ -199,12 +180,6 @@ __device__ __forceinline__ void tma_load_4d(uint32_t dst_smem, const CUtensorMap
         ::"r"(dst_smem), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
         : "memory");
 }
-// Pull a box into L2 ahead of the load that will stage it (no destination, no completion to wait for).
-__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
-    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(c0), "r"(c1),
-                 "r"(c2), "r"(c3)
-                 : "memory");
-}
 // K-major, 32-byte swizzle: rows 32 B apart inside an 8-row atom, atoms 256 B apart (SBO), LBO = 16 B.
 __device__ __forceinline__ uint64_t umma_smem_desc_sw32(uint32_t smem_addr) {
     uint64_t d = 0;
@@ -236,7 +211,7 @@ __host__ __device__ constexpr int vote_tma_ring(int cpr) {
     return n > 12 ? 12 : n;
 }
 
-template <int DT, int CPR, int POLY = 0>
+template <int DT, int CPR>
 __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __grid_constant__ VoteTmaBatchDev bd) {
     using Tr = Traits<DT>;
     using Key = typename Tr::Key;
@@ -361,10 +336,10 @@ __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __gri
                         float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
 #pragma unroll
                         for (int j = 0; j < 16; j += 4) {
-                            acc0 += ex2_mix<POLY>(fmaf(__uint_as_float(v[j]), c2, -m_new), 0);
-                            acc1 += ex2_mix<POLY>(fmaf(__uint_as_float(v[j + 1]), c2, -m_new), 1);
-                            acc2 += ex2_mix<POLY>(fmaf(__uint_as_float(v[j + 2]), c2, -m_new), 2);
-                            acc3 += ex2_mix<POLY>(fmaf(__uint_as_float(v[j + 3]), c2, -m_new), 3);
+                            acc0 += ex2(fmaf(__uint_as_float(v[j]), c2, -m_new));
+                            acc1 += ex2(fmaf(__uint_as_float(v[j + 1]), c2, -m_new));
+                            acc2 += ex2(fmaf(__uint_as_float(v[j + 2]), c2, -m_new));
+                            acc3 += ex2(fmaf(__uint_as_float(v[j + 3]), c2, -m_new));
                         }
                         if (m_new != m_run) l_run *= ex2(m_run - m_new);  // the maximum settles after a few tiles
                         l_run += (acc0 + acc1) + (acc2 + acc3);
@@ -427,10 +402,10 @@ __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __gri
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) {
                         const float4 mm = *reinterpret_cast<const float4*>(s_m + cb + j);
-                        vote0 += ex2_mix<POLY>(fmaf(__uint_as_float(v[j + 0]), c2, -mm.x), 0);
-                        vote1 += ex2_mix<POLY>(fmaf(__uint_as_float(v[j + 1]), c2, -mm.y), 1);
-                        vote2 += ex2_mix<POLY>(fmaf(__uint_as_float(v[j + 2]), c2, -mm.z), 2);
-                        vote3 += ex2_mix<POLY>(fmaf(__uint_as_float(v[j + 3]), c2, -mm.w), 3);
+                        vote0 += ex2(fmaf(__uint_as_float(v[j + 0]), c2, -mm.x));
+                        vote1 += ex2(fmaf(__uint_as_float(v[j + 1]), c2, -mm.y));
+                        vote2 += ex2(fmaf(__uint_as_float(v[j + 2]), c2, -mm.z));
+                        vote3 += ex2(fmaf(__uint_as_float(v[j + 3]), c2, -mm.w));
                     }
                 }
             }
@@ -445,22 +420,9 @@ __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __gri
     } else if (warp == 16) {
         // ================================================================ TMA producer (one thread)
         if (lane == 0) {
-            // A ring slot is held from the issue of its load until its MMAs have completed, so the ring depth times
-            // the slot size must cover that whole latency at full HBM rate — and at D = 128 five 32 KB slots do not
-            // quite (copies alone 10.4 ms, copies + MMAs 11.8 ms at c4).  Tiles are therefore pulled into L2 `pf` items
-            // ahead: the staging load then pays an L2 hit, not a DRAM access, and the slot turns around sooner.
-            const int pf = bd.pad[1];
             const bool tail = REM > 0 && !no_tail;  // KVC_VOTE_DEBUG=3: timing without the 32-byte tail box
-            auto prefetch = [&](int i) {
-                const int t = i < n1 ? i : i - n1;
-#pragma unroll
-                for (int kh = 0; kh < KH; ++kh) tma_prefetch_4d(&L.map, kh * 64, t * kVoteTile, h, b);
-                if (tail) tma_prefetch_4d(&L.map_tail, KH * 64, t * kVoteTile, h, b);
-            };
-            for (int i = 0; i < min(pf, n_items); ++i) prefetch(i);
             for (int i = 0; i < n_items; ++i) {
                 const int slot = i % RING;
-                if (pf > 0 && i + pf < n_items) prefetch(i + pf);
                 mbar_wait(bar_empty + 8 * slot, (uint32_t)(((i / RING) & 1) ^ 1));  // fresh barrier: passes
                 const int t = i < n1 ? i : i - n1;
                 mbar_arrive_expect_tx(bar_full + 8 * slot, tail || REM == 0 ? TILE_BYTES : KH * BOX_BYTES);
