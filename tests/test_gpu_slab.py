@@ -276,3 +276,81 @@ def test_stored_norms_replace_the_scan_bytes():
     got = kvcompress.h2o_l2_compress(slab, start_size=4, heavy_hitter_size=32, recent_size=92)
     for li in range(L):
         assert torch.equal(got[li][0], want[li][0]) and torch.equal(got[li][1], want[li][1])
+
+
+# ----------------------------------------------------------------------------------------------
+# Soak: randomised plans through the three data paths (K scan, stored norms out of place, in place), every result
+# compared bit for bit with torch ops on the same norms, every launch repeated.  compute-sanitizer is closed on this GPU
+# pool (profiles/r02_sanitizer.md); this is the standing check on the mbarrier / bulk-copy / in-place-overlap code:
+# a race shows up as a mismatch or as two launches that disagree.
+def _expected_rows(norms, plan):
+    """Kept rows per (b, h): sinks, the k_sel lowest (highest) norms of [sel_lo, sel_hi) with ties to the lowest index,
+    the tail — torch ops only."""
+    B, H, S = norms.shape
+    region = norms[:, :, plan.sel_lo:plan.sel_hi].float()
+    if plan.score == P.SCORE_L2_HIGH:
+        region = -region
+    order = torch.sort(region, dim=-1, stable=True)[1][..., :plan.k_sel]
+    sel = torch.sort(order, dim=-1)[0] + plan.sel_lo
+    dev = norms.device
+    sink = torch.arange(plan.sink, device=dev).expand(B, H, -1)
+    tail = torch.arange(S - plan.tail, S, device=dev).expand(B, H, -1)
+    return torch.cat([sink, sel, tail], dim=-1)
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_soak_random_plans_three_paths_agree_with_torch(seed):
+    import random
+
+    rng = random.Random(1000 + seed)
+    gen = torch.Generator(device="cuda").manual_seed(seed)
+    for _case in range(20):
+        dtype = rng.choice(["bf16", "bf16", "f16", "f32"])
+        D = rng.choice([64, 80, 128, 72, 40, 96] if dtype != "f32" else [32, 80, 100, 128])
+        L, B, H = rng.randint(1, 4), rng.randint(1, 3), rng.randint(1, 4)
+        plans = []
+        lens = []
+        for _ in range(L):
+            S = rng.choice([rng.randint(40, 300), rng.randint(300, 2500), rng.randint(2500, 6000)])
+            sink = rng.choice([0, 0, 4, rng.randint(0, min(40, S // 4))])
+            tail = rng.choice([0, rng.randint(0, S // 3), rng.randint(0, min(600, S // 2))])
+            lo = sink + rng.choice([0, 0, rng.randint(0, 10)])
+            hi = S - tail - rng.choice([0, 0, rng.randint(0, 10)])
+            if hi < lo:
+                lo = hi = sink
+            k = rng.choice([0, 1, rng.randint(0, hi - lo), (hi - lo) // 2, hi - lo])
+            score = rng.choice([P.SCORE_L2_LOW, P.SCORE_L2_LOW, P.SCORE_L2_HIGH]) if k else P.SCORE_NONE
+            if sink + k + tail == 0:
+                tail = 1
+                hi = min(hi, S - 1)
+                lo = min(lo, hi)
+                k = min(k, hi - lo)
+            plans.append(P.LayerPlan(P.GATHER, S, sink, lo, hi, k, tail, score, 1))
+            lens.append(S)
+        dt = DT[dtype]
+        kv = []
+        for S in lens:
+            k, v = rand_rows(B, H, S, D, dt, gen, spread=rng.random() < 0.7)
+            if rng.random() < 0.3:                       # ties: rows drawn from a small codebook
+                book = k[:, :, :7].clone()
+                k = book[:, :, torch.randint(0, 7, (S,), generator=gen, device="cuda")]
+            kv.append((k.contiguous(), v))
+        slab = KVSlabCache.from_legacy_cache(kv, capacity=max(lens) + rng.choice([0, 3, 8]))
+        want = []
+        for li, p in enumerate(plans):
+            rows = _expected_rows(slab.key_norms(li), p)
+            ix = rows.unsqueeze(-1).expand(-1, -1, -1, D)
+            want.append((torch.gather(kv[li][0], 2, ix), torch.gather(kv[li][1], 2, ix), rows))
+        ps = _engine.PlanSet(plans)
+        scan1, idx1 = _engine.run_plans(kv, ps, return_indices=True)                    # K scan (ctypes walk)
+        scan2 = _engine.run_plans(kv, ps)                                               # K scan (compiled binding)
+        by_norms = _engine.run_plans(slab.to_legacy_cache(), ps, norms=slab.key_norm_layers())
+        by_norms2 = _engine.run_plans(slab.to_legacy_cache(), ps, norms=slab.key_norm_layers())
+        slab.apply_plans_(ps)                                                           # in place
+        for li, (wk, wv, rows) in enumerate(want):
+            tag = (seed, _case, li, dtype, D, plans[li])
+            assert torch.equal(idx1[li].long(), rows), tag
+            for got in (scan1[li], scan2[li], by_norms[li], by_norms2[li], slab[li]):
+                assert torch.equal(got[0], wk) and torch.equal(got[1], wv), tag
+            assert slab.lengths[li] == rows.size(-1)
+            assert torch.equal(slab.key_norms(li), torch.gather(KVSlabCache.from_legacy_cache([kv[li]], capacity=lens[li]).key_norms(0), 2, rows)), tag
