@@ -411,7 +411,9 @@ def run_reference(args):
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
         "ms_per_step": round(res["seconds_per_step"] * 1e3, 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": cfg["dtype"], "data": "synthetic",
-        "config": workload_config(cfg, args.config, sb, 1),
+        # the SAME config as the repo arm's line (contract: "on your arm's config"); what was actually timed per step is
+        # the bounded sample described in cpu_baseline.sample
+        "config": workload_config(cfg, args.config, cfg["B"], max(1, args.gpus)),
         "cpu_baseline": {"value": round(res["gbs"], 3), "unit": "GB/s", "cores": res["threads"], "kind": "port",
                          "sample": res["sample"]},
         "cpu_baseline_reference": ref_line,
