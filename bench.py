@@ -580,8 +580,11 @@ def configs_table(args, device):
                 torch.cuda.empty_cache()
                 kv = make_cache(cfg, B, device, seed=4321)
                 kv_key = key
-            total_ms, per_call, launches, vote_flops, wall_ms = time_calls(cfg, B, kv, steps, 2, device)
+            sampler = ClockSampler(device.index or 0)
+            total_ms, per_call, launches, vote_flops, wall_ms = time_calls(cfg, B, kv, steps, 2, device, None, sampler)
+            clk = sampler.stop()
             entry = {"workload": workload_config(cfg, base, B, 1)["workload"], "steps": steps,
+                     "sm_mhz": clk.get("sm_mhz"), "clock_reasons": clk.get("reasons"),
                      "ms_per_step": round(total_ms / steps, 4), "wall_ms_per_step": round(wall_ms / steps, 4),
                      "per_call": per_call, "gpu_launches": launches,
                      "min_frac_of_peak": min(c["frac_of_peak"] for c in per_call)}
