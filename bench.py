@@ -494,7 +494,7 @@ def vote_inputs(cfg, B, kv, device):
     return extra, flops
 
 
-def time_calls(cfg, B, kv, steps, warmup, device, barrier=None, sampler=None):
+def time_calls(cfg, B, kv, steps, warmup, device, barrier=None, sampler=None, back_to_back=0):
     """`steps` timed passes of the config's calls on `kv` (CUDA events on torch's current stream = the launch stream).
     Returns (total_ms, per_call list of dicts, launches, vote_flops)."""
     import torch
@@ -555,6 +555,25 @@ def time_calls(cfg, B, kv, steps, warmup, device, barrier=None, sampler=None):
                          "algorithmic_bytes": per_call_bytes[i],
                          "gbs": round(per_call_bytes[i] / (mean * 1e-3) / 1e9, 1),
                          "frac_of_peak": round(per_call_bytes[i] / (mean * 1e-3) / 1e9 / peak, 4)})
+    if back_to_back:
+        # latency-bound shapes (batch 1): the calls queued back to back with no event in between — what a decode loop
+        # sees when the GPU already has work queued — timed once around the whole train
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        a.record()
+        for _ in range(back_to_back):
+            one_step()
+        b.record()
+        host_us = (time.perf_counter() - t0) * 1e6 / (back_to_back * len(fns))
+        torch.cuda.synchronize()
+        wall_us = (time.perf_counter() - t0) * 1e6 / (back_to_back * len(fns))
+        dev_us = a.elapsed_time(b) * 1e3 / (back_to_back * len(fns))
+        per_call.append({"call": "back_to_back", "calls": back_to_back * len(fns), "host_us_per_call": round(host_us, 1),
+                         "wall_us_per_call": round(wall_us, 1), "device_us_per_call": round(dev_us, 1),
+                         "gbs": round(sum(per_call_bytes) / len(fns) / dev_us / 1e3, 1),
+                         "frac_of_peak": round(sum(per_call_bytes) / len(fns) / dev_us / 1e3 / peak, 4),
+                         "us_mean": round(dev_us, 1), "us_min": round(dev_us, 1), "algorithmic_bytes": sum(per_call_bytes) // len(fns)})
     return total_ms, per_call, launches, vote_flops, wall_ms
 
 
@@ -581,17 +600,19 @@ def configs_table(args, device):
                 kv = make_cache(cfg, B, device, seed=4321)
                 kv_key = key
             sampler = ClockSampler(device.index or 0)
-            total_ms, per_call, launches, vote_flops, wall_ms = time_calls(cfg, B, kv, steps, 2, device, None, sampler)
+            total_ms, per_call, launches, vote_flops, wall_ms = time_calls(cfg, B, kv, steps, 2, device, None, sampler,
+                                                                            back_to_back=50 if B == 1 else 0)
             clk = sampler.stop()
             entry = {"workload": workload_config(cfg, base, B, 1)["workload"], "steps": steps,
                      "sm_mhz": clk.get("sm_mhz"), "clock_reasons": clk.get("reasons"),
                      "ms_per_step": round(total_ms / steps, 4), "wall_ms_per_step": round(wall_ms / steps, 4),
                      "per_call": per_call, "gpu_launches": launches,
-                     "min_frac_of_peak": min(c["frac_of_peak"] for c in per_call)}
+                     "min_frac_of_peak": min(c["frac_of_peak"] for c in per_call if c["call"] != "back_to_back")}
             if vote_flops:
                 entry["tensor_tflops"] = round(vote_flops / (total_ms / steps * 1e-3) / 1e12, 1)
             if B == 1:
-                entry["note"] = "batch 1 is host/launch-latency bound: wall_ms_per_step is what a decode loop sees"
+                entry["note"] = ("batch 1: the per-call rows time ONE call between two events on an idle GPU (launch latency "
+                                 "included); the back_to_back row is the same calls queued without events")
         except Exception as exc:  # one config failing must not take the headline line with it
             entry = {"error": repr(exc)[:300]}
             kv, kv_key = None, None

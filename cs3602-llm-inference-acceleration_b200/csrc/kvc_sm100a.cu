@@ -9,6 +9,7 @@
 //   gather (K3) copy sink rows + selected rows + tail rows of K and V into the dense output.
 // Several CTAs are resident per SM, so one unit's select overlaps its neighbours' HBM phases.
 // Algorithmic HBM bytes per unit: e*D*(R + 4*C)  (SURVEY.md §8d).
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cmath>
@@ -176,6 +177,7 @@ static size_t fused_smem_bytes(int dtype, int max_region, int idx_cap) {
 
 // ------------------------------------------------------------------ TMA form: variant + smem plan
 constexpr int kSmemPerSM = 228 * 1024;  // per-SM shared memory; every resident CTA reserves 1 KB of it
+constexpr int kSMs = 148;               // B200
 constexpr int kTmaHead = kMiscInts * 4 + 32 * 8;  // misc scalars + one mbarrier per warp
 
 struct TmaPlan {
@@ -203,7 +205,13 @@ static inline int vote_debug_mode() { return 0; }
 // Choose threads per CTA, resident CTAs per SM and staging warps so that (a) the on-chip key
 // buffer fits, (b) as close to 128 KB of rows as possible are in flight per SM, (c) as many CTAs as possible are
 // resident so one unit's select phase hides under its neighbours' HBM phases.
-static TmaPlan plan_tma(int dtype, int cpr, int max_region, int idx_cap, bool any_select, bool light_traffic = false) {
+// `units` / `unit_bytes` (optional): CTAs of the launch and the bytes one of them moves.  A launch of a few large
+// units (c1: 960 units of 2.75 MB on 148 SMs) ends in a partial wave whose CTAs each run alone on their SM; with 3
+// resident CTAs per SM that wave is a third of the whole launch, with one 512-thread CTA per SM a seventh
+// (measured: 446 -> 402 us, 0.90 -> 1.00 of the copy peak, profiles/r02_plan_sweep_few_units.json).  Small units
+// (decode steady state) and launches of many waves keep the residency-first choice.
+static TmaPlan plan_tma(int dtype, int cpr, int max_region, int idx_cap, bool any_select, bool light_traffic = false,
+                        int64_t units = 0, int64_t unit_bytes = 0) {
     TmaPlan best;
     const int stage = 32 * cpr * 16;
     int end = kTmaHead;
@@ -236,6 +244,18 @@ static TmaPlan plan_tma(int dtype, int cpr, int max_region, int idx_cap, bool an
         long score = (inflight < 131072 ? inflight : 131072) * 8 + ctas * 4096 + (inflight >> 6);
         // in-place compaction moves few bytes (scores come from stored norms): residency first, 2+ slots are enough
         if (light_traffic) score = (nsw >= 2 ? 1 : 0) * (1L << 30) + ctas * (1L << 20) + nsw;
+        if (!light_traffic && units > 0 && unit_bytes >= (1 << 20) && !force_nt && !force_ctas) {
+            // few large units: rank the candidates by the estimated length of the launch in unit-times — full waves,
+            // plus a last partial wave that costs at least ~0.35 of a full one (a lone CTA is latency-bound) — with
+            // a small handicap for lower residency (many-wave launches measure 256 x 3 about 5 % ahead of 512 x 1)
+            const long slots = (long)ctas * kSMs;
+            const long full = (long)(units / slots), rem = (long)(units - full * slots);
+            if (full < 8) {
+                const double est = (double)full * slots + (rem > 0 ? std::max((double)rem, 0.35 * slots) : 0.0);
+                const double handicap = ctas >= 3 ? 1.00 : (ctas == 2 ? 1.02 : (nt == 512 ? 1.05 : 1.10));
+                score = (long)(1e9 / (est * handicap + 1.0)) + (1L << 40);
+            }
+        }
         if (score > best_score) {
             best_score = score;
             best = base;
@@ -468,13 +488,16 @@ int kvc_compress_layers(const kvc_shape* shape, int32_t n_layers, const kvc_laye
 
 // Launch-chunk statistics shared by kvc_workspace_bytes and the launchers.
 static void chunk_stats(const kvc_layer_plan* plans, int nl, int* n_active, int* max_region, int* max_ksel,
-                        bool* any_select) {
+                        bool* any_select, int64_t* rows_moved = nullptr) {
     *n_active = *max_region = *max_ksel = 0;
     *any_select = false;
+    if (rows_moved) *rows_moved = 0;
     for (int l = 0; l < nl; ++l) {
         const kvc_layer_plan& p = plans[l];
         if (p.sink + p.k_sel + p.tail == 0) continue;
         ++*n_active;
+        // rows one unit of this layer moves if it scans K: the region once + kept rows of K and V read and written
+        if (rows_moved) *rows_moved += (p.k_sel > 0 ? p.sel_hi - p.sel_lo : 0) + 4LL * (p.sink + p.k_sel + p.tail);
         if (p.k_sel > 0) {
             *any_select = true;
             if (p.k_sel > *max_ksel) *max_ksel = p.k_sel;
@@ -491,10 +514,12 @@ int64_t kvc_workspace_bytes(const kvc_shape* shape, int32_t n_layers, const kvc_
         const int nl = (n_layers - l0) < KVC_MAX_LAYERS_PER_LAUNCH ? (n_layers - l0) : KVC_MAX_LAYERS_PER_LAUNCH;
         int n_active, max_region, max_ksel;
         bool any_select;
-        chunk_stats(plans + l0, nl, &n_active, &max_region, &max_ksel, &any_select);
+        int64_t rows_moved;
+        chunk_stats(plans + l0, nl, &n_active, &max_region, &max_ksel, &any_select, &rows_moved);
         if (!any_select) continue;
         const int idx_cap = (max_ksel + 3) & ~3;
-        const TmaPlan tp = plan_tma(shape->dtype, cpr, max_region, idx_cap, true);
+        const TmaPlan tp = plan_tma(shape->dtype, cpr, max_region, idx_cap, true, false,
+                                    (int64_t)shape->batch * shape->heads * n_active, rows_moved / n_active * cpr * 16);
         if (onchip_plan_ok(tp, cpr, false)) continue;
         const int64_t bytes = ws_layout(shape->dtype, max_region, idx_cap).unit * shape->batch * shape->heads * n_active;
         if (bytes > need) need = bytes;
@@ -548,11 +573,13 @@ int kvc_compress_layers_ws(const kvc_shape* shape, int32_t n_layers, const kvc_l
         bd.H = H;
         bd.cpr = cpr;
         int n_active = 0, max_region = 0, max_ksel = 0;
+        int64_t rows_moved = 0;
         bool any_select = false, any_scan = false;
         for (int l = 0; l < nl; ++l) {
             const kvc_layer_plan& p = plans[l0 + l];
             const kvc_layer_io& x = io[l0 + l];
             if (p.sink + p.k_sel + p.tail == 0) continue;
+            rows_moved += (p.k_sel > 0 ? p.sel_hi - p.sel_lo : 0) + 4LL * (p.sink + p.k_sel + p.tail);
             LayerDev& d = bd.layers[n_active++];
             d.k_in = (const char*)x.k_in;
             d.v_in = (const char*)x.v_in;
@@ -594,7 +621,8 @@ int kvc_compress_layers_ws(const kvc_shape* shape, int32_t n_layers, const kvc_l
         // no K scan in this launch (stored norms, caller-supplied scores or rows, pure slices with a select next to
         // them): only kept rows move -> residency over slot depth
         const bool light = any_select && !any_scan;
-        TmaPlan tp = plan_tma(dt, cpr, max_region, bd.idx_cap, any_select, light);
+        TmaPlan tp = plan_tma(dt, cpr, max_region, bd.idx_cap, any_select, light, (int64_t)B * H * n_active,
+                              rows_moved / n_active * cpr * 16);
         if (any_select && workspace != nullptr && !onchip_plan_ok(tp, cpr, light)) {
             // keys and kept indices go to the workspace; shared memory keeps the histogram and the slots
             const WsLayout w = ws_layout(dt, max_region, bd.idx_cap);
