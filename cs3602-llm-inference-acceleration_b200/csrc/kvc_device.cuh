@@ -55,8 +55,7 @@ struct BatchDev {
     int32_t B, H;
     int32_t idx_cap;   // ints reserved for the kept-index list in shared memory
     int32_t cpr;       // 16-byte chunks per row (the generic-width kernels read it at run time)
-    int32_t order;     // CTA -> unit mapping: 0 = (unit = blockIdx.x, layer = blockIdx.y); 1 = layers fastest; 2 = strided units
-    int32_t pad1;
+    int32_t pad0, pad1;
     int32_t nsw;       // TMA form: warps that own a staging slot (<= warps per CTA)
     int32_t off_hist, off_idx, off_keys, off_stage;  // TMA form: shared-memory layout (bytes)
     int32_t upc;       // TMA form: consecutive (batch, head) units walked by one CTA

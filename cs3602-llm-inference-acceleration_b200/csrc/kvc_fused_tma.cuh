@@ -162,17 +162,7 @@ __global__ void __launch_bounds__(NT, MINB) kvc_fused_tma_kernel(const __grid_co
     const int cpr = CPR > 0 ? CPR : bd.cpr;
     const int RB = cpr * 16;  // row bytes
 
-    // Which unit this CTA owns.  CTAs start in blockIdx order (x fastest), so the mapping decides which addresses
-    // are in flight together: order 1 spreads concurrently resident CTAs over the layers (separate allocations),
-    // order 2 strides over the (batch, head) units of one layer.
-    int bx = blockIdx.x, by = blockIdx.y;
-    if (bd.order == 1) {
-        const unsigned lin = blockIdx.y * gridDim.x + blockIdx.x;
-        by = (int)(lin % gridDim.y);
-        bx = (int)(lin / gridDim.y);
-    } else if (bd.order == 2) {
-        bx = (int)(((unsigned long long)blockIdx.x * 389ull) % gridDim.x);  // 389 is prime: a permutation unless 389 | grid
-    }
+    const int bx = blockIdx.x, by = blockIdx.y;  // (batch, head) unit (or run of `upc` units) and layer of this CTA
     const LayerDev& L = bd.layers[by];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 

@@ -640,9 +640,7 @@ int kvc_compress_layers_ws(const kvc_shape* shape, int32_t n_layers, const kvc_l
         bd.off_keys = tp.off_keys;
         bd.off_stage = tp.off_stage;
         bd.upc = tp.upc;
-        bd.order = env_int("KVC_TMA_ORDER", 0);
         dim3 grid((unsigned)(((int64_t)B * H + tp.upc - 1) / tp.upc), (unsigned)n_active, 1);
-        if (bd.order == 2 && grid.x % 389 == 0) bd.order = 0;
         st = ensure_tma_attrs((const void*)fn, shape->device);
         if (st != KVC_OK) return st;
         fn<<<grid, tp.nt, tp.smem, (cudaStream_t)stream>>>(bd);

@@ -5,7 +5,8 @@ Moves EXACTLY the bytes streaming_llm_compress(4, 508) moves at BASELINE c2 — 
 {K, V} x rows [0,4) and [3588,4096) of a [32,32,4096,80] bf16 tensor into a dense [32,32,512,80] tensor — four ways:
 
   product     kvcompress.streaming_llm_compress (kvc_fused_tma_kernel, one launch for all layers)
-  order1/2    the same kernel with the other CTA -> unit mappings (lab library: KVC_TMA_ORDER)
+  order1/2    (round-2 lab runs only: the kernel with other CTA -> unit mappings, KVC_TMA_ORDER — identical results,
+              the knob has been removed; profiles/r02_stream_copy_control.json keeps the numbers)
   ldg         a plain LDG.128 / STG.128 kernel (scripts/lab/copyctl.cu), one launch per tensor, 1 / 4 CTAs per unit
   memcpy2d    cudaMemcpy2DAsync, two calls per tensor (sink rows, tail rows)
   contiguous  the same number of bytes as one dense copy (torch copy_): the copy-peak reference on this box
