@@ -19,10 +19,14 @@ CASES = [
 ]
 
 
-def tiny_model_and_ids(device="cpu"):
+ATTN_KW = dict(start_size=4, heavy_hitter_size=8, recent_size=20)   # the attention-score harness (evaluate_attention.py)
+
+
+def tiny_model_and_ids(device="cpu", attn_implementation=None):
     from transformers import GPTNeoXConfig, GPTNeoXForCausalLM
 
     torch.manual_seed(0)
-    model = GPTNeoXForCausalLM(GPTNeoXConfig(**MODEL_KW)).eval()  # fp32, head_dim 64 -> 256-byte rows
+    extra = {"attn_implementation": attn_implementation} if attn_implementation else {}
+    model = GPTNeoXForCausalLM(GPTNeoXConfig(**MODEL_KW, **extra)).eval()  # fp32, head_dim 64 -> 256-byte rows
     ids = torch.randint(0, MODEL_KW["vocab_size"], (1, TOKENS), generator=torch.Generator().manual_seed(1))
     return model.to(device), ids

@@ -45,6 +45,23 @@ def main():
         out["cases"][name] = {"nlls": r["nlls"], "lengths": r["cache_lengths"], "perplexity": r["perplexity"],
                               "final_cache_size": r["final_cache_size"]}
         print(name, r["cache_lengths"], round(r["perplexity"], 3))
+    # the attention-score harness: OUR loop (kvcompress/evaluate_attention.py) driven with the REAL reference's
+    # h2o_attention_compress and H2OAttentionManager (eager attention: the model must return its weights)
+    import kvcompress.evaluate_attention as EA
+    from kvcompress_ref.methods.h2o_attention import H2OAttentionManager as RefManager
+    from kvcompress_ref.methods.h2o_attention import h2o_attention_compress as ref_h2o_attention
+
+    eager_model, ids = H.tiny_model_and_ids(attn_implementation="eager")
+    EA.h2o_attention_compress = ref_h2o_attention
+    manager = RefManager(num_layers=H.MODEL_KW["num_hidden_layers"], num_heads=H.MODEL_KW["num_attention_heads"],
+                         device=torch.device("cpu"), **H.ATTN_KW)
+    # skip_layers=[]: with transformers 5 the eager attention mask is sized from layer 0, so every layer must keep the
+    # same number of rows (the reference's own default [0, 1] fails inside HF there)
+    r = EA.evaluate_with_attention_compression(eager_model, input_ids=ids, h2o_manager=manager, skip_layers=[],
+                                               show_progress=False, return_nlls=True, **H.ATTN_KW)
+    out["cases"]["h2o_attention"] = {"nlls": r["nlls"], "lengths": r["cache_lengths"], "perplexity": r["perplexity"],
+                                     "final_cache_size": r["final_cache_size"]}
+    print("h2o_attention", r["cache_lengths"], round(r["perplexity"], 3))
     with open(os.path.join(HERE, "harness_golden.json"), "w") as f:
         json.dump(out, f)
 

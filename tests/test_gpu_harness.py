@@ -62,3 +62,24 @@ def test_generation_metrics_both_cache_paths(model_and_ids):
         r = measure_generation_metrics(model, input_ids=ids[:, :64], compress_fn=fn, compress_kwargs=kw,
                                        max_new_tokens=24, skip_layers=H.SKIP, cache=cache)
         assert r["num_tokens"] == 24 and r["input_length"] == 64 and r["ttft"] > 0 and r["tpot"] > 0
+
+
+def test_attention_score_harness_matches_reference_golden():
+    """kvcompress/evaluate_attention.py with OUR h2o_attention_compress + manager on the B200 against the loop driven
+    with the REAL reference's on CPU (tests/golden/make_harness_golden.py): same kept rows every step -> same NLLs."""
+    from kvcompress.evaluate_attention import compare_h2o_methods, evaluate_with_attention_compression
+
+    model, ids = H.tiny_model_and_ids("cuda", attn_implementation="eager")
+    ids = ids.cuda()
+    want = GOLDEN["cases"]["h2o_attention"]
+    n0 = _engine.launch_count()
+    got = evaluate_with_attention_compression(model, input_ids=ids, skip_layers=[], show_progress=False,
+                                              return_nlls=True, **H.ATTN_KW)
+    assert _engine.launch_count() > n0, "the sm_100a library must have run"
+    assert got["cache_lengths"] == want["lengths"] and got["final_cache_size"] == want["final_cache_size"]
+    assert got["num_tokens"] == H.TOKENS - 1
+    assert max(abs(a - b) for a, b in zip(got["nlls"], want["nlls"])) < 5e-3
+    assert abs(got["perplexity"] / want["perplexity"] - 1) < 1e-3
+    rows = compare_h2o_methods(model, input_ids=ids[:, :48], max_tokens=48, heavy_hitter_sizes=[8], skip_layers=[],
+                               show_progress=False)
+    assert [r["method"] for r in rows] == ["baseline", "h2o_l2_hh8", "h2o_attn_hh8"]
