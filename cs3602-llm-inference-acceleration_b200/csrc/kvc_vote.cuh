@@ -304,49 +304,60 @@ __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __gri
         const bool row_live = (((warp & 3) * 32) & (RB - 1)) < rows_q;
         const int c_lo = (gt / RB) * RB;        // this replica's share of a tile's key columns: [c_lo, c_lo + RB)
         const int nch = RB / 16;
+        // One pass-1 tile: 16 columns at a time, running maximum and sum of exponentials of this thread's row.
+        // MASKED is a template-like compile-time switch (two separate instantiations of the lambda body): only the
+        // last one or two tiles of a pass meet the causal window or the end of the sequence, and when both cases
+        // shared one loop the compiler if-converted the mask into two compares, an add and a select per score on
+        // EVERY tile — 168 instructions per 16 columns instead of ~85 (profiles/r02_ncu_full_vote_fused_c4_b4.json).
+        auto pass1_tile = [&](int i, auto masked_tag) {
+            constexpr bool MASKED = decltype(masked_tag)::value;
+            const int key0 = i * kVoteTile;
+            tmem_ld16_async(t_lane + c_lo, va);
+#pragma unroll
+            for (int ch = 0; ch < kVoteTile / 16; ++ch) {
+                if (ch >= nch) break;  // warp-uniform
+                const int cb = c_lo + ch * 16;
+                uint32_t(&v)[16] = (ch & 1) ? vb : va;
+                tmem_ld_wait();
+                if (ch + 1 < nch) tmem_ld16_async(t_lane + cb + 16, (ch & 1) ? va : vb);
+                float cmax = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    if (MASKED) {
+                        const int key = key0 + cb + j;
+                        if (key > limit || key >= S) v[j] = 0xff800000u;
+                    }
+                    cmax = fmaxf(cmax, __uint_as_float(v[j]));
+                }
+                const float m_new = fmaxf(m_run, cmax * c2);
+                if (m_new > -INFINITY) {
+                    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        acc0 += ex2(fmaf(__uint_as_float(v[j]), c2, -m_new));
+                        acc1 += ex2(fmaf(__uint_as_float(v[j + 1]), c2, -m_new));
+                        acc2 += ex2(fmaf(__uint_as_float(v[j + 2]), c2, -m_new));
+                        acc3 += ex2(fmaf(__uint_as_float(v[j + 3]), c2, -m_new));
+                    }
+                    if (m_new != m_run) l_run *= ex2(m_run - m_new);  // the maximum settles after a few tiles
+                    l_run += (acc0 + acc1) + (acc2 + acc3);
+                    m_run = m_new;
+                }
+            }
+        };
+        const int n_plain = min(n1, P / kVoteTile);  // tiles that lie entirely inside the prefix: no mask
         int i = grp;
+        for (; i < n_plain; i += 4) {
+            mbar_wait(bar_tfull + 8 * grp, (uint32_t)((i >> 2) & 1));
+            tc_fence_after();
+            if (row_live && dbg == 0) pass1_tile(i, std::false_type{});
+            tc_fence_before();
+            mbar_arrive(bar_tempty + 8 * grp);
+        }
         for (; i < n1; i += 4) {
             mbar_wait(bar_tfull + 8 * grp, (uint32_t)((i >> 2) & 1));
             tc_fence_after();
-            if (row_live && dbg == 0) {
-                const int key0 = i * kVoteTile;
-                const bool masked = key0 + kVoteTile > P;
-                tmem_ld16_async(t_lane + c_lo, va);
-#pragma unroll
-                for (int ch = 0; ch < kVoteTile / 16; ++ch) {
-                    if (ch >= nch) break;  // warp-uniform
-                    const int cb = c_lo + ch * 16;
-                    uint32_t(&v)[16] = (ch & 1) ? vb : va;
-                    tmem_ld_wait();
-                    if (ch + 1 < nch) tmem_ld16_async(t_lane + cb + 16, (ch & 1) ? va : vb);
-                    float cmax = -INFINITY;
-                    if (masked) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) {
-                            const int key = key0 + cb + j;
-                            if (key > limit || key >= S) v[j] = 0xff800000u;
-                            cmax = fmaxf(cmax, __uint_as_float(v[j]));
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) cmax = fmaxf(cmax, __uint_as_float(v[j]));
-                    }
-                    const float m_new = fmaxf(m_run, cmax * c2);
-                    if (m_new > -INFINITY) {
-                        float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-#pragma unroll
-                        for (int j = 0; j < 16; j += 4) {
-                            acc0 += ex2(fmaf(__uint_as_float(v[j]), c2, -m_new));
-                            acc1 += ex2(fmaf(__uint_as_float(v[j + 1]), c2, -m_new));
-                            acc2 += ex2(fmaf(__uint_as_float(v[j + 2]), c2, -m_new));
-                            acc3 += ex2(fmaf(__uint_as_float(v[j + 3]), c2, -m_new));
-                        }
-                        if (m_new != m_run) l_run *= ex2(m_run - m_new);  // the maximum settles after a few tiles
-                        l_run += (acc0 + acc1) + (acc2 + acc3);
-                        m_run = m_new;
-                    }
-                }
-            }
+            if (row_live && dbg == 0) pass1_tile(i, std::true_type{});
             tc_fence_before();
             mbar_arrive(bar_tempty + 8 * grp);
         }
