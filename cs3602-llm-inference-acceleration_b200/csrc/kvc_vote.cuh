@@ -296,8 +296,9 @@ __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __gri
         const int grp = warp >> 2, gt = tid & 127;
         const uint32_t t_lane = tmem + grp * kVoteTile + ((uint32_t)((warp & 3) * 32) << 16);
         float m_run = -INFINITY, l_run = 0.f;
-        // the accumulator is read 16 columns at a time with the next 16 already in flight (two register sets):
-        // TMEM reads (64 B/clk per SM) and the ex2 pipe are floors of the same size and must overlap
+        // the accumulator is read 16 columns at a time with the next 16 already in flight (two register sets); TMEM
+        // itself is not a limit (tcgen05.ld measures ~460 B/clk/SM with 16 warps, scripts/lab/tmem_ld_bw.cu: ten
+        // times what this kernel reads), the load's latency is what the second register set hides
         uint32_t va[16], vb[16];
         const int row = gt & (RB - 1);          // query row of this TMEM lane; replica gt / RB
         const int limit = P + ((row < rows_q) ? (row % W) : 0);
