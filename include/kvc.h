@@ -174,7 +174,7 @@ int kvc_snapkv_vote(const kvc_shape* shape, int32_t n_layers, const kvc_vote_lay
  * plans[l].tail rows, and gathers K and V into io[l].k_out / v_out.  plans[l]: sink 0, sel [0, S - W), score
  * KVC_SCORE_GIVEN_SCORE; io[l].k_in / strides must be layers[l]'s keys; layers[l].votes_out is still written (the votes
  * pass through it in the cache dtype).  KVC_ERR_TOO_LARGE when the prefix keys + kept indices exceed the shared
- * memory of the key ring (~80K rows): run kvc_snapkv_vote + kvc_compress_layers_ws instead. */
+ * memory of the key ring (~70-90K rows, by head_dim): run kvc_snapkv_vote + kvc_compress_layers_ws instead. */
 int kvc_snapkv_vote_compress(const kvc_shape* shape, int32_t n_layers, const kvc_vote_layer* layers,
                              const kvc_layer_plan* plans, const kvc_layer_io* io, int32_t group, int32_t window,
                              void* stream);

@@ -188,6 +188,29 @@ def test_fused_vote_compress_equals_the_two_launch_form(B, H, G, W, S, D, keep, 
     assert all(torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) for a, b in zip(api, out))
 
 
+def test_prefix_beyond_the_fused_tail_takes_two_launches():
+    """The fused tail keeps the prefix's radix keys in the (dead) key ring: ~90K rows at head_dim 64.  Longer prefixes
+    run as vote launch + select/gather launch (workspace), same result contract."""
+    B, H, G, W, S, D, keep = 1, 1, 2, 32, 100000, 64, 512
+    gen = torch.Generator(device="cuda").manual_seed(8)
+    k = torch.randn(B, H, S, D, generator=gen, device="cuda").bfloat16()
+    v = torch.randn(B, H, S, D, generator=gen, device="cuda").bfloat16()
+    q = (1.5 * torch.randn(B, H * G, W, D, generator=gen, device="cuda")).bfloat16()
+    n0 = _engine.launch_count()
+    out = kvcompress.snapkv_lite_compress([(k, v)], observation_window=W, keep_size=keep, obs_queries=[q])
+    assert _engine.launch_count() - n0 == 2
+    votes = _engine.snapkv_votes([(k, q)], W)[0]
+    want, idx = _engine.run_plans([(k, v)], [_planner_plan(S, W, keep)], given_scores={0: votes}, return_indices=True)
+    assert torch.equal(out[0][0], want[0][0]) and torch.equal(out[0][1], want[0][1])
+    assert torch.equal(out[0][1], torch.gather(v, 2, idx[0].long().unsqueeze(-1).expand(-1, -1, -1, D)))
+
+
+def _planner_plan(S, W, keep, pk=5):
+    from kvcompress import _planner
+
+    return _planner.LayerPlan(_planner.GATHER, S, 0, 0, S - W, keep - W, W, _planner.SCORE_GIVEN_SCORE, pk)
+
+
 def test_vote_errors():
     k = torch.randn(1, 2, 300, 128, device="cuda")
     q = torch.randn(1, 8, 32, 128, device="cuda")
