@@ -997,6 +997,12 @@ static int launch_vote_tma(const kvc_shape* shape, int32_t n_layers, const kvc_v
         bd.W = window;
         bd.scale_log2e = 1.4426950408889634f / sqrtf((float)D);
         bd.pad[0] = vote_debug_mode();
+#ifdef KVC_LAB
+        {   // lab: KVC_VOTE_TIMELINE=<hex device pointer> of a [CTAs][8] int64 buffer
+            const char* tl = getenv("KVC_VOTE_TIMELINE");
+            bd.lab_timeline = (tl && *tl) ? (long long*)strtoull(tl, nullptr, 16) : nullptr;
+        }
+#endif
         for (int l = 0; l < nl; ++l) {
             const kvc_vote_layer& v = layers[l0 + l];
             VoteTmaLayerDev& d = bd.layers[l];

@@ -112,6 +112,17 @@ __device__ __forceinline__ float ex2(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// Lab build only.  KVC_VOTE_DEBUG=6: the exponentials of both passes replaced by the identity (everything but the MUFU
+// work is timed); KVC_T0 / KVC_TACC: cycles a role spends inside its mbarrier waits, per CTA, into lab_timeline.
+#ifdef KVC_LAB
+#define KVC_EX2(x) (lab_noexp ? (x) : ex2(x))
+#define KVC_T0() const long long _t0 = clock64()
+#define KVC_TACC(var) var += clock64() - _t0
+#else
+#define KVC_EX2(x) ex2(x)
+#define KVC_T0()
+#define KVC_TACC(var)
+#endif
 
 // Chunk (row r, 16-byte chunk c) of a [rows][CPR chunks] operand tile in the canonical layout: dense
 // 128-byte core matrices (8 rows x 16 B), K chunks kVoteLBO = 128 B apart, 8-row groups CPR*128 B apart.
@@ -170,6 +181,7 @@ struct VoteTmaBatchDev {
     int32_t B, H, G, W;
     float scale_log2e;
     int32_t pad[3];
+    long long* lab_timeline;  // lab build: [CTAs][8] cycle counters, or nullptr
     VoteTmaLayerDev layers[32];
 };
 
@@ -235,7 +247,16 @@ __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __gri
     const int rows_q = G * W;
     const bool no_tail = bd.pad[0] == 3;            // profiling: every stage on, tail box not loaded
     const bool one_k = bd.pad[0] == 4;              // profiling: no math, ONE K step per tile
+#ifdef KVC_LAB
+    const bool lab_noexp = bd.pad[0] == 6;          // profiling: every stage on, exp2 replaced by the identity
+    const int dbg = (no_tail || lab_noexp) ? 0 : (one_k ? 1 : bd.pad[0]);  // 1 = no math, 2 = no math, no MMA
+    long long lab_w1 = 0, lab_w2 = 0, lab_we = 0, lab_wt = 0, lab_wf = 0, lab_wb = 0, lab_tail = 0;
+    const long long lab_start = clock64();
+    unsigned long long lab_ns0;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(lab_ns0));
+#else
     const int dbg = no_tail ? 0 : (one_k ? 1 : bd.pad[0]);  // profiling: 1 = no math, 2 = no math, no MMA
+#endif
     const int RB = rows_q <= 32 ? 32 : (rows_q <= 64 ? 64 : 128);  // rows per replica block, F = 128 / RB replicas
     const bool have_lse = L.lse != nullptr;  // the caller holds the softmax denominators: no pass 1
     const int n1 = have_lse ? 0 : (S + kVoteTile - 1) / kVoteTile, n2 = (P + kVoteTile - 1) / kVoteTile;
@@ -335,10 +356,10 @@ __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __gri
                     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) {
-                        acc0 += ex2(fmaf(__uint_as_float(v[j]), c2, -m_new));
-                        acc1 += ex2(fmaf(__uint_as_float(v[j + 1]), c2, -m_new));
-                        acc2 += ex2(fmaf(__uint_as_float(v[j + 2]), c2, -m_new));
-                        acc3 += ex2(fmaf(__uint_as_float(v[j + 3]), c2, -m_new));
+                        acc0 += KVC_EX2(fmaf(__uint_as_float(v[j]), c2, -m_new));
+                        acc1 += KVC_EX2(fmaf(__uint_as_float(v[j + 1]), c2, -m_new));
+                        acc2 += KVC_EX2(fmaf(__uint_as_float(v[j + 2]), c2, -m_new));
+                        acc3 += KVC_EX2(fmaf(__uint_as_float(v[j + 3]), c2, -m_new));
                     }
                     if (m_new != m_run) l_run *= ex2(m_run - m_new);  // the maximum settles after a few tiles
                     l_run += (acc0 + acc1) + (acc2 + acc3);
@@ -349,20 +370,31 @@ __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __gri
         const int n_plain = min(n1, P / kVoteTile);  // tiles that lie entirely inside the prefix: no mask
         int i = grp;
         for (; i < n_plain; i += 4) {
-            mbar_wait(bar_tfull + 8 * grp, (uint32_t)((i >> 2) & 1));
+            {
+                KVC_T0();
+                mbar_wait(bar_tfull + 8 * grp, (uint32_t)((i >> 2) & 1));
+                KVC_TACC(lab_w1);
+            }
             tc_fence_after();
             if (row_live && dbg == 0) pass1_tile(i, std::false_type{});
             tc_fence_before();
             mbar_arrive(bar_tempty + 8 * grp);
         }
         for (; i < n1; i += 4) {
-            mbar_wait(bar_tfull + 8 * grp, (uint32_t)((i >> 2) & 1));
+            {
+                KVC_T0();
+                mbar_wait(bar_tfull + 8 * grp, (uint32_t)((i >> 2) & 1));
+                KVC_TACC(lab_w1);
+            }
             tc_fence_after();
             if (row_live && dbg == 0) pass1_tile(i, std::true_type{});
             tc_fence_before();
             mbar_arrive(bar_tempty + 8 * grp);
         }
         // ---------------- pass boundary: merge the four groups' partial statistics
+#ifdef KVC_LAB
+        const long long lab_b0 = clock64();
+#endif
         s_part[(grp * 2 + 0) * 128 + gt] = m_run;
         s_part[(grp * 2 + 1) * 128 + gt] = l_run;
         asm volatile("bar.sync 1, 512;" ::: "memory");
@@ -399,9 +431,16 @@ __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __gri
             s_m[tid] = live ? m + log2f(l) : INFINITY;
         }
         asm volatile("bar.sync 1, 512;" ::: "memory");
+#ifdef KVC_LAB
+        lab_wb = clock64() - lab_b0;
+#endif
         // ---------------- pass 2: lane = key, columns = query rows
         for (; i < n_items; i += 4) {
-            mbar_wait(bar_tfull + 8 * grp, (uint32_t)((i >> 2) & 1));
+            {
+                KVC_T0();
+                mbar_wait(bar_tfull + 8 * grp, (uint32_t)((i >> 2) & 1));
+                KVC_TACC(lab_w2);
+            }
             tc_fence_after();
             float vote0 = 0.f, vote1 = 0.f, vote2 = 0.f, vote3 = 0.f;
             if (dbg == 0) tmem_ld16_async(t_lane, va);
@@ -414,10 +453,10 @@ __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __gri
 #pragma unroll
                     for (int j = 0; j < 16; j += 4) {
                         const float4 mm = *reinterpret_cast<const float4*>(s_m + cb + j);
-                        vote0 += ex2(fmaf(__uint_as_float(v[j + 0]), c2, -mm.x));
-                        vote1 += ex2(fmaf(__uint_as_float(v[j + 1]), c2, -mm.y));
-                        vote2 += ex2(fmaf(__uint_as_float(v[j + 2]), c2, -mm.z));
-                        vote3 += ex2(fmaf(__uint_as_float(v[j + 3]), c2, -mm.w));
+                        vote0 += KVC_EX2(fmaf(__uint_as_float(v[j + 0]), c2, -mm.x));
+                        vote1 += KVC_EX2(fmaf(__uint_as_float(v[j + 1]), c2, -mm.y));
+                        vote2 += KVC_EX2(fmaf(__uint_as_float(v[j + 2]), c2, -mm.z));
+                        vote3 += KVC_EX2(fmaf(__uint_as_float(v[j + 3]), c2, -mm.w));
                     }
                 }
             }
@@ -435,7 +474,11 @@ __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __gri
             const bool tail = REM > 0 && !no_tail;  // KVC_VOTE_DEBUG=3: timing without the 32-byte tail box
             for (int i = 0; i < n_items; ++i) {
                 const int slot = i % RING;
-                mbar_wait(bar_empty + 8 * slot, (uint32_t)(((i / RING) & 1) ^ 1));  // fresh barrier: passes
+                {
+                    KVC_T0();
+                    mbar_wait(bar_empty + 8 * slot, (uint32_t)(((i / RING) & 1) ^ 1));  // fresh barrier: passes
+                    KVC_TACC(lab_we);
+                }
                 const int t = i < n1 ? i : i - n1;
                 mbar_arrive_expect_tx(bar_full + 8 * slot, tail || REM == 0 ? TILE_BYTES : KH * BOX_BYTES);
 #pragma unroll
@@ -471,8 +514,16 @@ __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __gri
         const uint32_t idesc2 = umma_idesc_f16(DT == KVC_DTYPE_BF16 ? 1 : 0, kVoteM, n2cols);
         auto issue = [&](int i, auto keys_are_rows) {
             const int slot = i % RING, acc = i & 3;
-            mbar_wait(bar_tempty + 8 * acc, (uint32_t)(((i >> 2) & 1) ^ 1));  // accumulator drained (fresh: passes)
-            mbar_wait(bar_full + 8 * slot, (uint32_t)((i / RING) & 1));    // tile landed
+            {
+                KVC_T0();
+                mbar_wait(bar_tempty + 8 * acc, (uint32_t)(((i >> 2) & 1) ^ 1));  // accumulator drained (fresh: passes)
+                KVC_TACC(lab_wt);
+            }
+            {
+                KVC_T0();
+                mbar_wait(bar_full + 8 * slot, (uint32_t)((i / RING) & 1));    // tile landed
+                KVC_TACC(lab_wf);
+            }
             tc_fence_after();
             const uint32_t slot16 = (uint32_t)(slot * TILE_BYTES) >> 4;  // start-address field counts 16-byte units
             if (dbg < 2) {
@@ -497,6 +548,20 @@ __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __gri
     }
     tc_fence_before();
     __syncthreads();
+#ifdef KVC_LAB
+    const long long lab_vote_end = clock64();
+    if (bd.lab_timeline != nullptr) {
+        long long* t = bd.lab_timeline + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * 16;
+        if (tid == 0) {
+            t[0] = lab_w1;                      // math group 0, lane 0: waiting for accumulators, pass 1
+            t[1] = lab_w2;                      // ... pass 2
+            t[2] = lab_vote_end - lab_start;    // the whole vote phase of this unit
+            t[6] = lab_wb;                      // pass boundary (merge + two 512-thread barriers)
+        }
+        if (warp == 16 && lane == 0) t[3] = lab_we;                      // producer: waiting for a free ring slot
+        if (warp == 17 && lane == 0) { t[4] = lab_wt; t[5] = lab_wf; }  // MMA issuer: waiting for accumulator / tile
+    }
+#endif
     if (warp == 17) tmem_dealloc(tmem, 512);
     if (L.k_out == nullptr) return;  // votes only (CTA-uniform)
 
@@ -537,6 +602,21 @@ __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __gri
                         smem_u32(s_ring + off_stage) + (uint32_t)(warp * 32 * RBYTES), bar_tail + 8 * warp, parity, warp,
                         nstage, lane);
         }
+#ifdef KVC_LAB
+        __syncthreads();
+        if (tid == 0 && bd.lab_timeline != nullptr) {
+            long long* t = bd.lab_timeline + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * 16;
+            unsigned long long ns1;
+            unsigned smid;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns1));
+            asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+            t[7] = clock64() - lab_vote_end;
+            t[8] = (long long)smid;
+            t[9] = (long long)lab_ns0;
+            t[10] = (long long)ns1;
+            t[11] = clock64() - lab_start;
+        }
+#endif
     }
 }
 
