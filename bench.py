@@ -610,6 +610,12 @@ def configs_table(args, device):
                      "min_frac_of_peak": min(c["frac_of_peak"] for c in per_call if c["call"] != "back_to_back")}
             if vote_flops:
                 entry["tensor_tflops"] = round(vote_flops / (total_ms / steps * 1e-3) / 1e12, 1)
+            prof = profiled_traffic(name) if B == cfg["B"] else None
+            if prof and prof.get("per_call"):  # DRAM bytes per launch from the committed ncu captures
+                for c in per_call:
+                    if c["call"] in prof["per_call"]:
+                        c["traffic"] = prof["per_call"][c["call"]]
+                entry["traffic_source"] = prof["source"]
             if B == 1:
                 entry["note"] = ("batch 1: the per-call rows time ONE call between two events on an idle GPU (launch latency "
                                  "included); the back_to_back row is the same calls queued without events")

@@ -227,6 +227,19 @@ static TmaPlan plan_tma(int dtype, int cpr, int max_region, int idx_cap, bool an
     const int force_nt = env_int("KVC_TMA_NT", 0), force_ctas = env_int("KVC_TMA_CTAS", 0),
               force_nsw = env_int("KVC_TMA_NSW", 0);
     static const int cand[][2] = {{256, 3}, {256, 2}, {512, 1}, {256, 1}};
+    // a launch of a few large units: fewer than 8 waves at the highest residency that fits (then EVERY candidate is
+    // ranked by estimated launch length, below)
+    bool few_large_units = false;
+    if (!light_traffic && units > 0 && unit_bytes >= (1 << 20) && !force_nt && !force_ctas) {
+        for (const auto& c : cand) {
+            int limit = kSmemPerSM / c[1] - 1024;
+            if (limit > kMaxSmemOptin) limit = kMaxSmemOptin;
+            if (limit - base.off_stage >= stage) {
+                few_large_units = units / ((int64_t)c[1] * kSMs) < 8;
+                break;  // candidates are listed by falling residency
+            }
+        }
+    }
     long best_score = -1;
     for (const auto& c : cand) {
         const int nt = c[0], ctas = c[1];
@@ -244,17 +257,17 @@ static TmaPlan plan_tma(int dtype, int cpr, int max_region, int idx_cap, bool an
         long score = (inflight < 131072 ? inflight : 131072) * 8 + ctas * 4096 + (inflight >> 6);
         // in-place compaction moves few bytes (scores come from stored norms): residency first, 2+ slots are enough
         if (light_traffic) score = (nsw >= 2 ? 1 : 0) * (1L << 30) + ctas * (1L << 20) + nsw;
-        if (!light_traffic && units > 0 && unit_bytes >= (1 << 20) && !force_nt && !force_ctas) {
-            // few large units: rank the candidates by the estimated length of the launch in unit-times — full waves,
-            // plus a last partial wave that costs at least ~0.35 of a full one (a lone CTA is latency-bound) — with
-            // a small handicap for lower residency (many-wave launches measure 256 x 3 about 5 % ahead of 512 x 1)
+        if (few_large_units) {
+            // rank by the estimated length of the launch: full waves plus a last partial wave that costs at least
+            // ~0.35 of a full one (a lone CTA is latency-bound), over the rate this shape sustains — bytes in flight
+            // (64 KB per SM measured 8 % behind 128 KB) and residency (3 CTAs hide a unit's select under its
+            // neighbours' HBM phases: ~5 % on many-wave launches)
             const long slots = (long)ctas * kSMs;
             const long full = (long)(units / slots), rem = (long)(units - full * slots);
-            if (full < 8) {
-                const double est = (double)full * slots + (rem > 0 ? std::max((double)rem, 0.35 * slots) : 0.0);
-                const double handicap = ctas >= 3 ? 1.00 : (ctas == 2 ? 1.02 : (nt == 512 ? 1.05 : 1.10));
-                score = (long)(1e9 / (est * handicap + 1.0)) + (1L << 40);
-            }
+            const double est = (double)full * slots + (rem > 0 ? std::max((double)rem, 0.35 * slots) : 0.0);
+            const double fill = (double)(inflight < 131072 ? inflight : 131072) / 131072.0;
+            const double rate = (0.84 + 0.16 * fill) * (ctas >= 3 ? 1.05 : (ctas == 2 ? 1.03 : (nt == 512 ? 1.0 : 0.95)));
+            score = (long)(1e12 / (est / rate + 1.0));
         }
         if (score > best_score) {
             best_score = score;
