@@ -540,6 +540,31 @@ int64_t kvc_workspace_bytes(const kvc_shape* shape, int32_t n_layers, const kvc_
     return need;
 }
 
+int kvc_launch_shape(const kvc_shape* shape, int32_t n_layers, const kvc_layer_plan* plans, int32_t out[4]) {
+    int cpr = 0;
+    int st = check_shape(shape, &cpr);
+    if (st != KVC_OK) return st;
+    if (n_layers <= 0 || !plans || !out) return KVC_ERR_INVALID_ARG;
+    if (!row_width_ok(cpr)) return KVC_ERR_UNSUPPORTED;
+    const int nl = n_layers < KVC_MAX_LAYERS_PER_LAUNCH ? n_layers : KVC_MAX_LAYERS_PER_LAUNCH;
+    int n_active, max_region, max_ksel;
+    bool any_select;
+    int64_t rows_moved;
+    chunk_stats(plans, nl, &n_active, &max_region, &max_ksel, &any_select, &rows_moved);
+    if (n_active == 0) return KVC_ERR_INVALID_ARG;
+    const int idx_cap = (max_ksel + 3) & ~3;
+    TmaPlan tp = plan_tma(shape->dtype, cpr, max_region, idx_cap, any_select, false,
+                          (int64_t)shape->batch * shape->heads * n_active, rows_moved / n_active * cpr * 16);
+    const bool ws = any_select && !onchip_plan_ok(tp, cpr, false);
+    if (ws) tp = plan_tma(shape->dtype, cpr, 0, 0, true, false);
+    if (!tp.ok) return KVC_ERR_TOO_LARGE;
+    out[0] = tp.nt;
+    out[1] = tp.ctas;
+    out[2] = tp.nsw;
+    out[3] = ws ? 1 : 0;
+    return KVC_OK;
+}
+
 int kvc_compress_layers_ws(const kvc_shape* shape, int32_t n_layers, const kvc_layer_plan* plans,
                            const kvc_layer_io* io, void* workspace, int64_t workspace_bytes, void* stream) {
     if (!shape || n_layers < 0 || (n_layers > 0 && (!plans || !io))) return KVC_ERR_INVALID_ARG;

@@ -133,6 +133,10 @@ int kvc_compress_layers(const kvc_shape* shape, int32_t n_layers, const kvc_laye
  * fits on chip.  kvc_compress_layers(...) == kvc_compress_layers_ws(..., NULL, 0, ...), which reports
  * KVC_ERR_TOO_LARGE when a workspace would have been needed. */
 int64_t kvc_workspace_bytes(const kvc_shape* shape, int32_t n_layers, const kvc_layer_plan* plans);
+/* Pure host arithmetic, for tests and profiling notes: the launch shape kvc_compress_layers would use for the first
+ * launch of these plans when it scans K — out = {threads per CTA, resident CTAs per SM, staging slots of 32 rows per
+ * CTA, 1 if keys / kept indices go to the workspace}. */
+int kvc_launch_shape(const kvc_shape* shape, int32_t n_layers, const kvc_layer_plan* plans, int32_t out[4]);
 int kvc_compress_layers_ws(const kvc_shape* shape, int32_t n_layers, const kvc_layer_plan* plans,
                            const kvc_layer_io* io, void* workspace, int64_t workspace_bytes, void* stream);
 

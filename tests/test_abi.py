@@ -82,3 +82,40 @@ def test_integration_stub_uses_the_current_struct_layouts():
         assert f'struct.Struct("{fmt}")' in text, fmt
     header = open(os.path.join(ROOT, "include", "kvc.h")).read()
     assert f"#define KVC_ABI_VERSION {_engine.KVC_ABI_VERSION}" in header
+
+
+def test_launch_shapes_of_the_baseline_configs():
+    """kvc_launch_shape is the planner's answer without a GPU: many-wave launches keep 256 threads x 3 resident CTAs,
+    32K-row regions (64 KB of keys) take one 512-thread CTA per SM, and a launch of a few large units (c1: 960 units of
+    2.75 MB) is ranked by its estimated length — one CTA per SM, a short last wave.  (A scoring slip once sent c5 to
+    256 x 2 and cost it 7 %.)"""
+    import ctypes as C
+
+    from kvcompress import _planner as P
+
+    lib = _engine.load_library()
+    lib.kvc_launch_shape.restype = C.c_int
+
+    def shape_of(B, H, D, dtype, plans):
+        rec = b"".join(_engine._PLAN.pack(p.seq_len, p.sink, p.sel_lo, p.sel_hi, p.k_sel, p.tail, p.score, p.pool_kernel)
+                       for p in plans if p.kind == P.GATHER)
+        n = sum(p.kind == P.GATHER for p in plans)
+        out = (C.c_int32 * 4)()
+        assert lib.kvc_launch_shape(_engine._SHAPE.pack(B, H, D, dtype, 0), n, rec, out) == 0
+        return tuple(out)
+
+    BF16, F32 = 2, 0
+    c2 = shape_of(32, 32, 80, BF16, P.plan_fix_size([4096] * 32, 512, 0.2, "keep_low", [0, 1]))
+    assert c2[:2] == (256, 3) and c2[3] == 0
+    c3 = shape_of(32, 32, 80, BF16, P.plan_h2o([8192] * 32, 4, 64, 444, []))
+    assert c3[:2] == (256, 3)
+    c4 = shape_of(16, 8, 128, BF16, P.plan_snapkv([32768] * 32, 32, 512, 5, []))
+    c5 = shape_of(8, 8, 128, BF16, P.plan_pyramid([32768] * 32, 512, 0.9, 64, "exponential", []))
+    c5a = shape_of(8, 8, 128, BF16, P.plan_adaptive([32768] * 32, 512, 256, 1024, 0.3, 0.9, []))
+    assert c4[:2] == c5[:2] == c5a[:2] == (512, 1) and c4[2] == 16
+    c1 = shape_of(1, 32, 80, F32, P.plan_l2([2048] * 32, 0.8, 1000, [0, 1]))
+    assert c1[:2] == (512, 1)                                   # few large units: short last wave
+    steady_b1 = shape_of(1, 32, 80, BF16, P.plan_fix_size([513] * 32, 512, 0.2, "keep_low", [0, 1]))
+    assert steady_b1[:2] == (256, 3)                            # small units: residency first
+    big = shape_of(2, 8, 128, BF16, P.plan_h2o([200000], 4, 64, 444, []))
+    assert big[3] == 1                                          # keys beyond shared memory: workspace
