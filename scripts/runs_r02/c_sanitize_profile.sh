@@ -1,5 +1,6 @@
 #!/bin/bash
 # round 2, run c: compute-sanitizer over every kernel family, the streaming_llm copy control, ncu captures
+# NOTE: the KVC_TMA_ORDER knob swept below was removed after this run (no effect measured: profiles/r02_stream_copy_control.json); compute-sanitizer turned out to be closed on this pool.
 mkdir -p gpurun_out
 export PATH=/usr/local/cuda/bin:$PATH
 python scripts/sanitize.py > gpurun_out/r02c_sanitize_plain.log 2>&1; echo "plain rc=$?" | tee -a gpurun_out/r02c_sanitize_plain.log
