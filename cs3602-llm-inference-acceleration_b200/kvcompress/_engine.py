@@ -292,14 +292,17 @@ def run_plans(kv: Sequence[Tuple[torch.Tensor, torch.Tensor]], plans, given_indi
                 offs.append(offs[-1] + sz * esz)
         plan_buf = bytearray(_PLAN.size * n)
         io_buf = bytearray(_IO.size * n)
+        host_temps = False  # pinned temporaries made here: they must outlive the launch that reads them
         for m, (li, keys, values) in enumerate(members):
             plan = ps.plans[li]
             if not _rows_ok(keys):
                 keys = keys.contiguous().pin_memory() if on_host else keys.contiguous()
                 keepalive.append(keys)
+                host_temps = host_temps or on_host
             if not _rows_ok(values):
                 values = values.contiguous().pin_memory() if on_host else values.contiguous()
                 keepalive.append(values)
+                host_temps = host_temps or on_host
             if uniform:
                 k_out, v_out = parts[2 * m], parts[2 * m + 1]
                 k_out_ptr, v_out_ptr = base + 2 * m * step, base + (2 * m + 1) * step
@@ -323,6 +326,7 @@ def run_plans(kv: Sequence[Tuple[torch.Tensor, torch.Tensor]], plans, given_indi
                     raise ValueError(f"layer {li}: indices must be a contiguous int32 [B, H, k_sel] tensor on {device}")
                 if on_host and not gi.is_pinned():
                     gi = gi.pin_memory()
+                    host_temps = True
                 idx_in_ptr = gi.data_ptr()
                 keepalive.append(gi)
             score_in_ptr = 0
@@ -333,6 +337,9 @@ def run_plans(kv: Sequence[Tuple[torch.Tensor, torch.Tensor]], plans, given_indi
                 if gs.dtype != dtype or not gs.is_contiguous() or tuple(gs.shape) != (B, H, plan.sel_hi - plan.sel_lo) \
                         or gs.device != device:
                     raise ValueError(f"layer {li}: scores must be a contiguous {dtype} [B, H, region] tensor on {device}")
+                if on_host and not gs.is_pinned():
+                    gs = gs.pin_memory()
+                    host_temps = True
                 score_in_ptr = gs.data_ptr()
                 keepalive.append(gs)
             norms_ptr, nsb, nsh = 0, 0, 0
@@ -369,9 +376,11 @@ def run_plans(kv: Sequence[Tuple[torch.Tensor, torch.Tensor]], plans, given_indi
         status = lib.kvc_compress_layers_ws(shape_rec, n, plan_bytes, bytes(io_buf), ws_ptr, ws_bytes,
                                             ctypes.c_void_p(_stream_ptr(run_device)))
         _check(status, "kvc_compress_layers")
-        if on_host and not non_blocking and not to_device:
+        if on_host and (host_temps or not (non_blocking or to_device)):
             # host tensors are read by the caller with plain loads: finish before returning, as the reference's
-            # (synchronous) CPU path does; non_blocking=True leaves that to the caller (tensor.to(..., non_blocking=True))
+            # (synchronous) CPU path does; non_blocking=True leaves that to the caller (tensor.to(..., non_blocking=True)).
+            # Pinned temporaries (re-laid-out inputs, re-pinned indices) are not stream-ordered like device memory: the
+            # launch that reads them has to finish before they go back to the host allocator.
             torch.cuda.current_stream(run_device).synchronize()
     if return_indices:
         return out, indices

@@ -242,6 +242,7 @@ class KVSlabCache:
         slab_buf = bytearray(_SLAB.size * len(items))
         rows_buf = bytearray(_ROWS.size * len(items))
         keep = []
+        host_temps = False  # pinned temporaries are not stream-ordered: the launch must finish before they are freed
         dt, dev, want = self.dtype, self.device, None
         for m, (l, keys, values) in enumerate(items):
             shape = keys.shape
@@ -254,8 +255,10 @@ class KVSlabCache:
                 self._check_new(keys, values, l)
                 want = None
             if not _engine._rows_ok(keys):
+                host_temps = host_temps or not keys.is_cuda
                 keys = keys.contiguous() if keys.is_cuda else keys.contiguous().pin_memory()
             if not _engine._rows_ok(values):
+                host_temps = host_temps or not values.is_cuda
                 values = values.contiguous() if values.is_cuda else values.contiguous().pin_memory()
             keep.append((keys, values))
             ks, vs = keys.stride(), values.stride()
@@ -267,6 +270,8 @@ class KVSlabCache:
         _engine._check(status, "kvc_slab_append")
         for l, keys, _ in items:
             self.lengths[l] += keys.size(2)
+        if host_temps and not self.pinned:
+            torch.cuda.current_stream(self.device).synchronize()
         self._finish()
 
     def update(self, key_states: torch.Tensor, value_states: torch.Tensor, layer_idx: int, cache_kwargs=None):
@@ -290,10 +295,13 @@ class KVSlabCache:
             self._check_new(key_states, value_states, layer_idx)
         if T == 0:
             return self[layer_idx]
+        host_temps = False
         if not _engine._rows_ok(key_states):
-            key_states = key_states.contiguous()
+            host_temps = host_temps or not key_states.is_cuda
+            key_states = key_states.contiguous() if key_states.is_cuda else key_states.contiguous().pin_memory()
         if not _engine._rows_ok(value_states):
-            value_states = value_states.contiguous()
+            host_temps = host_temps or not value_states.is_cuda
+            value_states = value_states.contiguous() if value_states.is_cuda else value_states.contiguous().pin_memory()
         ks, vs = key_states.stride(), value_states.stride()
         rows = _ROWS.pack(key_states.data_ptr(), value_states.data_ptr(), ks[0], ks[1], ks[2], vs[0], vs[1], vs[2], n, T)
         if self._lib is None:
@@ -302,6 +310,8 @@ class KVSlabCache:
         if status:
             _engine._check(status, "kvc_slab_append")
         self.lengths[layer_idx] = n + T
+        if host_temps and not self.pinned:
+            torch.cuda.current_stream(self.device).synchronize()
         if self.pinned:
             self._finish()
         return self._k_layers[layer_idx].narrow(2, 0, n + T), self._v_layers[layer_idx].narrow(2, 0, n + T)
@@ -322,8 +332,12 @@ class KVSlabCache:
         T = k_new.size(3)
         if max(self.lengths) + T > self.capacity:
             raise ValueError(f"{max(self.lengths)} + {T} rows exceed the slab capacity {self.capacity}")
+        host_temps = False
         if not (_engine._rows_ok(k_new[0]) and _engine._rows_ok(v_new[0])):
+            host_temps = not k_new.is_cuda
             k_new, v_new = k_new.contiguous(), v_new.contiguous()
+            if host_temps:  # .contiguous() of a pinned tensor is pageable: the GPU cannot read it
+                k_new, v_new = k_new.pin_memory(), v_new.pin_memory()
         ks, vs, esz = k_new.stride(), v_new.stride(), k_new.element_size()
         kp, vp = k_new.data_ptr(), v_new.data_ptr()
         rows_buf = bytearray(_ROWS.size * self.num_layers)
@@ -334,6 +348,8 @@ class KVSlabCache:
                                                         ctypes.c_void_p(_engine._stream_ptr(self.device)))
         _engine._check(status, "kvc_slab_append")
         self.lengths = [n + T for n in self.lengths]
+        if host_temps and not self.pinned:
+            torch.cuda.current_stream(self.device).synchronize()
         self._finish()
         return self
 

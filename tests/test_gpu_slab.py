@@ -261,6 +261,36 @@ def test_pinned_slab_equals_device_slab_equals_functions(method, kwargs, dtype, 
             assert torch.equal(host[li][0].cuda(), dev[li][0]) and torch.equal(host.key_norms(li).cuda(), dev.key_norms(li))
 
 
+def test_host_rows_the_kernels_cannot_read_in_place_are_re_pinned():
+    """Pinned host rows whose layout the kernels cannot read in place (last dimension not dense) are re-laid-out into a
+    PINNED temporary (``.contiguous()`` alone gives pageable memory the GPU cannot reach) and the launch finishes before
+    that temporary is released — on a device slab's append paths and on the functions' ``non_blocking`` / ``output_device`` forms."""
+    L, B, H, S, D = 2, 2, 3, 300, 80
+    gen = torch.Generator(device="cuda").manual_seed(11)
+    kv = [rand_rows(B, H, S, D, torch.bfloat16, gen) for _ in range(L)]
+    # [B,H,D,S] storage viewed as [B,H,S,D]: stride(3) != 1
+    odd = [tuple(t.cpu().transpose(2, 3).contiguous().pin_memory().transpose(2, 3) for t in pair) for pair in kv]
+    assert odd[0][0].is_pinned() and odd[0][0].stride(3) != 1
+    dev = KVSlabCache(L, B, H, D, capacity=S + 8, dtype=torch.bfloat16)
+    dev.append(odd)                                   # every layer in one launch, from host temporaries
+    for l in range(L):
+        assert torch.equal(dev[l][0], kv[l][0]) and torch.equal(dev[l][1], kv[l][1])
+        assert torch.equal(dev.key_norms(l), torch.norm(kv[l][0], p=2, dim=-1))
+    one = [tuple(t.cpu().transpose(2, 3).contiguous().pin_memory().transpose(2, 3) for t in rand_rows(B, H, 1, D, torch.bfloat16, gen))
+           for _ in range(L)]
+    for l in range(L):
+        k_all, _ = dev.update(one[l][0], one[l][1], l)  # the per-layer HF path
+        assert torch.equal(k_all[:, :, -1:], one[l][0].cuda())
+    kw = dict(fix_kv_size=64, keep_ratio=0.25, skip_layers=[])
+    want = kvcompress.fix_size_l2_compress(kv, **kw)
+    queued = kvcompress.fix_size_l2_compress(odd, non_blocking=True, **kw)
+    fetched = kvcompress.fix_size_l2_compress(odd, output_device="cuda", **kw)
+    torch.cuda.synchronize()
+    for l in range(L):
+        assert torch.equal(queued[l][0].cuda(), want[l][0]) and torch.equal(queued[l][1].cuda(), want[l][1])
+        assert torch.equal(fetched[l][0], want[l][0]) and torch.equal(fetched[l][1], want[l][1])
+
+
 def test_stored_norms_replace_the_scan_bytes():
     """With stored norms no K row of the selection region is read for scoring: poison every K row that is NOT kept
     after recording the norms — the function must still return the rows the scan would have kept."""
