@@ -249,7 +249,9 @@ __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __gri
     const bool one_k = bd.pad[0] == 4;              // profiling: no math, ONE K step per tile
 #ifdef KVC_LAB
     const bool lab_noexp = bd.pad[0] == 6;          // profiling: every stage on, exp2 replaced by the identity
-    const int dbg = (no_tail || lab_noexp) ? 0 : (one_k ? 1 : bd.pad[0]);  // 1 = no math, 2 = no math, no MMA
+    const bool lab_l2_p2 = bd.pad[0] == 7;          // profiling: pass 2 re-reads 8 tiles that stay in L2 (no HBM traffic)
+    const bool lab_l2_all = bd.pad[0] == 8;         // profiling: both passes read those 8 tiles
+    const int dbg = (no_tail || lab_noexp || lab_l2_p2 || lab_l2_all) ? 0 : (one_k ? 1 : bd.pad[0]);  // 1 = no math, 2 = no math, no MMA
     long long lab_w1 = 0, lab_w2 = 0, lab_we = 0, lab_wt = 0, lab_wf = 0, lab_wb = 0, lab_tail = 0;
     const long long lab_start = clock64();
     unsigned long long lab_ns0;
@@ -479,7 +481,11 @@ __global__ void __launch_bounds__(576, 1) kvc_snapkv_vote_tma_kernel(const __gri
                     mbar_wait(bar_empty + 8 * slot, (uint32_t)(((i / RING) & 1) ^ 1));  // fresh barrier: passes
                     KVC_TACC(lab_we);
                 }
+#ifdef KVC_LAB
+                const int t = i < n1 ? (lab_l2_all ? (i & 7) : i) : ((lab_l2_p2 || lab_l2_all) ? ((i - n1) & 7) : i - n1);
+#else
                 const int t = i < n1 ? i : i - n1;
+#endif
                 mbar_arrive_expect_tx(bar_full + 8 * slot, tail || REM == 0 ? TILE_BYTES : KH * BOX_BYTES);
 #pragma unroll
                 for (int kh = 0; kh < KH; ++kh)  // rows beyond S are zero-filled by the TMA unit
