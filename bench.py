@@ -104,6 +104,8 @@ def parse_args():
     ap.add_argument("--no-strong", action="store_true", help="skip the strong-scaling section (global c3 / c5 jobs)")
     ap.add_argument("--no-eager", action="store_true", help="skip the reference-torch comparator legs")
     ap.add_argument("--table-steps", type=int, default=5, help="timed steps per entry of the configs table")
+    ap.add_argument("--sustain-s", type=float, default=1.5,
+                    help="configs table, c4 / c4_vote / c4_vote_lse: seconds of back-to-back calls for the sustained row")
     ap.add_argument("--e2e-slab", type=int, default=8, help="streams per host<->device slab in the e2e leg")
     ap.add_argument("--cpu-sample-batch", type=int, default=0,
                     help="streams in the CPU sample (0: enough (b,h) rows to occupy every host thread, at most 8)")
@@ -494,7 +496,7 @@ def vote_inputs(cfg, B, kv, device):
     return extra, flops
 
 
-def time_calls(cfg, B, kv, steps, warmup, device, barrier=None, sampler=None, back_to_back=0):
+def time_calls(cfg, B, kv, steps, warmup, device, barrier=None, sampler=None, back_to_back=0, sustain_s=0.0):
     """`steps` timed passes of the config's calls on `kv` (CUDA events on torch's current stream = the launch stream).
     Returns (total_ms, per_call list of dicts, launches, vote_flops)."""
     import torch
@@ -574,6 +576,31 @@ def time_calls(cfg, B, kv, steps, warmup, device, barrier=None, sampler=None, ba
                          "gbs": round(sum(per_call_bytes) / len(fns) / dev_us / 1e3, 1),
                          "frac_of_peak": round(sum(per_call_bytes) / len(fns) / dev_us / 1e3 / peak, 4),
                          "us_mean": round(dev_us, 1), "us_min": round(dev_us, 1), "algorithmic_bytes": sum(per_call_bytes) // len(fns)})
+    if sustain_s > 0:
+        # the timed steps above are a burst of a few calls; a kernel that needs SM cycles (the vote) slows down once
+        # the board settles at its power limit: the same calls back to back for `sustain_s` seconds, NVML beside them
+        torch.cuda.synchronize()
+        smp = ClockSampler(device.index or 0, period_s=0.005)
+        smp.start()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0, n = time.perf_counter(), 0
+        a.record()
+        while time.perf_counter() - t0 < sustain_s:
+            for _ in range(4):
+                one_step()
+            n += 4
+            torch.cuda.synchronize()
+        b.record()
+        torch.cuda.synchronize()
+        clk = smp.stop()
+        dev_us = a.elapsed_time(b) * 1e3 / (n * len(fns))
+        per_call.append({"call": "sustained", "calls": n * len(fns), "seconds": round(time.perf_counter() - t0, 2),
+                         "us_mean": round(dev_us, 1), "us_min": round(dev_us, 1),
+                         "algorithmic_bytes": sum(per_call_bytes) // len(fns),
+                         "gbs": round(sum(per_call_bytes) / len(fns) / dev_us / 1e3, 1),
+                         "frac_of_peak": round(sum(per_call_bytes) / len(fns) / dev_us / 1e3 / peak, 4),
+                         "sm_mhz": clk.get("sm_mhz"), "sm_mhz_min": clk.get("sm_mhz_min"),
+                         "power_w_max": clk.get("power_w_max"), "clock_reasons": clk.get("reasons")})
     return total_ms, per_call, launches, vote_flops, wall_ms
 
 
@@ -585,6 +612,7 @@ def configs_table(args, device):
     table = {}
     order = [("c2_steady", None), ("c2_steady_b1", ("c2_steady", 1)), ("c1", None), ("c3", None), ("c5", None),
              ("c4", None), ("c4_vote", None), ("c4_vote_lse", None), ("c2_vote", None)]
+    sustained = ("c4", "c4_vote", "c4_vote_lse")  # measured LAST: seconds at the power limit would colour later bursts
     kv, kv_key = None, None
     steps = max(2, args.table_steps)
     for name, alias in order:
@@ -600,14 +628,15 @@ def configs_table(args, device):
                 kv = make_cache(cfg, B, device, seed=4321)
                 kv_key = key
             sampler = ClockSampler(device.index or 0)
-            total_ms, per_call, launches, vote_flops, wall_ms = time_calls(cfg, B, kv, steps, 2, device, None, sampler,
-                                                                            back_to_back=50 if B == 1 else 0)
+            total_ms, per_call, launches, vote_flops, wall_ms = time_calls(
+                cfg, B, kv, steps, 2, device, None, sampler, back_to_back=50 if B == 1 else 0)
             clk = sampler.stop()
             entry = {"workload": workload_config(cfg, base, B, 1)["workload"], "steps": steps,
                      "sm_mhz": clk.get("sm_mhz"), "clock_reasons": clk.get("reasons"),
                      "ms_per_step": round(total_ms / steps, 4), "wall_ms_per_step": round(wall_ms / steps, 4),
                      "per_call": per_call, "gpu_launches": launches,
-                     "min_frac_of_peak": min(c["frac_of_peak"] for c in per_call if c["call"] != "back_to_back")}
+                     "min_frac_of_peak": min(c["frac_of_peak"] for c in per_call
+                                             if c["call"] not in ("back_to_back", "sustained"))}
             if vote_flops:
                 entry["tensor_tflops"] = round(vote_flops / (total_ms / steps * 1e-3) / 1e12, 1)
             prof = profiled_traffic(name) if B == cfg["B"] else None
@@ -625,6 +654,22 @@ def configs_table(args, device):
             torch.cuda.empty_cache()
         entry["seconds_incl_setup"] = round(time.perf_counter() - t0, 1)
         table[name] = entry
+    if args.sustain_s > 0:
+        for name in sustained:  # the three share one cache
+            cfg = dict(CONFIGS[name])
+            if "error" in table.get(name, {"error": 1}):
+                continue
+            try:
+                key = (cfg["model_shape"], cfg["B"], cfg["S"], cfg["dtype"])
+                if key != kv_key:
+                    kv = None
+                    torch.cuda.empty_cache()
+                    kv = make_cache(cfg, cfg["B"], device, seed=4321)
+                    kv_key = key
+                _, rows, _, _, _ = time_calls(cfg, cfg["B"], kv, 1, 1, device, None, None, sustain_s=args.sustain_s)
+                table[name]["per_call"] += [r for r in rows if r["call"] == "sustained"]
+            except Exception as exc:
+                table[name]["sustained_error"] = repr(exc)[:300]
     kv = None
     torch.cuda.empty_cache()
     return table
