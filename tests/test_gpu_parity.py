@@ -688,3 +688,45 @@ def test_calls_on_another_gpu_leave_the_current_device_alone():
     slab = kvcompress.KVSlabCache.from_legacy_cache(kv, capacity=800)
     slab.compress_("h2o_l2")
     assert torch.cuda.current_device() == 0 and slab.device.index == 1
+
+
+# ----------------------------------------------------------------------------------------------
+# Random calls (the generator tests/test_oracle_live_reference.py runs against the live reference on CPU): random
+# method, arguments, skip lists, ragged per-layer lengths, fp32 / bf16, continuous and tie-heavy keys.
+@pytest.mark.parametrize("seed", range(32))
+def test_random_calls_match_the_oracle(seed):
+    from test_oracle_live_reference import draw_call
+
+    rng = np.random.default_rng(9000 + seed)   # the same calls the live-reference test checks the oracle on
+    for _ in range(4):
+        method, kw, seq_lens, B, H, D, dtype, style = draw_call(rng)
+        layers = cases.make_cache(int(rng.integers(0, 1 << 30)), seq_lens, B, H, D, dtype, style)
+        what = (seed, method, kw, seq_lens, B, H, D, dtype, style)
+        kv = kv_to_torch(layers, dtype)
+        results = O.METHODS[method](layers, dtype, **kw)
+        n0 = _engine.launch_count()
+        out = kvcompress.get_compress_fn(method)(kv, **kw)
+        plans = plan_for(method, seq_lens, kw)
+        n_gather = sum(1 for p in plans if p.kind == P.GATHER)
+        assert _engine.launch_count() - n0 == (1 if n_gather else 0), what
+        assert [k.size(2) for k, _ in out] == O.out_lengths(layers, results), what
+        out2, idx = _engine.run_plans(kv, plans, return_indices=True)
+        for li, res in enumerate(results):
+            k_in, v_in = kv[li]
+            if res.untouched:
+                assert out[li][0] is k_in and out[li][1] is v_in, (what, li)
+                continue
+            aliases = out[li][0].untyped_storage().data_ptr() == k_in.untyped_storage().data_ptr()
+            assert aliases == bool(res.is_view), (what, li)   # tail-only results alias the input like the reference's
+            assert res.is_view or (out[li][0].is_contiguous() and out[li][1].is_contiguous()), (what, li)
+            if plans[li].kind != P.GATHER:
+                rows = torch.from_numpy(res.rows).cuda()
+                assert torch.equal(out[li][0], gather_rows(k_in, rows)) and torch.equal(out[li][1], gather_rows(v_in, rows))
+                continue
+            rows = idx[li]
+            assert torch.equal(out2[li][0], gather_rows(k_in, rows)) and torch.equal(out2[li][1], gather_rows(v_in, rows))
+            assert torch.equal(out2[li][0], out[li][0]) and torch.equal(out2[li][1], out[li][1]), (what, li)
+            info = O.check_layer(layers[li][0], dtype, res, rows.cpu().numpy())
+            assert info["valid"], (what, li, info)
+            if dtype == "f32" and style != "ties":
+                assert info["identical_heads"] == info["heads"], (what, li, info)
