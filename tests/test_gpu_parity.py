@@ -730,3 +730,41 @@ def test_random_calls_match_the_oracle(seed):
             assert info["valid"], (what, li, info)
             if dtype == "f32" and style != "ties":
                 assert info["identical_heads"] == info["heads"], (what, li, info)
+
+
+@pytest.mark.parametrize("method,kw", [
+    ("fix_size_l2", dict(fix_kv_size=128, keep_ratio=0.2, skip_layers=[0])),
+    ("h2o_l2", dict(start_size=4, heavy_hitter_size=32, recent_size=92)),
+    ("streaming_llm", dict(start_size=4, recent_size=124)),
+    ("snapkv_lite", dict(observation_window=16, keep_size=128)),
+])
+def test_function_call_replays_from_a_cuda_graph(method, kw):
+    """The drop-in functions enqueue one launch on the current stream and synchronise nothing, so a steady-state call
+    (same shapes every step, evaluate.py:154-166) can be captured with torch.cuda.graph and replayed: the replay reads
+    the caches' CURRENT contents and writes the same output tensors."""
+    L, B, H, S, D = 3, 2, 4, 129, 80
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    kv = [(torch.randn(B, H, S, D, generator=gen, device="cuda").bfloat16(),
+           torch.randn(B, H, S, D, generator=gen, device="cuda").bfloat16()) for _ in range(L)]
+    fn = kvcompress.get_compress_fn(method)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):          # warm-up off the capture: library attributes, plan cache
+        fn(kv, **kw)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    n0 = _engine.launch_count()
+    with torch.cuda.graph(graph):
+        out = fn(kv, **kw)
+    assert _engine.launch_count() - n0 == 1
+    for step in range(3):
+        for k, v in kv:                    # new cache contents in the same tensors
+            k.copy_(torch.randn(B, H, S, D, generator=gen, device="cuda") * (1 + step))
+            v.copy_(torch.randn(B, H, S, D, generator=gen, device="cuda"))
+        graph.replay()
+        want = fn(kv, **kw)
+        for li in range(L):
+            if want[li][0] is kv[li][0]:
+                assert out[li][0] is kv[li][0]
+                continue
+            assert torch.equal(out[li][0], want[li][0]) and torch.equal(out[li][1], want[li][1]), (method, step, li)
