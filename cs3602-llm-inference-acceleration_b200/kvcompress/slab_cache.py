@@ -381,6 +381,16 @@ class KVSlabCache:
                      for li, p in enumerate(plans) if p.kind == P.GATHER and p.score == P.SCORE_GIVEN_INDEX}
         return self.apply_plans_(plans, given_indices=given, return_indices=return_indices)
 
+    def evict_for_space_(self, num_coming: int, start_size: int = 4, recent_size: int = 508,
+                         skip_layers: Sequence[int] = (), return_indices: bool = False):
+        """``evict_for_space`` (reference streaming_llm.py:114-170) in place: make room for ``num_coming`` rows before
+        a prefill chunk is appended — sinks stay where they are, the shortened recent window slides down behind them."""
+        from .methods._common import cached_plans
+
+        plans = cached_plans(P.plan_evict_for_space, self.lengths, num_coming, start_size, recent_size,
+                             skip_layers=skip_layers)
+        return self.apply_plans_(plans, return_indices=return_indices)
+
     def apply_plans_(self, plans, given_indices: Optional[dict] = None, return_indices: bool = False):
         ps = plans if isinstance(plans, _engine.PlanSet) else _engine.PlanSet(plans)
         if len(ps) != self.num_layers:

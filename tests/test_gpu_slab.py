@@ -261,6 +261,30 @@ def test_pinned_slab_equals_device_slab_equals_functions(method, kwargs, dtype, 
             assert torch.equal(host[li][0].cuda(), dev[li][0]) and torch.equal(host.key_norms(li).cuda(), dev.key_norms(li))
 
 
+def test_chunked_prefill_evicts_in_place_like_the_function():
+    """evict_for_space before every prefill chunk (reference streaming_llm.py:114-170), on the slab in place and with
+    the function on plain (K, V) lists: the same cache after every chunk."""
+    L, B, H, D, chunk = 3, 2, 3, 80, 48
+    gen = torch.Generator(device="cuda").manual_seed(21)
+    slab = KVSlabCache(L, B, H, D, capacity=160, dtype=torch.bfloat16)
+    kv = None
+    for step in range(7):
+        new = [rand_rows(B, H, chunk, D, torch.bfloat16, gen) for _ in range(L)]
+        if kv is not None:
+            kv = kvcompress.evict_for_space(kv, chunk, start_size=4, recent_size=100, skip_layers=[1] if step < 3 else [])
+            n0 = _engine.launch_count()
+            slab.evict_for_space_(chunk, start_size=4, recent_size=100, skip_layers=[1] if step < 3 else [])
+            assert _engine.launch_count() - n0 <= 1
+            if step >= 3:   # layer 1 was skipped for three chunks (it grew); from now on it is evicted like the others
+                assert slab.lengths[1] + chunk <= 160
+        kv = new if kv is None else [(torch.cat([k, nk], 2), torch.cat([v, nv], 2)) for (k, v), (nk, nv) in zip(kv, new)]
+        slab.append(new)
+        assert slab.lengths == [k.size(2) for k, _ in kv], step
+        for l in range(L):
+            assert torch.equal(slab[l][0], kv[l][0]) and torch.equal(slab[l][1], kv[l][1]), (step, l)
+            assert torch.equal(slab.key_norms(l), torch.norm(kv[l][0], p=2, dim=-1)), (step, l)
+
+
 def test_host_rows_the_kernels_cannot_read_in_place_are_re_pinned():
     """Pinned host rows whose layout the kernels cannot read in place (last dimension not dense) are re-laid-out into a
     PINNED temporary (``.contiguous()`` alone gives pageable memory the GPU cannot reach) and the launch finishes before
