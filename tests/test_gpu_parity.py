@@ -556,6 +556,10 @@ def test_full_baseline_size_checksums(name, calls, L, B, H, S, D):
     """Whole-job properties at the sizes bench.py runs: every output row is an input row (checksum of rows
     against the gather by the reported indices), sinks / tails are where the plan says, indices ascend,
     the kept rows are the lowest-norm rows, and a second call on the result is the identity."""
+    import gc
+
+    gc.collect()
+    torch.cuda.empty_cache()   # blocks cached by earlier tests are not "free" to mem_get_info
     free, _ = torch.cuda.mem_get_info()
     need = 2 * L * B * H * S * D * 2 * 1.25
     if free < need:
