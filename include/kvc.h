@@ -33,7 +33,9 @@
  * space (cudaHostAlloc / cudaHostRegister under UVA): an offloaded cache is then read
  * and written in place over PCIe, each needed row crossing the link once per read.
  * Every entry point runs on shape->device and restores the calling thread's current CUDA
- * device before it returns.  The library reads no environment variable.
+ * device before it returns.  The library reads no environment variable.  Each entry point that
+ * launches opens an NVTX range named after itself (kvc_compress_layers_ws, kvc_slab_append, ...),
+ * so profilers attribute every kernel to the C-ABI call that enqueued it.
  */
 #ifndef KVC_H_
 #define KVC_H_

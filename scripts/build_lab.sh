@@ -13,5 +13,5 @@ for part in 1 2 4 8 16 32; do
   pids+=($!)
 done
 for p in "${pids[@]}"; do wait $p; done
-nvcc -shared -gencode arch=compute_100a,code=sm_100a -o "$CSRC/libkvc_sm100a_lab.so" "$CSRC"/build_lab/kvc_part*.o
+nvcc -shared -gencode arch=compute_100a,code=sm_100a -o "$CSRC/libkvc_sm100a_lab.so" "$CSRC"/build_lab/kvc_part{1,2,4,8,16,32}.o -ldl
 echo "built $CSRC/libkvc_sm100a_lab.so"
