@@ -155,8 +155,9 @@ public:
             int64_t off = 0;
             for (size_t m = 0; m < n; ++m) {
                 const int64_t C = out_len(plans_[m]), sz = B * H * C * D;
-                k_out[m] = flat.narrow(0, off, sz).view({B, H, C, D});
-                v_out[m] = flat.narrow(0, off + sz, sz).view({B, H, C, D});
+                // one view op per tensor (narrow + view would be two): per-layer budgets make 2 x layers of them per call
+                k_out[m] = flat.as_strided({B, H, C, D}, {H * C * D, C * D, D, 1}, off);
+                v_out[m] = flat.as_strided({B, H, C, D}, {H * C * D, C * D, D, 1}, off + sz);
                 off += 2 * sz;
             }
         }
