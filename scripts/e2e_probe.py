@@ -75,6 +75,27 @@ def main():
         res["queued_step_ms"] = round((time.perf_counter() - t0) / 3 * 1e3, 2)
         print("queued step", res["queued_step_ms"], flush=True)
 
+    # two streams: the pure-copy call and the scattered-row call in flight together (do they fill each other's gaps on
+    # the link, or is the link simply full?)
+    if "non_blocking" in kvcompress.streaming_llm_compress.__doc__:
+        s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+        def two_stream_step():
+            outs = []
+            for _ in range(4):
+                with torch.cuda.stream(s1):
+                    outs.append(kvcompress.get_compress_fn(calls[0][0])(slab, non_blocking=True, **calls[0][1]))
+                with torch.cuda.stream(s2):
+                    outs.append(kvcompress.get_compress_fn(calls[1][0])(slab, non_blocking=True, **calls[1][1]))
+            torch.cuda.synchronize()
+            return outs
+        two_stream_step()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            two_stream_step()
+        res["two_stream_step_ms"] = round((time.perf_counter() - t0) / 3 * 1e3, 2)
+        print("two-stream step", res["two_stream_step_ms"], flush=True)
+
     def blocking_step():
         for _ in range(4):
             for name, kw in calls:
