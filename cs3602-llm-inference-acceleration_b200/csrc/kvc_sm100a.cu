@@ -195,6 +195,7 @@ constexpr int kTmaHead = kMiscInts * 4 + 32 * 8;  // misc scalars + one mbarrier
 struct TmaPlan {
     bool ok = false;
     int nt = 0, ctas = 0, nsw = 0, upc = 1;
+    int slide_slots = 0;  // in-place plans: slots the slide can use (planned slots + the dead key array)
     int off_hist = 0, off_idx = 0, off_keys = 0, off_stage = 0;
     size_t smem = 0;
 };
@@ -222,8 +223,13 @@ static inline int vote_debug_mode() { return 0; }
 // resident CTAs per SM that wave is a third of the whole launch, with one 512-thread CTA per SM a seventh
 // (measured: 446 -> 402 us, 0.90 -> 1.00 of the copy peak, profiles/r02_plan_sweep_few_units.json).  Small units
 // (decode steady state) and launches of many waves keep the residency-first choice.
+// `in_place` (kvc_slab_compress with the keys on chip): the kept-index list is only written by the select's last pass,
+// after the histogram's last reader, so it ALIASES the histogram (k_sel <= 2048); and the slide runs after the select,
+// when the key array is dead and serves as staging, so the plan may hold NO slot of its own.  At 32K bf16 rows that is
+// 72.7 KB instead of 84.6 KB per CTA: three resident CTAs per SM instead of two (one unit's select and slide rounds
+// hide under its neighbours').
 static TmaPlan plan_tma(int dtype, int cpr, int max_region, int idx_cap, bool any_select, bool light_traffic = false,
-                        int64_t units = 0, int64_t unit_bytes = 0) {
+                        int64_t units = 0, int64_t unit_bytes = 0, bool in_place = false) {
     TmaPlan best;
     const int stage = 32 * cpr * 16;
     int end = kTmaHead;
@@ -233,9 +239,14 @@ static TmaPlan plan_tma(int dtype, int cpr, int max_region, int idx_cap, bool an
         base.off_hist = kTmaHead;
         base.off_idx = base.off_hist + kHistBins * 4;
         base.off_keys = base.off_idx + ((idx_cap * 4 + 15) & ~15);
+        if (in_place && idx_cap <= kHistBins) {
+            base.off_idx = base.off_hist;
+            base.off_keys = base.off_hist + kHistBins * 4;
+        }
         end = base.off_keys + (int)(((size_t)max_region * key_bytes(dtype) + 15) & ~(size_t)15);
     }
     base.off_stage = (end + 127) & ~127;
+    const int dead_keys = in_place ? base.off_stage - ((base.off_keys + 127) & ~127) : 0;  // bytes the slide inherits
     const int force_nt = env_int("KVC_TMA_NT", 0), force_ctas = env_int("KVC_TMA_CTAS", 0),
               force_nsw = env_int("KVC_TMA_NSW", 0);
     static const int cand[][2] = {{256, 3}, {256, 2}, {512, 1}, {256, 1}};
@@ -260,15 +271,18 @@ static TmaPlan plan_tma(int dtype, int cpr, int max_region, int idx_cap, bool an
         int limit = kSmemPerSM / ctas - 1024;
         if (limit > kMaxSmemOptin) limit = kMaxSmemOptin;
         const int avail = limit - base.off_stage;
-        if (avail < stage) continue;
+        if (avail < (in_place ? 0 : stage)) continue;
         int nsw = avail / stage;
         if (nsw > nt / 32) nsw = nt / 32;
+        int slide = (dead_keys + nsw * stage) / stage;  // what the slab kernel computes for its rounds
+        if (slide > nt / 32) slide = nt / 32;
+        if (in_place && slide < 1) continue;
         if (force_nsw && force_nsw < nsw) nsw = force_nsw;
         const long inflight = (long)ctas * nsw * stage;
         // saturating score: bytes in flight up to 128 KB matter most (measured: c5 +8% from 64 -> 128 KB), then residency
         long score = (inflight < 131072 ? inflight : 131072) * 8 + ctas * 4096 + (inflight >> 6);
         // in-place compaction moves few bytes (scores come from stored norms): residency first, 2+ slots are enough
-        if (light_traffic) score = (nsw >= 2 ? 1 : 0) * (1L << 30) + ctas * (1L << 20) + nsw;
+        if (light_traffic) score = ((in_place ? slide : nsw) >= 2 ? 1 : 0) * (1L << 30) + ctas * (1L << 20) + (in_place ? slide : nsw);
         if (few_large_units) {
             // rank by the estimated length of the launch: full waves plus a last partial wave that costs at least
             // ~0.35 of a full one (a lone CTA is latency-bound), over the rate this shape sustains — bytes in flight
@@ -288,6 +302,7 @@ static TmaPlan plan_tma(int dtype, int cpr, int max_region, int idx_cap, bool an
             best.nt = nt;
             best.ctas = ctas;
             best.nsw = nsw;
+            best.slide_slots = in_place ? slide : nsw;
             best.smem = (size_t)base.off_stage + (size_t)nsw * stage;
         }
     }
@@ -310,7 +325,7 @@ static WsLayout ws_layout(int dtype, int max_region, int idx_cap) {
 // or has at least two slots (in-place compaction, whose traffic is light).
 static bool onchip_plan_ok(const TmaPlan& tp, int cpr, bool light_traffic) {
     if (!tp.ok) return false;
-    if (light_traffic) return tp.nsw >= 2;
+    if (light_traffic) return tp.slide_slots >= 2;
     return (long)tp.ctas * tp.nsw * 32 * cpr * 16 >= 48 * 1024;
 }
 
@@ -969,7 +984,7 @@ int kvc_slab_compress(const kvc_shape* shape, int32_t n_layers, const kvc_layer_
         }
         if (n_active == 0) continue;
         bd.idx_cap = (max_ksel + 3) & ~3;
-        TmaPlan tp = plan_tma(dt, cpr, max_region, bd.idx_cap, any_select, /*light_traffic=*/true);
+        TmaPlan tp = plan_tma(dt, cpr, max_region, bd.idx_cap, any_select, /*light_traffic=*/true, 0, 0, /*in_place=*/true);
         if (any_select && workspace != nullptr && !onchip_plan_ok(tp, cpr, true)) {
             const WsLayout w = ws_layout(dt, max_region, bd.idx_cap);
             if (w.unit * B * H * n_active > workspace_bytes) return KVC_ERR_INVALID_ARG;
