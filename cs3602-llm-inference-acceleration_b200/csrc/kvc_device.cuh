@@ -17,6 +17,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "kvc.h"
 
 namespace kvc {
@@ -439,6 +441,17 @@ __device__ __forceinline__ void snapkv_transform_rows4(typename Traits<DT>::Key*
 #pragma unroll
         for (int k = 0; k < 4; ++k) out[k] = score((uint32_t)r[k], i0 + k);
     };
+    // the same without the per-row range checks, for blocks that lie entirely inside [0, R)
+    auto load4_inside = [&](int i0, float (&out)[4]) {
+        Key r[4];
+        if (sizeof(Key) == 2)
+            *reinterpret_cast<uint2*>(r) = *reinterpret_cast<const uint2*>(keys + i0);
+        else
+            *reinterpret_cast<uint4*>(r) = *reinterpret_cast<const uint4*>(keys + i0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            out[k] = invert ? round_dt<DT>(mxe - Tr::from_raw((uint32_t)r[k])) : Tr::from_raw((uint32_t)r[k]);
+    };
     float left_edge[4], after[4], s[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -448,10 +461,18 @@ __device__ __forceinline__ void snapkv_transform_rows4(typename Traits<DT>::Key*
     }
     load4(w_lo + 4 * lane, s);
     __syncthreads();  // every warp holds its boundary rows before any segment is rewritten
-    for (int b0 = w_lo; b0 < w_hi; b0 += 128) {
+    // One 128-row block.  INSIDE (a compile-time switch, two instantiations of the body): the block AND the next one
+    // lie entirely inside [0, R), so no load, store or histogram update needs a range check — all but the last one or
+    // two blocks of a unit.  With the checks on every row the block cost 241 warp instructions, ~100 of them compares,
+    // branches and index arithmetic (profiles/r02_slab_ncu_full_c4.json).
+    auto block = [&](int b0, auto inside_tag) {
+        constexpr bool INSIDE = decltype(inside_tag)::value;
         float n[4];
         if (b0 + 128 < w_hi) {
-            load4(b0 + 128 + 4 * lane, n);
+            if (INSIDE)
+                load4_inside(b0 + 128 + 4 * lane, n);
+            else
+                load4(b0 + 128 + 4 * lane, n);
         } else {
 #pragma unroll
             for (int k = 0; k < 4; ++k) n[k] = after[k];
@@ -475,7 +496,7 @@ __device__ __forceinline__ void snapkv_transform_rows4(typename Traits<DT>::Key*
             for (int t = 0; t < PK; ++t) acc += win[4 + r + t - PAD];
             out[r] = ordered_key<Key>(Tr::to_raw(round_dt<DT>(acc / den)), /*descending=*/true);
         }
-        if (i0 + 4 <= R) {
+        if (INSIDE || i0 + 4 <= R) {
             if (sizeof(Key) == 2)
                 *reinterpret_cast<uint2*>(keys + i0) = *reinterpret_cast<const uint2*>(out);
             else
@@ -483,8 +504,8 @@ __device__ __forceinline__ void snapkv_transform_rows4(typename Traits<DT>::Key*
         }
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-            if (i0 + r < R) {
-                if (i0 + 4 > R) keys[i0 + r] = out[r];
+            if (INSIDE || i0 + r < R) {
+                if (!INSIDE && i0 + 4 > R) keys[i0 + r] = out[r];
                 atomicAdd(&hist[(uint32_t)out[r] >> kShift0], 1u);
             }
         }
@@ -493,7 +514,10 @@ __device__ __forceinline__ void snapkv_transform_rows4(typename Traits<DT>::Key*
             left_edge[k] = __shfl_sync(0xffffffffu, s[k], 31);
             s[k] = n[k];
         }
-    }
+    };
+    int b0 = w_lo;
+    for (; b0 + 256 <= R && b0 < w_hi; b0 += 128) block(b0, std::true_type{});
+    for (; b0 < w_hi; b0 += 128) block(b0, std::false_type{});
     __syncthreads();
 }
 
