@@ -772,3 +772,41 @@ def test_function_call_replays_from_a_cuda_graph(method, kw):
                 assert out[li][0] is kv[li][0]
                 continue
             assert torch.equal(out[li][0], want[li][0]) and torch.equal(out[li][1], want[li][1]), (method, step, li)
+
+
+def test_concurrent_calls_from_two_threads_on_their_own_streams():
+    """The library keeps no mutable state besides per-thread error text and a launch counter: two Python threads, each
+    on its own CUDA stream, compress their own caches at the same time and get what a serial call gets."""
+    import threading
+
+    L, B, H, S, D = 4, 2, 4, 700, 80
+    gen = torch.Generator(device="cuda").manual_seed(99)
+    caches = [[(torch.randn(B, H, S, D, generator=gen, device="cuda").bfloat16(),
+                torch.randn(B, H, S, D, generator=gen, device="cuda").bfloat16()) for _ in range(L)] for _ in range(2)]
+    calls = [("h2o_l2", dict(start_size=4, heavy_hitter_size=32, recent_size=92)),
+             ("snapkv_lite", dict(observation_window=16, keep_size=128))]
+    want = [kvcompress.get_compress_fn(m)(kv, **kw) for kv, (m, kw) in zip(caches, calls)]
+    torch.cuda.synchronize()
+    errors, results = [], [None, None]
+
+    def worker(i):
+        try:
+            stream = torch.cuda.Stream()
+            with torch.cuda.stream(stream):
+                m, kw = calls[i]
+                for _ in range(40):
+                    out = kvcompress.get_compress_fn(m)(caches[i], **kw)
+                stream.synchronize()
+            results[i] = out
+        except Exception as exc:  # surfaced below: an exception in a thread would otherwise be lost
+            errors.append(repr(exc))
+
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+    for i in range(2):
+        for li in range(L):
+            assert torch.equal(results[i][li][0], want[i][li][0]) and torch.equal(results[i][li][1], want[i][li][1]), (i, li)
