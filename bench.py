@@ -604,6 +604,37 @@ def time_calls(cfg, B, kv, steps, warmup, device, barrier=None, sampler=None, ba
     return total_ms, per_call, launches, vote_flops, wall_ms
 
 
+def time_in_place(cfg, B, kv, steps, device):
+    """The config's calls IN PLACE on a KVSlabCache holding the same rows (stored key norms instead of the K scan, kept
+    rows slide down inside the slab): per call the mean / min device time of `compress_` over `steps` runs.  A
+    prefill-sized compress is re-armed by rewinding the slab's lengths (timing does not depend on the values)."""
+    import torch
+
+    from kvcompress import KVSlabCache
+
+    S, rows = cfg["S"], []
+    per_call_bytes = call_bytes(cfg, B)
+    for i, (method, kw) in enumerate(cfg["calls"]):
+        run_kw = {k: v for k, v in kw.items() if not k.startswith("_")}
+        slab = KVSlabCache.from_legacy_cache(kv, capacity=S + 8)
+        ms = []
+        for step in range(steps + 2):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            slab.compress_(method, **run_kw)
+            b.record()
+            torch.cuda.synchronize()
+            slab.lengths = [S] * cfg["L"]
+            if step >= 2:
+                ms.append(a.elapsed_time(b))
+        rows.append({"call": method, "us_mean": round(statistics.mean(ms) * 1e3, 1), "us_min": round(min(ms) * 1e3, 1),
+                     "speedup_over_function": None,
+                     "effective_gbs": round(per_call_bytes[i] / (statistics.mean(ms) * 1e-3) / 1e9, 1)})
+        del slab
+        torch.cuda.empty_cache()
+    return rows
+
+
 def configs_table(args, device):
     """Every other BASELINE configuration on this GPU, a few timed steps each (driver-visible copies of the numbers
     DESIGN.md quotes).  Caches are generated and freed one config at a time."""
@@ -648,6 +679,17 @@ def configs_table(args, device):
             if B == 1:
                 entry["note"] = ("batch 1: the per-call rows time ONE call between two events on an idle GPU (launch latency "
                                  "included); the back_to_back row is the same calls queued without events")
+            if name in ("c2_steady", "c4", "c5"):  # the cache and a slab copy of it fit next to each other
+                try:
+                    entry["in_place"] = {"what": "the same calls as KVSlabCache.compress_ on a slab holding the same rows "
+                                                 "(scores from the stored key norms, kept rows slide down in place); "
+                                                 "effective_gbs = the function's algorithmic bytes / this time",
+                                         "per_call": time_in_place(cfg, B, kv, steps, device)}
+                    fn_us = {c["call"]: c["us_mean"] for c in per_call}
+                    for r in entry["in_place"]["per_call"]:
+                        r["speedup_over_function"] = round(fn_us[r["call"]] / r["us_mean"], 2) if r["call"] in fn_us else None
+                except Exception as exc:
+                    entry["in_place"] = {"error": repr(exc)[:300]}
         except Exception as exc:  # one config failing must not take the headline line with it
             entry = {"error": repr(exc)[:300]}
             kv, kv_key = None, None
