@@ -261,6 +261,26 @@ def test_pinned_slab_equals_device_slab_equals_functions(method, kwargs, dtype, 
             assert torch.equal(host[li][0].cuda(), dev[li][0]) and torch.equal(host.key_norms(li).cuda(), dev.key_norms(li))
 
 
+@pytest.mark.parametrize("S,keep_ratio", [(4000, 0.8), (2600, 0.79), (9000, 0.3)])
+def test_in_place_with_more_kept_rows_than_histogram_bins(S, keep_ratio):
+    """The in-place plan lets the kept-index list alias the (dead) 2048-bin histogram; selections that keep more rows
+    than that get their own list.  Both sides of the threshold (k_sel = 3200 / 2054 / 2700) against the function."""
+    L, B, H, D = 2, 2, 3, 80
+    gen = torch.Generator(device="cuda").manual_seed(S)
+    kv = [rand_rows(B, H, S, D, torch.float32, gen) for _ in range(L)]
+    kw = dict(keep_ratio=keep_ratio, prune_after=100, skip_layers=[])
+    want = kvcompress.l2_compress(kv, **kw)
+    slab = KVSlabCache.from_legacy_cache(kv, capacity=S + 4)
+    slab, idx = slab.compress_("l2_compress", return_indices=True, **kw)
+    fresh = KVSlabCache.from_legacy_cache(want, capacity=S + 4)   # the norms the append kernel records for the kept rows
+    for l in range(L):
+        assert slab.lengths[l] == want[l][0].size(2)
+        assert torch.equal(slab[l][0], want[l][0]) and torch.equal(slab[l][1], want[l][1])
+        rows = idx[l].long()
+        assert torch.all(rows[..., 1:] > rows[..., :-1])
+        assert torch.equal(slab.key_norms(l), fresh.key_norms(l))  # norms slid with their rows
+
+
 def test_chunked_prefill_evicts_in_place_like_the_function():
     """evict_for_space before every prefill chunk (reference streaming_llm.py:114-170), on the slab in place and with
     the function on plain (K, V) lists: the same cache after every chunk."""
