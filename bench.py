@@ -679,7 +679,7 @@ def configs_table(args, device):
             if B == 1:
                 entry["note"] = ("batch 1: the per-call rows time ONE call between two events on an idle GPU (launch latency "
                                  "included); the back_to_back row is the same calls queued without events")
-            if name in ("c2_steady", "c4", "c5"):  # the cache and a slab copy of it fit next to each other
+            if name in ("c2_steady", "c2_steady_b1", "c4", "c5"):  # the cache and a slab copy of it fit next to each other
                 try:
                     entry["in_place"] = {"what": "the same calls as KVSlabCache.compress_ on a slab holding the same rows "
                                                  "(scores from the stored key norms, kept rows slide down in place); "
