@@ -99,6 +99,15 @@ def h2o_attention_compress(past_key_values, attention_scores=None, h2o_manager: 
     if h2o_manager is None:
         return execute(layers, plans)
 
+    plans, given = manager_plans(layers, plans, h2o_manager, heavy_hitter_size)
+    return execute(layers, plans, given_indices=given)
+
+
+def manager_plans(layers, plans, h2o_manager: H2OAttentionManager, heavy_hitter_size: int):
+    """Rewrite the h2o plans with the manager's heavy hitters (reference h2o_attention.py:318-331): per compressed
+    layer the head-summed top-k rows become caller-supplied rows of the gather (``SCORE_GIVEN_INDEX``).  Returns
+    (plans, {layer: int32 [B, H, count] absolute rows, ascending}).  Shared by the function and by
+    ``KVSlabCache.compress_("h2o_attention", h2o_manager=...)``."""
     plans = list(plans)  # the manager rewrites per-layer plans below: never touch the cached set
     given = {}
     for li, plan in enumerate(plans):
@@ -118,7 +127,7 @@ def h2o_attention_compress(past_key_values, attention_scores=None, h2o_manager: 
                                        score=_planner.SCORE_GIVEN_INDEX if count > 0 else _planner.SCORE_NONE)
         if count > 0:
             given[li] = rows.to(torch.int32).view(1, 1, count).expand(batch, heads, count).contiguous()
-    return execute(layers, plans, given_indices=given)
+    return plans, given
 
 
 def create_h2o_manager_from_model(model, **kwargs) -> H2OAttentionManager:
@@ -135,4 +144,4 @@ def create_h2o_manager_from_model(model, **kwargs) -> H2OAttentionManager:
     )
 
 
-__all__ = ["H2OAttentionManager", "h2o_attention_compress", "create_h2o_manager_from_model"]
+__all__ = ["H2OAttentionManager", "h2o_attention_compress", "create_h2o_manager_from_model", "manager_plans"]

@@ -372,6 +372,8 @@ class KVSlabCache:
     def compress_(self, method: str, return_indices: bool = False, **kwargs):
         """``cache = to_dynamic_cache(get_compress_fn(method)(normalize_kv_cache(cache), **kwargs))`` in place:
         one launch for every layer, no allocation, scores from the stored key norms."""
+        if method == "h2o_attention":
+            return self._compress_h2o_attention(return_indices=return_indices, **kwargs)
         plans = self.plans_for(method, **kwargs)
         given = None
         if method == "fix_size_l2" and kwargs.get("strategy") == "random":
@@ -379,6 +381,27 @@ class KVSlabCache:
 
             given = {li: _random_indices(self[li][0], p.sel_hi, p.k_sel)
                      for li, p in enumerate(plans) if p.kind == P.GATHER and p.score == P.SCORE_GIVEN_INDEX}
+        return self.apply_plans_(plans, given_indices=given, return_indices=return_indices)
+
+    def _compress_h2o_attention(self, attention_scores=None, h2o_manager=None, start_size: int = 4,
+                                heavy_hitter_size: int = 64, recent_size: int = 444, skip_layers: Sequence[int] = (),
+                                return_indices: bool = False, **_ignored):
+        """``h2o_attention_compress`` in place (reference h2o_attention.py:216-363): without a manager it is exactly
+        ``h2o_l2`` (:337-351); with one, its head-summed heavy hitters are the caller-supplied rows of the in-place
+        compaction (they must ascend strictly — the manager sorts them, a clamp collision is refused)."""
+        from .methods._common import cached_plans
+        from .methods.h2o_attention import manager_plans
+
+        if h2o_manager is None:
+            return self.compress_("h2o_l2", return_indices=return_indices, start_size=start_size,
+                                  heavy_hitter_size=heavy_hitter_size, recent_size=recent_size, skip_layers=skip_layers)
+        if attention_scores is not None:
+            h2o_manager.update_attention_scores(attention_scores, list(skip_layers))
+        plans = cached_plans(P.plan_h2o, self.lengths, start_size, heavy_hitter_size, recent_size, skip_layers=skip_layers)
+        plans, given = manager_plans(self.to_legacy_cache(), plans, h2o_manager, heavy_hitter_size)
+        for li, rows in given.items():
+            if rows.size(-1) > 1 and not bool((rows[0, 0, 1:] > rows[0, 0, :-1]).all()):
+                raise ValueError(f"layer {li}: the manager's rows must ascend strictly for the in-place compaction")
         return self.apply_plans_(plans, given_indices=given, return_indices=return_indices)
 
     def evict_for_space_(self, num_coming: int, start_size: int = 4, recent_size: int = 508,

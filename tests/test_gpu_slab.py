@@ -281,6 +281,49 @@ def test_in_place_with_more_kept_rows_than_histogram_bins(S, keep_ratio):
         assert torch.equal(slab.key_norms(l), fresh.key_norms(l))  # norms slid with their rows
 
 
+def test_h2o_attention_manager_in_place_matches_the_reference_rows():
+    """``compress_("h2o_attention", h2o_manager=...)``: the manager's heavy hitters as caller-supplied rows of the
+    in-place compaction, against the rows the REAL reference kept (tests/golden/extras_golden.json) and against
+    the function; without a manager it is h2o_l2."""
+    import json
+    import os
+
+    import cases
+    import extras_cases as E
+
+    want = json.load(open(os.path.join(os.path.dirname(cases.GOLDEN_NPZ), "extras_golden.json")))
+    c = E.H2O_CASE
+    kw = dict(start_size=c["start_size"], heavy_hitter_size=c["heavy_hitter_size"], recent_size=c["recent_size"],
+              skip_layers=c["skip_layers"])
+
+    def manager():
+        return kvcompress.H2OAttentionManager(start_size=c["start_size"], heavy_hitter_size=c["heavy_hitter_size"],
+                                              recent_size=c["recent_size"], num_layers=c["layers"], num_heads=c["heads"],
+                                              decay_factor=c["decay_factor"])
+
+    m_fn, m_slab = manager(), manager()
+    for step, ref in enumerate(want["h2o"]):
+        kv, attn = E.h2o_inputs(step, ref["seq_len"])
+        kv = [(k.cuda(), v.cuda()) for k, v in kv]
+        attn = [a.cuda() for a in attn]
+        out = kvcompress.h2o_attention_compress(kv, attention_scores=attn, h2o_manager=m_fn, **kw)
+        slab = KVSlabCache.from_legacy_cache(kv, capacity=ref["seq_len"] + 4)
+        n0 = _engine.launch_count()
+        slab.compress_("h2o_attention", attention_scores=attn, h2o_manager=m_slab, **kw)
+        assert _engine.launch_count() - n0 <= 1
+        assert slab.lengths == ref["lengths"], step
+        for l in range(len(kv)):
+            assert slab[l][1][0, :, :, 0].long().tolist() == ref["rows"][l], (step, l)   # V carries the row positions
+            assert torch.equal(slab[l][0], out[l][0]) and torch.equal(slab[l][1], out[l][1]), (step, l)
+    # no manager: the h2o_l2 selection (reference h2o_attention.py:337-351)
+    gen = torch.Generator(device="cuda").manual_seed(8)
+    kv = [rand_rows(2, 3, 300, 80, torch.bfloat16, gen) for _ in range(2)]
+    a = KVSlabCache.from_legacy_cache(kv, capacity=304).compress_("h2o_attention", start_size=4, heavy_hitter_size=16, recent_size=44)
+    b = KVSlabCache.from_legacy_cache(kv, capacity=304).compress_("h2o_l2", start_size=4, heavy_hitter_size=16, recent_size=44)
+    for l in range(2):
+        assert torch.equal(a[l][0], b[l][0]) and torch.equal(a[l][1], b[l][1])
+
+
 def test_chunked_prefill_evicts_in_place_like_the_function():
     """evict_for_space before every prefill chunk (reference streaming_llm.py:114-170), on the slab in place and with
     the function on plain (K, V) lists: the same cache after every chunk."""
