@@ -931,9 +931,11 @@ int kvc_slab_compress(const kvc_shape* shape, int32_t n_layers, const kvc_layer_
         if (p.k_sel > 0) {
             if (p.sel_lo < p.sink || p.sel_hi > p.seq_len - p.tail || p.sel_lo > p.sel_hi) return KVC_ERR_INVALID_ARG;
             if (p.k_sel > p.sel_hi - p.sel_lo) return KVC_ERR_INVALID_ARG;
-            if (p.score <= KVC_SCORE_NONE || p.score > KVC_SCORE_GIVEN_INDEX) return KVC_ERR_INVALID_ARG;
-            if (p.score == KVC_SCORE_GIVEN_INDEX && (!idx_in || !idx_in[l])) return KVC_ERR_INVALID_ARG;
-            if (p.score == KVC_SCORE_SNAPKV_POOL && p.pool_kernel > 2 * kMaxPoolHalo) return KVC_ERR_UNSUPPORTED;
+            if (p.score <= KVC_SCORE_NONE || p.score > KVC_SCORE_GIVEN_SCORE) return KVC_ERR_INVALID_ARG;
+            if ((p.score == KVC_SCORE_GIVEN_INDEX || p.score == KVC_SCORE_GIVEN_SCORE) && (!idx_in || !idx_in[l]))
+                return KVC_ERR_INVALID_ARG;
+            if ((p.score == KVC_SCORE_SNAPKV_POOL || p.score == KVC_SCORE_GIVEN_SCORE) && p.pool_kernel > 2 * kMaxPoolHalo)
+                return KVC_ERR_UNSUPPORTED;
         }
         if (p.sink + p.k_sel + p.tail == 0) continue;
         if (!sl.k || !sl.v || !sl.norms) return KVC_ERR_INVALID_ARG;

@@ -374,6 +374,8 @@ class KVSlabCache:
         one launch for every layer, no allocation, scores from the stored key norms."""
         if method == "h2o_attention":
             return self._compress_h2o_attention(return_indices=return_indices, **kwargs)
+        if method == "snapkv_lite" and kwargs.get("obs_queries") is not None:
+            return self._compress_snapkv_vote(return_indices=return_indices, **kwargs)
         plans = self.plans_for(method, **kwargs)
         given = None
         if method == "fix_size_l2" and kwargs.get("strategy") == "random":
@@ -382,6 +384,30 @@ class KVSlabCache:
             given = {li: _random_indices(self[li][0], p.sel_hi, p.k_sel)
                      for li, p in enumerate(plans) if p.kind == P.GATHER and p.score == P.SCORE_GIVEN_INDEX}
         return self.apply_plans_(plans, given_indices=given, return_indices=return_indices)
+
+    def _compress_snapkv_vote(self, obs_queries, obs_lse=None, return_indices: bool = False, **kwargs):
+        """snapkv_lite in vote mode, in place: the tcgen05 q.K^T vote over the slab's keys (one launch), then pool ->
+        top-k -> slide inside the slab with the votes as caller-supplied scores (one launch).  Keeps the rows
+        ``snapkv_lite_compress(cache, obs_queries=...)`` keeps."""
+        from dataclasses import replace
+
+        if self.pinned:
+            raise RuntimeError("the q.K^T vote reads the keys through TMA tensor maps: device-resident slabs only")
+        plans = self.plans_for("snapkv_lite", **kwargs)
+        if len(obs_queries) != self.num_layers:
+            raise ValueError(f"obs_queries: {len(obs_queries)} entries for {self.num_layers} layers")
+        window = kwargs.get("observation_window", _method_defaults("snapkv_lite")["observation_window"])
+        voted = [li for li, p in enumerate(plans) if p.kind == P.GATHER and p.k_sel > 0]
+        for li in voted:
+            if obs_queries[li] is None:
+                raise ValueError(f"obs_queries[{li}] is missing for a layer that is compressed")
+        scores = {}
+        if voted:
+            votes = _engine.snapkv_votes([(self[li][0], obs_queries[li]) for li in voted], window,
+                                         lse=None if obs_lse is None else [obs_lse[li] for li in voted])
+            scores = dict(zip(voted, votes))
+        new_plans = [replace(p, score=P.SCORE_GIVEN_SCORE) if li in scores else p for li, p in enumerate(plans)]
+        return self.apply_plans_(new_plans, given_scores=scores, return_indices=return_indices)
 
     def _compress_h2o_attention(self, attention_scores=None, h2o_manager=None, start_size: int = 4,
                                 heavy_hitter_size: int = 64, recent_size: int = 444, skip_layers: Sequence[int] = (),
@@ -414,7 +440,8 @@ class KVSlabCache:
                              skip_layers=skip_layers)
         return self.apply_plans_(plans, return_indices=return_indices)
 
-    def apply_plans_(self, plans, given_indices: Optional[dict] = None, return_indices: bool = False):
+    def apply_plans_(self, plans, given_indices: Optional[dict] = None, return_indices: bool = False,
+                     given_scores: Optional[dict] = None):
         ps = plans if isinstance(plans, _engine.PlanSet) else _engine.PlanSet(plans)
         if len(ps) != self.num_layers:
             raise ValueError(f"{len(ps)} plans for {self.num_layers} layers")
@@ -450,10 +477,20 @@ class KVSlabCache:
                 indices[i] = t
                 ptrs[m] = t.data_ptr()
             idx_out = ptrs
-        if given_indices:
+        if given_indices or given_scores:
             ptrs = (ctypes.c_void_p * len(ids))()
             for m, i in enumerate(ids):
-                gi = given_indices.get(i)
+                gs = given_scores.get(i) if given_scores else None
+                if gs is not None:  # SCORE_GIVEN_SCORE: the region's scores travel in the idx_in slot (kvc.h)
+                    region = ps.plans[i].sel_hi - ps.plans[i].sel_lo
+                    if gs.dtype != self.dtype or not gs.is_contiguous() or gs.device != self.device \
+                            or tuple(gs.shape) != (self.batch, self.heads, region):
+                        raise ValueError(f"layer {i}: scores must be a contiguous {self.dtype} [B, H, {region}] tensor "
+                                         f"on {self.device}")
+                    keep.append(gs)
+                    ptrs[m] = gs.data_ptr()
+                    continue
+                gi = given_indices.get(i) if given_indices else None
                 if gi is not None:
                     if gi.device.type == "cpu" and self.pinned:
                         gi = gi.contiguous().pin_memory()  # drawn on the host for a host-resident slab

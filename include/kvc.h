@@ -227,7 +227,9 @@ int kvc_slab_append(const kvc_shape* shape, int32_t n_layers, const kvc_slab_lay
 /* Compact n_layers slabs in place in one launch.  plans[l].seq_len = rows currently valid.
  * idx_out[l] (optional, may be NULL / hold NULLs): [B,H,C] kept absolute rows; idx_in[l]: GIVEN_INDEX rows, which
  * must be STRICTLY ASCENDING inside [sel_lo, sel_hi) per (b,h): kept rows only ever move towards row 0, which is what
- * makes the compaction safe in place (values outside [0, seq_len) are clamped, never dereferenced). */
+ * makes the compaction safe in place (values outside [0, seq_len) are clamped, never dereferenced).
+ * KVC_SCORE_GIVEN_SCORE: idx_in[l] carries, instead, the [B,H,sel_hi-sel_lo] scores of the region's rows (cache dtype,
+ * dense; e.g. kvc_snapkv_vote's output) — pooled with plans[l].pool_kernel, the k_sel highest kept. */
 int kvc_slab_compress(const kvc_shape* shape, int32_t n_layers, const kvc_layer_plan* plans,
                       const kvc_slab_layer* slabs, int32_t* const* idx_out, const int32_t* const* idx_in,
                       void* workspace, int64_t workspace_bytes, void* stream);

@@ -220,3 +220,32 @@ def test_vote_errors():
         _engine.snapkv_votes([(k.bfloat16(), torch.randn(1, 16, 32, 128, device="cuda").bfloat16())], 32)
     with pytest.raises(ValueError, match="obs_queries"):
         kvcompress.snapkv_lite_compress([(k.bfloat16(), k.bfloat16())], obs_queries=[])
+
+
+def test_vote_mode_in_place_on_a_slab_keeps_the_rows_of_the_function():
+    """``KVSlabCache.compress_("snapkv_lite", obs_queries=...)``: vote launch + in-place compaction with the votes as
+    caller-supplied scores (``KVC_SCORE_GIVEN_SCORE`` in ``kvc_slab_compress``) against the fused function call."""
+    from kvcompress import KVSlabCache
+
+    torch.manual_seed(5)
+    L, B, H, G, W, S, D, keep = 3, 2, 2, 4, 32, 1500, 128, 256
+    kv = [(torch.randn(B, H, S, D, device="cuda").bfloat16(), torch.randn(B, H, S, D, device="cuda").bfloat16())
+          for _ in range(L)]
+    qs = [(2.0 * torch.randn(B, H * G, W, D, device="cuda")).bfloat16() for _ in range(L)]
+    for pk, skip in ((5, []), (4, [1]), (1, [])):
+        kw = dict(observation_window=W, keep_size=keep, pooling_kernel=pk, skip_layers=skip)
+        want = kvcompress.snapkv_lite_compress(kv, obs_queries=qs, **kw)
+        slab = KVSlabCache.from_legacy_cache(kv, capacity=S + 8)
+        n0 = _engine.launch_count()
+        slab.compress_("snapkv_lite", obs_queries=qs, **kw)
+        assert _engine.launch_count() - n0 == 2          # the vote, then the in-place select + slide
+        assert slab.lengths == [k.size(2) for k, _ in want]
+        for li in range(L):
+            assert torch.equal(slab[li][0], want[li][0]) and torch.equal(slab[li][1], want[li][1]), (pk, li)
+    # single pass with the caller's log-sum-exp
+    lse = [lse_reference(k, q, W) for (k, _), q in zip(kv, qs)]
+    want = kvcompress.snapkv_lite_compress(kv, obs_queries=qs, obs_lse=lse, observation_window=W, keep_size=keep)
+    slab = KVSlabCache.from_legacy_cache(kv, capacity=S + 8)
+    slab.compress_("snapkv_lite", obs_queries=qs, obs_lse=lse, observation_window=W, keep_size=keep)
+    for li in range(L):
+        assert torch.equal(slab[li][0], want[li][0]) and torch.equal(slab[li][1], want[li][1])
